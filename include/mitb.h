@@ -1,0 +1,107 @@
+/* libmitb -- C ABI of the B200-native detect -> OCR -> inpaint hot path.
+ *
+ * Drop-in boundary for manga-image-translator's three dense-inference plugins.  Every entry point replaces the
+ * torch call made by the reference at the cited line (paths relative to manga_translator/):
+ *
+ *   mitb_dbnet_forward[_u8]  <- det_batch_forward_default: MODEL(batch); db.sigmoid()   detection/dbnet_convnext.py:499-509
+ *   mitb_ocr_forward[_u8]    <- OCR.decode up to the host loop: backbone, encoders, heads,
+ *                               log_softmax + max, colour clamp                           ocr/model_48px_ctc.py:447-463
+ *   mitb_lama_forward        <- LamaFourier.__call__ (inpaint_only): MPE embed, generator,
+ *                               pred*mask+(1-mask)*img                                    inpainting/inpainting_lama_mpe.py:713-726
+ *   mitb_*_load / _unload    <- the plugins' _load/_unload (torch.load + load_state_dict)  dbnet_convnext.py:527-539,
+ *                               model_48px_ctc.py:38-60, inpainting_lama_mpe.py:46-51,131-136,818-825
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Every function returns 0 on success, non-zero on
+ * failure with the message available from mitb_last_error().  All data pointers are DEVICE pointers on the
+ * context's GPU (fp32 NCHW like the reference tensors) unless the name says _u8/host; `stream` is a cudaStream_t
+ * (NULL = default stream) and calls are asynchronous on it.  A context is bound to one GPU and is not re-entrant.
+ * There is no CPU fallback: without a CUDA device mitb_create fails.
+ */
+#ifndef MITB_H
+#define MITB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mitb_ctx mitb_ctx;
+
+/* One named fp32 tensor of a PyTorch state_dict, resident on the device (contiguous, row-major). */
+typedef struct {
+  const char* name;      /* state_dict key, e.g. "backbone.stem.0.weight" */
+  const float* data;     /* device pointer */
+  int32_t ndim;          /* 0..4 */
+  int64_t shape[4];
+} mitb_tensor;
+
+int mitb_create(int device_ordinal, mitb_ctx** out);
+void mitb_destroy(mitb_ctx* ctx);
+const char* mitb_last_error(const mitb_ctx* ctx);      /* valid until the next call on ctx; ctx may be NULL */
+const char* mitb_version(void);
+long long mitb_launch_count(const mitb_ctx* ctx);      /* kernels launched by this context so far */
+size_t mitb_workspace_bytes(const mitb_ctx* ctx);      /* current activation workspace size */
+
+/* ---- DBNet-ConvNeXt text detector (state_dict keys of DBNetConvNext, dbnet_convnext.py:450-472) ---- */
+int mitb_dbnet_load(mitb_ctx* ctx, const mitb_tensor* weights, int n_weights);
+int mitb_dbnet_unload(mitb_ctx* ctx);
+/* x: [n,3,h,w] already normalised (u8/127.5-1), h and w multiples of 256.
+ * db: [n,2,h,w] = sigmoid(DBHead output) (channel 1 is sigmoid applied twice, as the reference does);
+ * mask: [n,1,h/2,w/2]. */
+int mitb_dbnet_forward(mitb_ctx* ctx, const float* x, int n, int h, int w, float* db, float* mask, void* stream);
+/* Same, input uint8 NHWC [n,h,w,3] on the device; the u8/127.5-1 normalisation is fused into the first kernel. */
+int mitb_dbnet_forward_u8(mitb_ctx* ctx, const uint8_t* img, int n, int h, int w, float* db, float* mask, void* stream);
+
+/* ---- 48px ResNet+Transformer CTC recogniser (state_dict keys of OCR, model_48px_ctc.py:425-436) ---- */
+int mitb_ocr_load(mitb_ctx* ctx, const mitb_tensor* weights, int n_weights);
+int mitb_ocr_unload(mitb_ctx* ctx);
+int mitb_ocr_timesteps(int wp);                         /* T = floor(floor(wp/2)/2) - 1 */
+/* x: [n,3,48,wp] normalised ((u8-127.5)/127.5).  Outputs per timestep, T = mitb_ocr_timesteps(wp):
+ * argmax [n,T] int32, logprob [n,T] (log-softmax value at the argmax), colors [n,T,6] clamped to [0,1].
+ * The [n,T,V] logits are never materialised. */
+int mitb_ocr_forward(mitb_ctx* ctx, const float* x, int n, int wp, int32_t* argmax, float* logprob, float* colors,
+                     void* stream);
+int mitb_ocr_forward_u8(mitb_ctx* ctx, const uint8_t* img /*[n,48,wp,3]*/, int n, int wp, int32_t* argmax,
+                        float* logprob, float* colors, void* stream);
+
+/* ---- LaMa FFC inpainter, MPE (9 blocks + str_state_dict) or large (18 blocks) ----
+ * weights: generator keys "model.*" plus, for MPE, "mpe.rel_pos_emb.weight", "mpe.direct_emb.weight",
+ * "mpe.alpha5", "mpe.alpha6" (the str_state_dict keys prefixed with "mpe."). */
+int mitb_lama_load(mitb_ctx* ctx, const mitb_tensor* weights, int n_weights);
+int mitb_lama_unload(mitb_ctx* ctx);
+/* img [n,3,h,w] in [0,1] (pre-masked or not: the generator multiplies by 1-mask itself), mask [n,1,h,w] in {0,1},
+ * h and w multiples of 8; rel_pos int32 [n,h,w] in [0,127] and direct int32 [n,h,w,4] in {0,1} are the MPE tables
+ * (NULL for the large model); out [n,3,h,w] = pred*mask + (1-mask)*img. */
+int mitb_lama_forward(mitb_ctx* ctx, const float* img, const float* mask, const int32_t* rel_pos,
+                      const int32_t* direct, int n, int h, int w, float* out, void* stream);
+
+/* ---- standalone operators (parity tests and micro-benchmarks; same kernels the networks use) ---- */
+/* General conv through the implicit-GEMM kernel.  x [n,cin,h,w], wt PyTorch layout [cout,cin,kh,kw], y [n,cout,ho,wo]
+ * (all NCHW device fp32).  pad_mode 0 zero / 1 reflect; act 0 none,1 relu,2 gelu(erf),3 silu,4 sigmoid.
+ * bias / in_scale / in_shift may be NULL; in_relu applies relu(x*in_scale+in_shift) before the conv. */
+int mitb_op_conv2d(mitb_ctx* ctx, const float* x, int n, int cin, int h, int w, const float* wt, int cout, int kh,
+                   int kw, int stride_y, int stride_x, int pad_y, int pad_x, int pad_mode, const float* bias, int act,
+                   const float* in_scale, const float* in_shift, int in_relu, float* y, void* stream);
+/* ConvTranspose2d, stride 2: (k=2,p=0,op=0), (k=4,p=1,op=0) or (k=3,p=1,op=1).  wt [cin,cout,k,k]. */
+int mitb_op_conv_transpose2d(mitb_ctx* ctx, const float* x, int n, int cin, int h, int w, const float* wt, int cout,
+                             int k, int pad, int out_pad, const float* bias, int act, float* y, void* stream);
+/* depthwise 7x7 (pad 3, bias) + LayerNorm over C (eps), NCHW in/out. */
+int mitb_op_dwconv7_ln(mitb_ctx* ctx, const float* x, int n, int c, int h, int w, const float* wdw, const float* bdw,
+                       const float* lnw, const float* lnb, float eps, float* y, void* stream);
+/* LayerNorm over the last dim of [rows, c]. */
+int mitb_op_layernorm(mitb_ctx* ctx, const float* x, int rows, int c, const float* w, const float* b, float eps,
+                      float* y, void* stream);
+/* torch.fft.rfftn / irfftn over (h,w), norm='ortho', planar [c,h,w] <-> [2c,h,w/2+1] (re/im interleaved per channel). */
+int mitb_op_rfft2(mitb_ctx* ctx, const float* x, int c, int h, int w, float* spec, void* stream);
+int mitb_op_irfft2(mitb_ctx* ctx, const float* spec, int c, int h, int w, float* y, void* stream);
+/* Multi-head attention core: qk [n*t, 2*d] (q then k, already projected), v [n*t, d] -> out [n*t, d]. */
+int mitb_op_attention(mitb_ctx* ctx, const float* qk, const float* v, int n, int t, int heads, int head_dim,
+                      float* out, void* stream);
+/* cv2.bilateralFilter(img, 17, 80, 80) on a uint8 HWC3 device image (detector pre-filter, dbnet_convnext.py:549). */
+int mitb_op_bilateral17(mitb_ctx* ctx, const uint8_t* img, int h, int w, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MITB_H */

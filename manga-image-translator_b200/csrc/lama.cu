@@ -1,0 +1,161 @@
+// LaMa FFC generator forward, MPE (9 blocks + masked positional encoding) or large (18 blocks).
+// Reference: inpainting/inpainting_lama_mpe.py:187-436 (FourierUnit / SpectralTransform / FFC / FFC_BN_ACT / FFCResnetBlock),
+// :545-613 (FFCResNetGenerator), :616-632 (MPE), :713-726 (LamaFourier.__call__).
+//
+// Data layout: the bottleneck tensor is ONE NHWC buffer of 512 channels = [local 128 | global 384]; the three spatial 3x3
+// convs of an FFC layer become two implicit GEMMs over channel slices (l2l+g2l share one accumulation over all 512 input
+// channels).  The spectral branch runs planar (NCHW): 1x1 conv+BN+ReLU -> rfft2 -> 1x1 spectral conv+BN+ReLU -> irfft2
+// (+residual) -> 1x1 conv whose epilogue adds the l2g branch, applies BN_g + ReLU and the block residual.
+#include <math.h>
+#include "exec.h"
+
+namespace mitb {
+
+static const float kBnEps = 1e-5f;
+
+struct FfcLayer {                      // one FFC_BN_ACT of a res-block
+  ConvW to_l;                          // [l2l ; g2l] over 512 input channels -> 128, epilogue bn_l + relu
+  ConvW l2g;                           // 128 -> 384 raw
+  ConvW sp1;                           // 1x1 384 -> 192, bn + relu (planar out)
+  ConvW fu;                            // 1x1 384 -> 384 on the spectrum, bn + relu (planar in/out)
+  ConvW sp2;                           // 1x1 192 -> 384, epilogue (+l2g) bn_g relu
+};
+struct UpLayer { ConvW ph[4]; };
+
+struct LamaModel {
+  DevBlob blob;
+  int n_blocks = 0; bool use_mpe = false;
+  ConvW stem, d1, d2, d3l, d3g;
+  std::vector<FfcLayer> layers;        // 2 per block
+  UpLayer up[3];
+  ConvW outc;
+  const float* mpe_table = nullptr; const float* mpe_dirw = nullptr; float a5 = 0.f, a6 = 0.f;
+};
+
+static void fold_bias_bn(Loader& L, const std::string& bias, const std::string& bn, const float** scale, const float** shift, int C) {
+  const float *s = nullptr, *b = nullptr;
+  L.bn_fold(bn, kBnEps, &s, &b);
+  std::vector<float> hs(C), hb(C), bi(C);
+  CUDA_OK(cudaMemcpy(hs.data(), s, C * sizeof(float), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(hb.data(), b, C * sizeof(float), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(bi.data(), L.W.get(bias).data, C * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < C; ++i) hb[i] = (float)((double)bi[i] * (double)hs[i] + (double)hb[i]);
+  float* d = L.blob.alloc_f(C + 4);
+  CUDA_OK(cudaMemcpy(d, hb.data(), C * sizeof(float), cudaMemcpyHostToDevice));
+  *scale = s; *shift = d;
+}
+
+LamaModel* lama_build(Ctx& ctx, const Weights& W) {
+  LamaModel* m = new LamaModel();
+  try {
+    Loader L{W, m->blob, 0};
+    while (W.has("model." + std::to_string(5 + m->n_blocks) + ".conv1.ffc.convl2l.weight")) ++m->n_blocks;
+    MITB_CHECK(m->n_blocks > 0, "lama: no FFC res-blocks found in the state_dict");
+    m->stem = L.conv("model.1.ffc.convl2l.weight", 3, 3); L.bn_fold("model.1.bn_l.", kBnEps, &m->stem.scale, &m->stem.shift);
+    m->d1 = L.conv("model.2.ffc.convl2l.weight", 1, 1); L.bn_fold("model.2.bn_l.", kBnEps, &m->d1.scale, &m->d1.shift);
+    m->d2 = L.conv("model.3.ffc.convl2l.weight", 1, 1); L.bn_fold("model.3.bn_l.", kBnEps, &m->d2.scale, &m->d2.shift);
+    m->d3l = L.conv("model.4.ffc.convl2l.weight", 1, 1); L.bn_fold("model.4.bn_l.", kBnEps, &m->d3l.scale, &m->d3l.shift);
+    m->d3g = L.conv("model.4.ffc.convl2g.weight", 1, 1); L.bn_fold("model.4.bn_g.", kBnEps, &m->d3g.scale, &m->d3g.shift);
+    for (int b = 0; b < m->n_blocks; ++b)
+      for (int c = 0; c < 2; ++c) {
+        const std::string p = "model." + std::to_string(5 + b) + (c == 0 ? ".conv1." : ".conv2.");
+        const std::string f = p + "ffc.";
+        FfcLayer l;
+        l.to_l = L.conv_cat_cin({f + "convl2l.weight", f + "convg2l.weight"}, 1, 1);
+        L.bn_fold(p + "bn_l.", kBnEps, &l.to_l.scale, &l.to_l.shift);
+        l.l2g = L.conv(f + "convl2g.weight", 1, 1);
+        l.sp1 = L.conv(f + "convg2g.conv1.0.weight", 0, 0); L.bn_fold(f + "convg2g.conv1.1.", kBnEps, &l.sp1.scale, &l.sp1.shift);
+        l.fu = L.conv(f + "convg2g.fu.conv_layer.weight", 0, 0); L.bn_fold(f + "convg2g.fu.bn.", kBnEps, &l.fu.scale, &l.fu.shift);
+        l.sp2 = L.conv(f + "convg2g.conv2.weight", 0, 0); L.bn_fold(p + "bn_g.", kBnEps, &l.sp2.scale, &l.sp2.shift);
+        m->layers.push_back(l);
+      }
+    int k = 5 + m->n_blocks + 1;
+    const int ups[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      const std::string wn = "model." + std::to_string(k) + ".weight";
+      const float *s = nullptr, *sh = nullptr;
+      fold_bias_bn(L, "model." + std::to_string(k) + ".bias", "model." + std::to_string(k + 1) + ".", &s, &sh, ups[i]);
+      for (int ph = 0; ph < 4; ++ph) { m->up[i].ph[ph] = L.convT_phase(wn, 3, 1, ph >> 1, ph & 1); m->up[i].ph[ph].scale = s; m->up[i].ph[ph].shift = sh; }
+      k += 3;
+    }
+    m->outc = L.conv("model." + std::to_string(k + 1) + ".weight", 3, 3); m->outc.shift = L.vec("model." + std::to_string(k + 1) + ".bias");
+    if (W.has("mpe.rel_pos_emb.weight")) {
+      m->use_mpe = true;
+      m->mpe_table = L.vec("mpe.rel_pos_emb.weight"); m->mpe_dirw = L.vec("mpe.direct_emb.weight");
+      m->a5 = L.scalar("mpe.alpha5"); m->a6 = L.scalar("mpe.alpha6");
+    }
+    CUDA_OK(cudaDeviceSynchronize());
+  } catch (...) { delete m; throw; }
+  return m;
+}
+
+void lama_free(LamaModel* m) { delete m; }
+
+// One FFC_BN_ACT on the 512-channel bottleneck (inpainting_lama_mpe.py:349-369, 394-399).
+// X -> Y ; `res` (optional) is the block input added after the activation (FFCResnetBlock, :432).
+void run_ffc_layer(Exec& e, const FfcLayer& l, const View& X, const View& Y, const View* res) {
+  Arena& ws = e.ws();
+  const size_t mk = ws.mark();
+  const int n = X.N, h = X.H, w = X.W, w2 = w / 2 + 1;
+  View Xl = X.slice(0, 128), Xg = X.slice(128, 384), Yl = Y.slice(0, 128), Yg = Y.slice(128, 384);
+  View G = ws.view(n, h, w, 384);
+  { ConvOp op = Exec::op_from(l.l2g, Xl, G, 1, PAD_REFLECT); op.scale = nullptr; op.shift = nullptr; e.conv(op); }
+  View S = ws.view(n, h, w, 192, true), SP = ws.view(n, h, w2, 384, true), FP = ws.view(n, h, w2, 384, true),
+       U = ws.view(n, h, w, 192, true);
+  float2* tmp = (float2*)ws.alloc((size_t)n * 192 * h * w2 * sizeof(float2));
+  { ConvOp op = Exec::op_from(l.sp1, Xg, S); op.act = ACT_RELU; e.conv(op); }
+  if (!e.dry) launch_rfft2(S, SP, tmp, e.st);
+  { ConvOp op = Exec::op_from(l.fu, SP, FP); op.act = ACT_RELU; e.conv(op); }
+  if (!e.dry) launch_irfft2(FP, U, &S, tmp, e.st);
+  {
+    ConvOp op = Exec::op_from(l.sp2, U, Yg); op.add0 = G; op.act = ACT_RELU;
+    if (res) op.add1 = res->slice(128, 384);
+    e.conv(op);
+  }
+  // local output last: it may overwrite X_l in place (its own residual is read element-wise by the same thread)
+  {
+    ConvOp op = Exec::op_from(l.to_l, X, Yl, 1, PAD_REFLECT); op.act = ACT_RELU;
+    if (res) op.add1 = res->slice(0, 128);
+    e.conv(op);
+  }
+  ws.release(mk);
+}
+
+void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const int* rel_pos, const int* direct, int n, int h,
+              int w, float* out, cudaStream_t st) {
+  MITB_CHECK(n >= 1 && h % 8 == 0 && w % 8 == 0 && h >= 32 && w >= 32, "lama: input %dx%d must be a multiple of 8 (>=32)", h, w);
+  MITB_CHECK(!m.use_mpe || (rel_pos && direct), "lama_mpe needs the rel_pos/direct tables");
+  run_with_workspace(ctx, st, [&](Exec& e) {
+    Arena& ws = e.ws();
+    const int h8 = h / 8, w8 = w / 8;
+    View X = ws.view(n, h8, w8, 512), Y = ws.view(n, h8, w8, 512), Z = ws.view(n, h8, w8, 512);
+    {
+      const size_t mk = ws.mark();
+      View x4 = ws.view(n, h, w, 4), s1 = ws.view(n, h, w, 64), s2 = ws.view(n, h / 2, w / 2, 128), s3 = ws.view(n, h / 4, w / 4, 256);
+      if (!e.dry) launch_lama_pack_input(img, mask, n, h, w, x4, st);
+      { ConvOp op = Exec::op_from(m.stem, x4, s1, 1, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
+      if (m.use_mpe && !e.dry) launch_mpe_add(s1, rel_pos, direct, m.mpe_table, m.mpe_dirw, m.a5, m.a6, st);
+      { ConvOp op = Exec::op_from(m.d1, s1, s2, 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
+      { ConvOp op = Exec::op_from(m.d2, s2, s3, 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
+      { ConvOp op = Exec::op_from(m.d3l, s3, X.slice(0, 128), 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
+      { ConvOp op = Exec::op_from(m.d3g, s3, X.slice(128, 384), 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
+      ws.release(mk);
+    }
+    // FFCResnetBlock x n (inpainting_lama_mpe.py:421-436): X -> Y -> Z (+X), then Z becomes the next X
+    for (int b = 0; b < m.n_blocks; ++b) {
+      run_ffc_layer(e, m.layers[2 * b], X, Y, nullptr);
+      run_ffc_layer(e, m.layers[2 * b + 1], Y, Z, &X);
+      View t = X; X = Z; Z = t;
+    }
+    // upsampling: 3 x [ConvTranspose2d(3,s2,p1,op1) + BN + ReLU], then ReflectionPad(3) + Conv7x7 + sigmoid
+    View u1 = ws.view(n, h / 4, w / 4, 256), u2 = ws.view(n, h / 2, w / 2, 128), u3 = ws.view(n, h, w, 64);
+    e.convT2(m.up[0].ph, X, u1, [](ConvOp& op) { op.act = ACT_RELU; });
+    e.convT2(m.up[1].ph, u1, u2, [](ConvOp& op) { op.act = ACT_RELU; });
+    e.convT2(m.up[2].ph, u2, u3, [](ConvOp& op) { op.act = ACT_RELU; });
+    View pred = ws.view(n, h, w, 3, true);
+    { ConvOp op = Exec::op_from(m.outc, u3, pred, 1, PAD_REFLECT); op.act = ACT_SIGMOID; e.conv(op); }
+    if (!e.dry) launch_lama_blend(pred, img, mask, out, st);
+  });
+}
+
+}  // namespace mitb

@@ -1,0 +1,184 @@
+// Internal declarations shared by the kernels and the network drivers of libmitb.
+// Layout convention: activations are NHWC fp32 "views" (a channel slice of a wider tensor), so channel
+// concatenation (DBNet skip connections, LaMa local|global halves) never costs a copy.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+#include "../../include/mitb.h"
+
+namespace mitb {
+
+// ------------------------------------------------------------------ errors
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+#define MITB_CHECK(cond, ...)                                                          \
+  do { if (!(cond)) { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__);              \
+       throw ::mitb::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + _b); } } while (0)
+#define CUDA_OK(expr)                                                                  \
+  do { cudaError_t _e = (expr); if (_e != cudaSuccess)                                 \
+       throw ::mitb::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " #expr ": " + \
+                           cudaGetErrorString(_e)); } while (0)
+
+// ------------------------------------------------------------------ tensor view
+struct View {              // NHWC slice: element (n,y,x,c) at p[((n*H+y)*W+x)*cs + coff + c]
+  float* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;   // C = channels in this view
+  int cs = 0, coff = 0;             // channel stride of the backing tensor, offset of this slice
+  bool planar = false;              // NCHW instead: element at p[((n*cs + coff + c)*H + y)*W + x]
+  View slice(int off, int c) const { View v = *this; v.coff = coff + off; v.C = c; return v; }
+  size_t pixels() const { return (size_t)N * H * W; }
+};
+
+// ------------------------------------------------------------------ bump arena with mark/release
+struct Arena {
+  char* base = nullptr; size_t cap = 0, off = 0, peak = 0; bool dry = false;
+  float* alloc_f(size_t n) { return (float*)alloc(n * sizeof(float)); }
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes; if (off > peak) peak = off;
+    if (dry) return (void*)(uintptr_t)(0x1000 + a);      // fake, never dereferenced
+    MITB_CHECK(off <= cap, "workspace overflow (%zu > %zu)", off, cap);
+    return base + a;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+  View view(int N, int H, int W, int C, bool planar = false) {
+    View v; v.p = alloc_f((size_t)N * H * W * C); v.N = N; v.H = H; v.W = W; v.C = C; v.cs = C; v.coff = 0;
+    v.planar = planar; return v;
+  }
+};
+
+// ------------------------------------------------------------------ conv op
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_SIGMOID2 = 5, ACT_CLAMP01 = 6 };
+enum Pad { PAD_ZERO = 0, PAD_REFLECT = 1 };
+constexpr int kMaxTaps = 49;
+
+struct ConvOp {
+  View in, out;                       // out grid may be larger than the logical (Ho,Wo) grid (transposed phases)
+  const float* w = nullptr;           // [ntaps*Cin][ldw] K-major rows, ldw = round4(Cout)
+  int ldw = 0, ntaps = 1;
+  int8_t tdy[kMaxTaps] = {0}, tdx[kMaxTaps] = {0};   // input offset of each tap relative to (oy*sy, ox*sx)
+  int sy = 1, sx = 1, pad = PAD_ZERO;
+  int Ho = 0, Wo = 0;                 // logical output grid of this launch
+  int oy_mul = 1, oy_add = 0, ox_mul = 1, ox_add = 0;   // out pixel = (oy*oy_mul+oy_add, ox*ox_mul+ox_add)
+  // prologue on the input: relu?(x*in_scale[c]+in_shift[c]) ; padding contributes 0 AFTER the transform
+  const float* in_scale = nullptr; const float* in_shift = nullptr; int in_relu = 0;
+  // epilogue: v = acc (+add0) ; v = v*scale[c]+shift[c] ; v = act(v) ; v *= mul1[c] ; v += add1
+  View add0, add1;                    // same pixel grid as out; p==nullptr when unused
+  const float* scale = nullptr; const float* shift = nullptr; const float* mul1 = nullptr;
+  int act = ACT_NONE;
+  // optional fused row statistics (vocabulary head): no tensor output, per (row, column-block) partials
+  float* stat_max = nullptr; float* stat_sum = nullptr; int* stat_idx = nullptr; int stat_ld = 0;
+};
+
+void launch_conv(const ConvOp& op, cudaStream_t st);
+int conv_stat_blocks(int Cout);       // number of column blocks the row-stat epilogue writes per row
+void launch_rowstat_final(const float* pmax, const float* psum, const int* pidx, int rows, int nblk,
+                          int* idx, float* logprob, cudaStream_t st);
+
+// weight repack: dst[(t*Cin+c)*ldw + co] = src[co*s_co + c*s_c + ky[t]*s_ky + kx[t]*s_kx] (zero for co>=Cout)
+void launch_repack(float* dst, const float* src, int Cout, int Cin, int ntaps, const int* ky, const int* kx,
+                   long s_co, long s_c, long s_ky, long s_kx, int ldw, cudaStream_t st);
+
+// ------------------------------------------------------------------ other kernels
+void launch_layernorm(const View& in, const View& out, const float* w, const float* b, float eps,
+                      const float* pe /*[T,C] added into out2*/, const View* out2, int T, cudaStream_t st);
+void launch_dwconv7_ln(const View& in, const View& out, const float* wdw /*[49][C]*/, const float* bdw,
+                       const float* lnw, const float* lnb, float eps, cudaStream_t st);
+void launch_avgpool(const View& in, const View& out, int mode /*0: 2x2s2, 1: k2 s(2,1) p(0,1)*/, cudaStream_t st);
+void launch_nchw_to_nhwc(const float* src, int N, int C, int H, int W, const View& dst, cudaStream_t st);
+void launch_nhwc_to_nchw(const View& src, float* dst, cudaStream_t st);
+void launch_u8_to_nhwc(const uint8_t* src, int N, int H, int W, int C, const View& dst, float mul, float add,
+                       int div_first, cudaStream_t st);
+void launch_affine_act(const View& in, const View& out, const float* scale, const float* shift, int act,
+                       cudaStream_t st);
+void launch_attention(const float* qk /*[N*T,2D]*/, const float* v /*[N*T,D]*/, float* out /*[N*T,D]*/,
+                      int N, int T, int heads, int hd, cudaStream_t st);
+void launch_lama_pack_input(const float* img, const float* mask, int N, int H, int W, const View& dst, cudaStream_t st);
+void launch_lama_blend(const View& pred, const float* img, const float* mask, float* out, cudaStream_t st);
+void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, const float* table, const float* dirw,
+                    float a5, float a6, cudaStream_t st);
+
+// real 2-D FFT of planar tensors, norm='ortho' (spectrum planes interleaved c0_re,c0_im,c1_re,...)
+struct FftPlan;
+FftPlan* fft_plan_get(int n);          // cached per length, lives for the process
+void launch_rfft2(const View& in /*planar [C][h][w]*/, const View& spec /*planar [2C][h][w/2+1]*/, float2* tmp,
+                  cudaStream_t st);
+void launch_irfft2(const View& spec, const View& out, const View* add /*planar, optional residual*/, float2* tmp,
+                   cudaStream_t st);
+
+// ------------------------------------------------------------------ weights
+struct Weights {
+  std::map<std::string, mitb_tensor> t;
+  const mitb_tensor& get(const std::string& name) const {
+    auto it = t.find(name); MITB_CHECK(it != t.end(), "missing weight '%s'", name.c_str()); return it->second;
+  }
+  bool has(const std::string& name) const { return t.count(name) != 0; }
+};
+
+struct DevBlob {                       // owning device allocation for repacked weights
+  std::vector<void*> ptrs;
+  float* alloc_f(size_t n) { void* p = nullptr; CUDA_OK(cudaMalloc(&p, (n ? n : 1) * sizeof(float))); ptrs.push_back(p); return (float*)p; }
+  void free_all() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); }
+  ~DevBlob() { free_all(); }
+};
+
+// conv weight handle produced at load time
+struct ConvW {
+  const float* w = nullptr; int ldw = 0, Cin = 0, Cout = 0, ntaps = 1;
+  int8_t tdy[kMaxTaps] = {0}, tdx[kMaxTaps] = {0};
+  const float* scale = nullptr; const float* shift = nullptr;   // folded BN / bias (may be null)
+};
+
+struct Loader {                        // helpers used by the network builders at load time
+  const Weights& W; DevBlob& blob; cudaStream_t st;
+  // PyTorch Conv2d weight [Cout,Cin,kh,kw] -> K-major; taps enumerated row-major with offsets (ky-pad_y, kx-pad_x)
+  ConvW conv(const std::string& wname, int pad_y, int pad_x);
+  // concatenate several Conv2d weights along Cin (same Cout/kh/kw)
+  ConvW conv_cat_cin(const std::vector<std::string>& wnames, int pad_y, int pad_x);
+  // ConvTranspose2d weight [Cin,Cout,kh,kw], stride 2: phase (py,px) sub-kernel
+  ConvW convT_phase(const std::string& wname, int k, int pad, int py, int px);
+  // rows [r0, r0+nr) of a Linear weight [out,in] as a 1x1 conv (packed in_proj of nn.MultiheadAttention)
+  ConvW linear_rows(const std::string& wname, int r0, int nr);
+  const float* vec_slice(const std::string& name, int off, int n);
+  ConvW conv_padcin(const std::string& wname, int pad, int cin_pad);   // zero-pad input channels (RGB -> 4)
+  const float* vec(const std::string& name);                    // copy a 1-D tensor
+  const float* vec_tiled(const std::string& name, int reps);
+  void bn_fold(const std::string& prefix, float eps, const float** scale, const float** shift);
+  float scalar(const std::string& name);
+};
+
+// ------------------------------------------------------------------ networks
+struct Ctx;
+struct DbnetModel; struct OcrModel; struct LamaModel;
+DbnetModel* dbnet_build(Ctx&, const Weights&);
+void dbnet_free(DbnetModel*);
+void dbnet_run(Ctx&, DbnetModel&, const float* x_nchw, const uint8_t* x_u8, int n, int h, int w, float* db,
+               float* mask, cudaStream_t st);
+OcrModel* ocr_build(Ctx&, const Weights&);
+void ocr_free(OcrModel*);
+void ocr_run(Ctx&, OcrModel&, const float* x_nchw, const uint8_t* x_u8, int n, int wp, int* idx, float* logprob,
+             float* colors, cudaStream_t st);
+int ocr_vocab(const OcrModel&);
+LamaModel* lama_build(Ctx&, const Weights&);
+void lama_free(LamaModel*);
+void lama_run(Ctx&, LamaModel&, const float* img, const float* mask, const int* rel_pos, const int* direct, int n,
+              int h, int w, float* out, cudaStream_t st);
+
+struct Ctx {
+  int device = 0;
+  std::string err;
+  Arena ws;
+  DbnetModel* dbnet = nullptr; OcrModel* ocr = nullptr; LamaModel* lama = nullptr;
+  long launches = 0;                   // kernels launched by this library (bench.py "gpu_launches")
+  void ensure_ws(size_t bytes);
+};
+extern thread_local long* g_launch_counter;
+inline void count_launch() { if (g_launch_counter) ++*g_launch_counter; }
+
+}  // namespace mitb

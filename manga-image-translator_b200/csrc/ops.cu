@@ -1,0 +1,414 @@
+// HBM-bound helper kernels: LayerNorm, fused depthwise-7x7 + LayerNorm, pooling, layout / dtype conversion,
+// the LaMa input pack / MPE add / final blend, and the small OCR attention core.
+// All operate on NHWC views (channel slice of a wider tensor) with 128-bit accesses along C where aligned.
+#include "mitb_internal.h"
+
+namespace mitb {
+
+#define LAUNCH_END() do { count_launch(); CUDA_OK(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm over C for every pixel (row).  One warp per row, two-pass (mean, then centred variance) in
+// registers, C <= 1024 and C % 32 == 0.  Optionally also writes out2 = out + pe[row % T] (the OCR encoder adds
+// the positional encoding to q/k only, model_48px_ctc.py:263-266).
+template <int PER_LANE>
+__global__ void layernorm_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs, int out_coff,
+                                 const float* w, const float* b, float eps, long rows, int C, const float* pe,
+                                 float* out2, int out2_cs, int out2_coff, int T) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = in + row * in_cs + in_coff;
+  float v[PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) { int c = lane + 32 * i; v[i] = c < C ? src[c] : 0.f; s += v[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) { int c = lane + 32 * i; float d = c < C ? v[i] - mean : 0.f; q += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  float* dst = out + row * out_cs + out_coff;
+  float* dst2 = out2 ? out2 + row * out2_cs + out2_coff : nullptr;
+  const float* per = pe ? pe + (size_t)(row % T) * C : nullptr;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    int c = lane + 32 * i;
+    if (c < C) {
+      float y = (v[i] - mean) * rstd * w[c] + b[c];
+      dst[c] = y;
+      if (dst2) dst2[c] = y + per[c];
+    }
+  }
+}
+
+void launch_layernorm(const View& in, const View& out, const float* w, const float* b, float eps, const float* pe,
+                      const View* out2, int T, cudaStream_t st) {
+  MITB_CHECK(!in.planar && !out.planar, "layernorm expects NHWC views");
+  const int C = in.C; const long rows = (long)in.pixels();
+  MITB_CHECK(C <= 1024 && out.C == C, "layernorm: C=%d unsupported", C);
+  const int per = (C + 31) / 32;
+  dim3 grid((unsigned)((rows + 7) / 8));
+  float* o2 = out2 ? out2->p : nullptr; int o2cs = out2 ? out2->cs : 0, o2off = out2 ? out2->coff : 0;
+#define LN_CASE(P) layernorm_kernel<P><<<grid, 256, 0, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, w, b, eps, rows, C, pe, o2, o2cs, o2off, T)
+  if (per <= 4) LN_CASE(4); else if (per <= 8) LN_CASE(8); else if (per <= 10) LN_CASE(10);
+  else if (per <= 16) LN_CASE(16); else LN_CASE(32);
+#undef LN_CASE
+  LAUNCH_END();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ConvNeXt token mixer: depthwise 7x7 (pad 3, bias) immediately followed by LayerNorm over C
+// (dbnet_convnext.py:114-122).  blockDim = (C/4, PY): a thread owns 4 channels (one float4) of TX=8 consecutive
+// output pixels of one row; the C/4 threads with the same threadIdx.y jointly normalise those 8 pixels.
+constexpr int DW_TX = 8;
+
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs,
+                                                         int out_coff, const float* wdw, const float* bdw, const float* lnw,
+                                                         const float* lnb, float eps, int N, int H, int W, int C) {
+  extern __shared__ float red[];                 // [PY][nwarps_per_row][DW_TX]
+  const int c = threadIdx.x * 4;
+  const int xt = blockIdx.x * DW_TX;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int n = blockIdx.z;
+  const bool row_ok = y < H;
+  float4 acc[DW_TX];
+  const float4 bias = *reinterpret_cast<const float4*>(bdw + c);
+#pragma unroll
+  for (int i = 0; i < DW_TX; ++i) acc[i] = bias;
+  if (row_ok) {
+    for (int dy = 0; dy < 7; ++dy) {
+      const int iy = y + dy - 3;
+      if (iy < 0 || iy >= H) continue;
+      float4 wv[7];
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) wv[dx] = __ldg(reinterpret_cast<const float4*>(wdw + (size_t)(dy * 7 + dx) * C + c));
+      const float* rowp = in + ((size_t)(n * H + iy) * W) * in_cs + in_coff + c;
+#pragma unroll
+      for (int j = 0; j < DW_TX + 6; ++j) {
+        const int ix = xt + j - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(rowp + (size_t)ix * in_cs));
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx) {
+          const int i = j - dx;                  // output pixel fed by this input through tap dx
+          if (i >= 0 && i < DW_TX) {
+            acc[i].x = fmaf(v.x, wv[dx].x, acc[i].x); acc[i].y = fmaf(v.y, wv[dx].y, acc[i].y);
+            acc[i].z = fmaf(v.z, wv[dx].z, acc[i].z); acc[i].w = fmaf(v.w, wv[dx].w, acc[i].w);
+          }
+        }
+      }
+    }
+  }
+  // ---- LayerNorm over C across the threadIdx.x dimension (two-pass)
+  const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+  const int wrow = blockDim.x >> 5 ? blockDim.x >> 5 : 1;      // warps per pixel row (C/128), >=1
+  const int warp_in_row = threadIdx.x >> 5;
+  float* myred = red + (size_t)threadIdx.y * wrow * DW_TX;
+  float mean[DW_TX], rstd[DW_TX];
+  for (int pass = 0; pass < 2; ++pass) {
+    float part[DW_TX];
+#pragma unroll
+    for (int i = 0; i < DW_TX; ++i) {
+      if (pass == 0) part[i] = acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+      else {
+        float a = acc[i].x - mean[i], b = acc[i].y - mean[i], cc = acc[i].z - mean[i], d = acc[i].w - mean[i];
+        part[i] = a * a + b * b + cc * cc + d * d;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
+    }
+    if (blockDim.x >= 32) {
+      __syncthreads();
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < DW_TX; ++i) myred[warp_in_row * DW_TX + i] = part[i];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < DW_TX; ++i) {
+        float t = 0.f;
+        for (int wv = 0; wv < wrow; ++wv) t += myred[wv * DW_TX + i];
+        part[i] = t;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DW_TX; ++i) {
+      if (pass == 0) mean[i] = part[i] / C; else rstd[i] = rsqrtf(part[i] / C + eps);
+    }
+  }
+  if (!row_ok) return;
+  const float4 g = *reinterpret_cast<const float4*>(lnw + c), be = *reinterpret_cast<const float4*>(lnb + c);
+  float* orow = out + ((size_t)(n * H + y) * W) * out_cs + out_coff + c;
+#pragma unroll
+  for (int i = 0; i < DW_TX; ++i) {
+    const int x = xt + i;
+    if (x < W) {
+      float4 r;
+      r.x = (acc[i].x - mean[i]) * rstd[i] * g.x + be.x; r.y = (acc[i].y - mean[i]) * rstd[i] * g.y + be.y;
+      r.z = (acc[i].z - mean[i]) * rstd[i] * g.z + be.z; r.w = (acc[i].w - mean[i]) * rstd[i] * g.w + be.w;
+      *reinterpret_cast<float4*>(orow + (size_t)x * out_cs) = r;
+    }
+  }
+}
+
+void launch_dwconv7_ln(const View& in, const View& out, const float* wdw, const float* bdw, const float* lnw,
+                       const float* lnb, float eps, cudaStream_t st) {
+  const int C = in.C;
+  MITB_CHECK(C % 128 == 0 && C <= 1024, "dwconv7_ln: C=%d must be a multiple of 128 (<=1024)", C);
+  MITB_CHECK(in.cs % 4 == 0 && in.coff % 4 == 0 && out.cs % 4 == 0 && out.coff % 4 == 0, "dwconv7_ln alignment");
+  const int tx = C / 4;
+  int py = 256 / tx; if (py < 1) py = 1;
+  dim3 block(tx, py), grid((in.W + DW_TX - 1) / DW_TX, (in.H + py - 1) / py, in.N);
+  const size_t smem = (size_t)py * (tx / 32) * DW_TX * sizeof(float);
+  dwconv7_ln_kernel<<<grid, block, smem, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, wdw, bdw, lnw, lnb, eps,
+                                               in.N, in.H, in.W, C);
+  LAUNCH_END();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AvgPool2d: mode 0 = kernel 2 stride 2; mode 1 = kernel 2, stride (2,1), padding (0,1), count_include_pad
+// (model_48px_ctc.py:289,295,301) -> out width W+1, zero columns averaged in.
+__global__ void avgpool_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs, int out_coff, int N,
+                               int H, int W, int C4, int Ho, int Wo, int mode) {
+  const long total = (long)N * Ho * Wo * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4; long r = i / C4;
+    const int ox = (int)(r % Wo); r /= Wo; const int oy = (int)(r % Ho); const int n = (int)(r / Ho);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = oy * 2 + dy;
+        const int ix = mode == 0 ? ox * 2 + dx : ox - 1 + dx;
+        if (ix >= 0 && ix < W && iy < H) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)(n * H + iy) * W + ix) * in_cs + in_coff + c));
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+      }
+    s.x *= 0.25f; s.y *= 0.25f; s.z *= 0.25f; s.w *= 0.25f;
+    *reinterpret_cast<float4*>(out + ((size_t)(n * Ho + oy) * Wo + ox) * out_cs + out_coff + c) = s;
+  }
+}
+
+void launch_avgpool(const View& in, const View& out, int mode, cudaStream_t st) {
+  MITB_CHECK(in.C % 4 == 0 && in.cs % 4 == 0 && in.coff % 4 == 0 && out.cs % 4 == 0 && out.coff % 4 == 0, "avgpool alignment");
+  const long total = (long)out.N * out.H * out.W * (in.C / 4);
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  avgpool_kernel<<<blocks, 256, 0, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, in.N, in.H, in.W, in.C / 4,
+                                         out.H, out.W, mode);
+  LAUNCH_END();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout conversions.  NCHW -> NHWC view (missing channels of the view are zero-filled, e.g. RGB -> 4 channels).
+__global__ void nchw_to_nhwc_kernel(const float* src, int N, int C, int H, int W, float* dst, int cs, int coff, int Cv) {
+  const long total = (long)N * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i % ((long)H * W); const int n = (int)(i / ((long)H * W));
+    for (int c = 0; c < Cv; ++c)
+      dst[i * cs + coff + c] = c < C ? src[((size_t)n * C + c) * H * W + pix] : 0.f;
+  }
+}
+void launch_nchw_to_nhwc(const float* src, int N, int C, int H, int W, const View& dst, cudaStream_t st) {
+  const long total = (long)N * H * W;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  nchw_to_nhwc_kernel<<<blocks, 256, 0, st>>>(src, N, C, H, W, dst.p, dst.cs, dst.coff, dst.C);
+  LAUNCH_END();
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* src, int cs, int coff, int N, int C, int H, int W, float* dst) {
+  const long total = (long)N * C * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i % ((long)H * W); long r = i / ((long)H * W); const int c = (int)(r % C); const int n = (int)(r / C);
+    dst[i] = src[((size_t)n * H * W + pix) * cs + coff + c];
+  }
+}
+void launch_nhwc_to_nchw(const View& src, float* dst, cudaStream_t st) {
+  const long total = (long)src.N * src.C * src.H * src.W;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  nhwc_to_nchw_kernel<<<blocks, 256, 0, st>>>(src.p, src.cs, src.coff, src.N, src.C, src.H, src.W, dst);
+  LAUNCH_END();
+}
+
+// uint8 NHWC image -> fp32 NHWC view with the reference's normalisation:
+//   div_first=1: x/127.5 - 1.0   (numpy fp32, dbnet_convnext.py:503: divide, then subtract)
+//   div_first=0: (x - 127.5)/127.5 (model_48px_ctc.py:101: subtract, then divide)
+__global__ void u8_to_nhwc_kernel(const uint8_t* src, long npix, int C, float* dst, int cs, int coff, int Cv, float mul,
+                                  float add, int div_first) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+    for (int c = 0; c < Cv; ++c) {
+      float v = 0.f;
+      if (c < C) {
+        const float x = (float)src[i * C + c];
+        v = div_first ? __fsub_rn(__fdiv_rn(x, mul), add) : __fdiv_rn(__fsub_rn(x, add), mul);
+      }
+      dst[i * cs + coff + c] = v;
+    }
+  }
+}
+void launch_u8_to_nhwc(const uint8_t* src, int N, int H, int W, int C, const View& dst, float mul, float add,
+                       int div_first, cudaStream_t st) {
+  const long npix = (long)N * H * W;
+  int blocks = (int)((npix + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  u8_to_nhwc_kernel<<<blocks, 256, 0, st>>>(src, npix, C, dst.p, dst.cs, dst.coff, dst.C, mul, add, div_first);
+  LAUNCH_END();
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case ACT_SILU: return v / (1.f + expf(-v));
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+__global__ void affine_act_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs, int out_coff, long npix,
+                                  int C, const float* scale, const float* shift, int act) {
+  const long total = npix * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); const long pix = i / C;
+    float v = in[pix * in_cs + in_coff + c];
+    if (scale) v = v * scale[c] + shift[c];
+    out[pix * out_cs + out_coff + c] = act_apply(v, act);
+  }
+}
+void launch_affine_act(const View& in, const View& out, const float* scale, const float* shift, int act, cudaStream_t st) {
+  const long total = (long)in.pixels() * in.C;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  affine_act_kernel<<<blocks, 256, 0, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, (long)in.pixels(), in.C, scale, shift, act);
+  LAUNCH_END();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// OCR self-attention core (model_48px_ctc.py:263-269 -> F.multi_head_attention_forward): one CTA per
+// (line, head); K and V of that head staged in shared memory (stride hd+1), one warp per query row,
+// softmax(q.k / sqrt(hd)) v with no padding mask.
+__global__ void attention_kernel(const float* qk, const float* v, float* out, int T, int heads, int hd, float scale) {
+  extern __shared__ float sm[];
+  const int D = heads * hd;
+  const int n = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int ld = hd + 1;
+  float* Ks = sm; float* Vs = Ks + (size_t)T * ld;
+  float* Ps = Vs + (size_t)T * ld;               // [nwarps][T] probabilities
+  float* Qs = Ps + (size_t)(blockDim.x >> 5) * T; // [nwarps][hd]
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    Ks[t * ld + d] = qk[((size_t)n * T + t) * 2 * D + D + h * hd + d];
+    Vs[t * ld + d] = v[((size_t)n * T + t) * D + h * hd + d];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float* P = Ps + (size_t)warp * T; float* Q = Qs + warp * hd;
+  for (int t = warp; t < T; t += nw) {
+    for (int d = lane; d < hd; d += 32) Q[d] = qk[((size_t)n * T + t) * 2 * D + h * hd + d];
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      float s = 0.f;
+      for (int d = 0; d < hd; ++d) s = fmaf(Q[d], Ks[j * ld + d], s);
+      s *= scale; P[j] = s; mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) { float e = expf(P[j] - mx); P[j] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int d = lane; d < hd; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < T; ++j) a = fmaf(P[j], Vs[j * ld + d], a);
+      out[((size_t)n * T + t) * D + h * hd + d] = a * inv;
+    }
+    __syncwarp();
+  }
+}
+
+void launch_attention(const float* qk, const float* v, float* out, int N, int T, int heads, int hd, cudaStream_t st) {
+  const int threads = 256;
+  const size_t smem = ((size_t)2 * T * (hd + 1) + (size_t)(threads / 32) * T + (size_t)(threads / 32) * hd) * sizeof(float);
+  MITB_CHECK(smem <= 200 * 1024, "attention: sequence too long (T=%d)", T);
+  static bool attr_set = false;
+  if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+  attention_kernel<<<N * heads, threads, smem, st>>>(qk, v, out, T, heads, hd, 1.0f / sqrtf((float)hd));
+  LAUNCH_END();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LaMa glue.  pack: cat(img*(1-mask), mask) NCHW -> NHWC 4 channels (inpainting_lama_mpe.py:604).
+__global__ void lama_pack_kernel(const float* img, const float* mask, int N, long HW, float* dst, int cs, int coff) {
+  const long total = (long)N * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i % HW; const int n = (int)(i / HW);
+    const float m = mask[(size_t)n * HW + pix];
+    float4 v;
+    v.x = img[((size_t)n * 3 + 0) * HW + pix] * (1.f - m);
+    v.y = img[((size_t)n * 3 + 1) * HW + pix] * (1.f - m);
+    v.z = img[((size_t)n * 3 + 2) * HW + pix] * (1.f - m);
+    v.w = m;
+    *reinterpret_cast<float4*>(dst + i * cs + coff) = v;
+  }
+}
+void launch_lama_pack_input(const float* img, const float* mask, int N, int H, int W, const View& dst, cudaStream_t st) {
+  const long total = (long)N * H * W;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  lama_pack_kernel<<<blocks, 256, 0, st>>>(img, mask, N, (long)H * W, dst.p, dst.cs, dst.coff);
+  LAUNCH_END();
+}
+
+// blend: out = pred*mask + (1-mask)*img, pred planar NCHW view (inpainting_lama_mpe.py:726)
+__global__ void lama_blend_kernel(const float* pred, const float* img, const float* mask, float* out, int N, long HW) {
+  const long total = (long)N * 3 * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i % HW; const int n = (int)(i / (3 * HW));
+    const float m = mask[(size_t)n * HW + pix];
+    out[i] = pred[i] * m + (1.f - m) * img[i];
+  }
+}
+void launch_lama_blend(const View& pred, const float* img, const float* mask, float* out, cudaStream_t st) {
+  MITB_CHECK(pred.planar && pred.C == 3 && pred.cs == 3 && pred.coff == 0, "blend expects a planar 3-channel prediction");
+  const long total = (long)pred.N * 3 * pred.H * pred.W;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  lama_blend_kernel<<<blocks, 256, 0, st>>>(pred.p, img, mask, out, pred.N, (long)pred.H * pred.W);
+  LAUNCH_END();
+}
+
+// x_l += table[rel_pos]*alpha5 ; x_l += (direct @ W)*alpha6  (inpainting_lama_mpe.py:609-612, 625-632)
+__global__ void mpe_add_kernel(float* x, int cs, int coff, long npix, const int* rel_pos, const int* direct,
+                               const float* table, const float* dirw, float a5, float a6) {
+  const long total = npix * 16;                  // 64 channels = 16 float4 per pixel
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 15) * 4; const long pix = i >> 4;
+    const int rp = rel_pos[pix];
+    const int4 d = *reinterpret_cast<const int4*>(direct + pix * 4);
+    float4 v = *reinterpret_cast<float4*>(x + pix * cs + coff + c);
+    const float4 e = *reinterpret_cast<const float4*>(table + rp * 64 + c);
+    const float4 w0 = *reinterpret_cast<const float4*>(dirw + 0 * 64 + c), w1 = *reinterpret_cast<const float4*>(dirw + 1 * 64 + c);
+    const float4 w2 = *reinterpret_cast<const float4*>(dirw + 2 * 64 + c), w3 = *reinterpret_cast<const float4*>(dirw + 3 * 64 + c);
+    const float d0 = (float)d.x, d1 = (float)d.y, d2 = (float)d.z, d3 = (float)d.w;
+    v.x += e.x * a5; v.y += e.y * a5; v.z += e.z * a5; v.w += e.w * a5;
+    v.x += (d0 * w0.x + d1 * w1.x + d2 * w2.x + d3 * w3.x) * a6;
+    v.y += (d0 * w0.y + d1 * w1.y + d2 * w2.y + d3 * w3.y) * a6;
+    v.z += (d0 * w0.z + d1 * w1.z + d2 * w2.z + d3 * w3.z) * a6;
+    v.w += (d0 * w0.w + d1 * w1.w + d2 * w2.w + d3 * w3.w) * a6;
+    *reinterpret_cast<float4*>(x + pix * cs + coff + c) = v;
+  }
+}
+void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, const float* table, const float* dirw, float a5,
+                    float a6, cudaStream_t st) {
+  MITB_CHECK(x.C == 64 && x.cs % 4 == 0 && x.coff % 4 == 0, "mpe_add expects the 64-channel stem output");
+  const long total = (long)x.pixels() * 16;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  mpe_add_kernel<<<blocks, 256, 0, st>>>(x.p, x.cs, x.coff, (long)x.pixels(), rel_pos, direct, table, dirw, a5, a6);
+  LAUNCH_END();
+}
+
+}  // namespace mitb

@@ -1,0 +1,230 @@
+"""Thin Python host over the C ABI: owns one mitb context per GPU, hands torch CUDA tensors (used purely as device
+memory containers) to the library and returns torch tensors.  No arithmetic of the hot path happens in torch."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MitbError, MitbTensor
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One context bound to one CUDA device (one process per GPU in multi-GPU runs)."""
+
+    def __init__(self, device="cuda:0"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise MitbError("mit_b200 needs a CUDA (B200, sm_100a) device; there is no CPU fallback")
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        if self.device.type != "cuda":
+            raise MitbError(f"mit_b200 runs on CUDA only, got device '{device}'")
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        rc = self.lib.mitb_create(self.device.index or 0, C.byref(h))
+        if rc != 0:
+            raise MitbError(self.lib.mitb_last_error(None).decode())
+        self._h = h
+        self._keep = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mitb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MitbError(self.lib.mitb_last_error(self._h).decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.mitb_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.mitb_workspace_bytes(self._h))
+
+    def _tensors(self, sd: Dict[str, torch.Tensor]):
+        keep, arr = [], (MitbTensor * len(sd))()
+        for i, (k, v) in enumerate(sd.items()):
+            t = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            arr[i].name = k.encode()
+            arr[i].data = t.data_ptr()
+            arr[i].ndim = t.dim()
+            for d in range(t.dim()):
+                arr[i].shape[d] = t.shape[d]
+        return arr, keep
+
+    @staticmethod
+    def _float_sd(sd):
+        return {k: v for k, v in sd.items() if torch.is_tensor(v) and v.is_floating_point() and v.dim() <= 4}
+
+    # ------------------------------------------------------------------ models
+    def load_dbnet(self, state_dict):
+        arr, keep = self._tensors(self._float_sd(state_dict))
+        self._check(self.lib.mitb_dbnet_load(self._h, arr, len(arr)))
+        torch.cuda.synchronize(self.device)
+
+    def unload_dbnet(self):
+        self._check(self.lib.mitb_dbnet_unload(self._h))
+
+    def dbnet_forward(self, x: torch.Tensor):
+        """x: float32 [n,3,h,w] normalised, or uint8 [n,h,w,3]; returns (db sigmoid [n,2,h,w], mask [n,1,h/2,w/2])."""
+        x = x.to(self.device).contiguous()
+        if x.dtype == torch.uint8:
+            n, h, w, _ = x.shape
+        else:
+            n, _, h, w = x.shape
+        db = torch.empty((n, 2, h, w), dtype=torch.float32, device=self.device)
+        mask = torch.empty((n, 1, h // 2, w // 2), dtype=torch.float32, device=self.device)
+        fn = self.lib.mitb_dbnet_forward_u8 if x.dtype == torch.uint8 else self.lib.mitb_dbnet_forward
+        self._check(fn(self._h, _ptr(x), n, h, w, _ptr(db), _ptr(mask), self._stream()))
+        return db, mask
+
+    def load_ocr(self, state_dict, pe_table: Optional[torch.Tensor] = None):
+        sd = self._float_sd(state_dict)
+        sd = {k: v for k, v in sd.items() if not k.endswith("pe.pe")}
+        if pe_table is not None:
+            sd["pe.table"] = pe_table
+        arr, keep = self._tensors(sd)
+        self._check(self.lib.mitb_ocr_load(self._h, arr, len(arr)))
+        torch.cuda.synchronize(self.device)
+
+    def unload_ocr(self):
+        self._check(self.lib.mitb_ocr_unload(self._h))
+
+    def ocr_forward(self, x: torch.Tensor):
+        """x: float32 [n,3,48,wp] normalised or uint8 [n,48,wp,3]; returns (argmax int32 [n,T], logprob [n,T], colors [n,T,6])."""
+        x = x.to(self.device).contiguous()
+        if x.dtype == torch.uint8:
+            n, _, wp, _ = x.shape
+        else:
+            n, _, _, wp = x.shape
+        T = self.lib.mitb_ocr_timesteps(wp)
+        idx = torch.empty((n, T), dtype=torch.int32, device=self.device)
+        lp = torch.empty((n, T), dtype=torch.float32, device=self.device)
+        col = torch.empty((n, T, 6), dtype=torch.float32, device=self.device)
+        fn = self.lib.mitb_ocr_forward_u8 if x.dtype == torch.uint8 else self.lib.mitb_ocr_forward
+        self._check(fn(self._h, _ptr(x), n, wp, _ptr(idx), _ptr(lp), _ptr(col), self._stream()))
+        return idx, lp, col
+
+    def load_lama(self, gen_state_dict, mpe_state_dict=None):
+        sd = self._float_sd(gen_state_dict)
+        if mpe_state_dict is not None:
+            for k, v in mpe_state_dict.items():
+                sd["mpe." + k] = v
+        arr, keep = self._tensors(sd)
+        self._check(self.lib.mitb_lama_load(self._h, arr, len(arr)))
+        torch.cuda.synchronize(self.device)
+
+    def unload_lama(self):
+        self._check(self.lib.mitb_lama_unload(self._h))
+
+    def lama_forward(self, img: torch.Tensor, mask: torch.Tensor, rel_pos=None, direct=None):
+        img = img.to(self.device, torch.float32).contiguous()
+        mask = mask.to(self.device, torch.float32).contiguous()
+        n, _, h, w = img.shape
+        if rel_pos is not None:
+            rel_pos = torch.as_tensor(rel_pos).to(self.device, torch.int32).contiguous()
+            direct = torch.as_tensor(direct).to(self.device, torch.int32).contiguous()
+        out = torch.empty_like(img)
+        self._check(self.lib.mitb_lama_forward(self._h, _ptr(img), _ptr(mask), _ptr(rel_pos), _ptr(direct), n, h, w,
+                                               _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ standalone operators (tests / micro-benchmarks)
+    def _dev(self, t, dtype=torch.float32):
+        return None if t is None else torch.as_tensor(t).to(self.device, dtype).contiguous()
+
+    def conv2d(self, x, w, bias=None, stride=(1, 1), padding=(0, 0), pad_mode="zeros", act=0, in_scale=None, in_shift=None,
+               in_relu=False):
+        x, w, bias, in_scale, in_shift = map(self._dev, (x, w, bias, in_scale, in_shift))
+        n, cin, h, wd = x.shape
+        cout, _, kh, kw = w.shape
+        ho = (h + 2 * padding[0] - kh) // stride[0] + 1
+        wo = (wd + 2 * padding[1] - kw) // stride[1] + 1
+        y = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=self.device)
+        self._check(self.lib.mitb_op_conv2d(self._h, _ptr(x), n, cin, h, wd, _ptr(w), cout, kh, kw, stride[0], stride[1],
+                                            padding[0], padding[1], 1 if pad_mode == "reflect" else 0, _ptr(bias), act,
+                                            _ptr(in_scale), _ptr(in_shift), int(in_relu), _ptr(y), self._stream()))
+        return y
+
+    def conv_transpose2d(self, x, w, bias=None, k=2, pad=0, out_pad=0, act=0):
+        x, w, bias = map(self._dev, (x, w, bias))
+        n, cin, h, wd = x.shape
+        cout = w.shape[1]
+        y = torch.empty((n, cout, 2 * h, 2 * wd), dtype=torch.float32, device=self.device)
+        self._check(self.lib.mitb_op_conv_transpose2d(self._h, _ptr(x), n, cin, h, wd, _ptr(w), cout, k, pad, out_pad,
+                                                      _ptr(bias), act, _ptr(y), self._stream()))
+        return y
+
+    def dwconv7_ln(self, x, wdw, bdw, lnw, lnb, eps=1e-6):
+        x, wdw, bdw, lnw, lnb = map(self._dev, (x, wdw, bdw, lnw, lnb))
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        self._check(self.lib.mitb_op_dwconv7_ln(self._h, _ptr(x), n, c, h, w, _ptr(wdw), _ptr(bdw), _ptr(lnw), _ptr(lnb),
+                                                eps, _ptr(y), self._stream()))
+        return y
+
+    def layernorm(self, x, w, b, eps):
+        x, w, b = map(self._dev, (x, w, b))
+        rows, c = x.shape
+        y = torch.empty_like(x)
+        self._check(self.lib.mitb_op_layernorm(self._h, _ptr(x), rows, c, _ptr(w), _ptr(b), eps, _ptr(y), self._stream()))
+        return y
+
+    def rfft2(self, x):
+        x = self._dev(x)
+        c, h, w = x.shape
+        spec = torch.empty((2 * c, h, w // 2 + 1), dtype=torch.float32, device=self.device)
+        self._check(self.lib.mitb_op_rfft2(self._h, _ptr(x), c, h, w, _ptr(spec), self._stream()))
+        return spec
+
+    def irfft2(self, spec, w):
+        spec = self._dev(spec)
+        c2, h, _ = spec.shape
+        y = torch.empty((c2 // 2, h, w), dtype=torch.float32, device=self.device)
+        self._check(self.lib.mitb_op_irfft2(self._h, _ptr(spec), c2 // 2, h, w, _ptr(y), self._stream()))
+        return y
+
+    def attention(self, qk, v, n, t, heads, hd):
+        qk, v = map(self._dev, (qk, v))
+        out = torch.empty_like(v)
+        self._check(self.lib.mitb_op_attention(self._h, _ptr(qk), _ptr(v), n, t, heads, hd, _ptr(out), self._stream()))
+        return out
+
+    def bilateral17(self, img_u8):
+        img = torch.as_tensor(img_u8).to(self.device, torch.uint8).contiguous()
+        h, w, _ = img.shape
+        out = torch.empty_like(img)
+        self._check(self.lib.mitb_op_bilateral17(self._h, _ptr(img), h, w, _ptr(out), self._stream()))
+        return out
+
+
+_engines = {}
+
+
+def get_engine(device="cuda:0") -> Engine:
+    """Process-wide engine per device (the three plugins of one process share workspace and stream)."""
+    key = str(torch.device(device if str(device) != "cuda" else "cuda:0"))
+    if key not in _engines:
+        _engines[key] = Engine(key)
+    return _engines[key]

@@ -1,0 +1,153 @@
+"""Parity of the standalone CUDA operators (called through the C ABI) against plain torch CPU fp32 ops.
+Tolerances: fp32 kernels with different summation order -> 2e-4 relative to the output scale (observed ~1e-6)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from mit_b200.engine import get_engine
+    return get_engine("cuda:0")
+
+
+def _close(a, b, tol=2e-4, what=""):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    scale = max(1.0, b.abs().max().item())
+    assert err <= tol * scale, f"{what}: max abs err {err:.3e} (scale {scale:.3e})"
+
+
+ACTS = {0: lambda x: x, 1: F.relu, 2: F.gelu, 3: F.silu, 4: torch.sigmoid}
+
+CONV_CASES = [
+    # n, cin, h, w, cout, kh, kw, stride, pad, mode, act
+    (1, 8, 17, 23, 40, 3, 3, (1, 1), (1, 1), "zeros", 1),
+    (2, 3, 24, 40, 40, 3, 3, (1, 1), (1, 1), "zeros", 0),      # RGB stem (cin padded to 4)
+    (1, 3, 32, 32, 128, 4, 4, (4, 4), (0, 0), "zeros", 0),     # ConvNeXt patchify
+    (1, 64, 20, 28, 128, 3, 3, (2, 2), (1, 1), "reflect", 1),  # LaMa downsample
+    (1, 4, 19, 21, 64, 7, 7, (1, 1), (3, 3), "reflect", 1),    # LaMa stem
+    (1, 160, 9, 15, 128, 7, 7, (1, 1), (3, 3), "zeros", 0),    # dense 7x7 (UpconvSkip)
+    (1, 320, 6, 33, 320, 3, 3, (2, 1), (1, 1), "zeros", 0),    # OCR conv4_1 stride (2,1)
+    (1, 320, 3, 33, 320, 3, 3, (1, 1), (0, 0), "zeros", 0),    # OCR conv4_2 no padding
+    (3, 128, 16, 12, 512, 1, 1, (1, 1), (0, 0), "zeros", 2),   # MLP fc1 + GELU
+    (1, 64, 30, 30, 3, 7, 7, (1, 1), (3, 3), "reflect", 4),    # LaMa output conv (thin output kernel)
+    (1, 32, 25, 31, 1, 1, 1, (1, 1), (0, 0), "zeros", 4),      # mask head 1x1 -> 1 channel
+    (1, 256, 8, 8, 192, 2, 2, (2, 2), (0, 0), "zeros", 3),     # downsample conv, Cout not a multiple of 64
+    (2, 40, 12, 50, 80, 3, 3, (1, 1), (1, 1), "zeros", 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d(eng, case):
+    n, cin, h, w, cout, kh, kw, stride, pad, mode, act = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xp = F.pad(x, (pad[1], pad[1], pad[0], pad[0]), mode="reflect") if mode == "reflect" else x
+    ref = ACTS[act](F.conv2d(xp, wt, b, stride=stride, padding=(0, 0) if mode == "reflect" else pad))
+    y = eng.conv2d(x, wt, b, stride, pad, mode, act)
+    _close(y, ref, what=f"conv2d {case}")
+
+
+def test_conv2d_bn_relu_prologue(eng):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 80, 12, 37, generator=g)
+    wt = torch.randn(160, 80, 3, 3, generator=g) / 27
+    sc, sh = torch.rand(80, generator=g) + 0.5, torch.randn(80, generator=g) * 0.3
+    ref = F.conv2d(F.relu(x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)), wt, padding=1)
+    y = eng.conv2d(x, wt, None, (1, 1), (1, 1), "zeros", 0, sc, sh, True)
+    _close(y, ref, what="prologue conv")
+    ref = F.conv2d(x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1), wt[:, :, 1:2, 1:2])
+    y = eng.conv2d(x, wt[:, :, 1:2, 1:2].contiguous(), None, (1, 1), (0, 0), "zeros", 0, sc, sh, False)
+    _close(y, ref, what="prologue conv (no relu, 1x1)")
+
+
+@pytest.mark.parametrize("k,pad,op,cin,cout", [(2, 0, 0, 64, 64), (4, 1, 0, 32, 32), (4, 1, 0, 32, 1), (3, 1, 1, 128, 64)])
+def test_conv_transpose2d(eng, k, pad, op, cin, cout):
+    g = torch.Generator().manual_seed(k * 100 + cout)
+    x = torch.randn(2, cin, 11, 14, generator=g)
+    wt = torch.randn(cin, cout, k, k, generator=g) / (cin * k * k / 4) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv_transpose2d(x, wt, b, stride=2, padding=pad, output_padding=op)
+    y = eng.conv_transpose2d(x, wt, b, k, pad, op, 0)
+    _close(y, ref, what=f"convT k{k} p{pad} op{op}")
+
+
+@pytest.mark.parametrize("c,h,w", [(128, 19, 27), (256, 16, 16), (512, 9, 13), (1024, 4, 6)])
+def test_dwconv7_ln(eng, c, h, w):
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(2, c, h, w, generator=g)
+    wdw, bdw = torch.randn(c, 1, 7, 7, generator=g) / 7, torch.randn(c, generator=g) * 0.1
+    lw, lb = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    ref = F.conv2d(x, wdw, bdw, padding=3, groups=c).permute(0, 2, 3, 1)
+    ref = F.layer_norm(ref, (c,), lw, lb, 1e-6).permute(0, 3, 1, 2)
+    y = eng.dwconv7_ln(x, wdw, bdw, lw, lb, 1e-6)
+    _close(y, ref, what=f"dwconv7_ln C={c}")
+
+
+@pytest.mark.parametrize("c", [128, 320, 1024])
+def test_layernorm(eng, c):
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(77, c, generator=g) * 3 + 1
+    w, b = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    _close(eng.layernorm(x, w, b, 1e-5), F.layer_norm(x, (c,), w, b, 1e-5), what=f"layernorm {c}")
+
+
+FFT_SIZES = [(8, 8), (16, 12), (20, 14), (11, 15), (32, 24), (256, 192), (40, 30), (97, 6), (6, 97), (13, 128)]
+
+
+@pytest.mark.parametrize("h,w", FFT_SIZES)
+def test_rfft2_irfft2(eng, h, w):
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    c = 3 if h * w > 10000 else 6
+    x = torch.randn(c, h, w, generator=g)
+    f = torch.fft.rfftn(x, dim=(-2, -1), norm="ortho")
+    ref = torch.stack((f.real, f.imag), dim=1).reshape(2 * c, h, w // 2 + 1)
+    spec = eng.rfft2(x)
+    _close(spec, ref, 2e-5, what=f"rfft2 {h}x{w}")
+    # inverse of an arbitrary (non-Hermitian-consistent) half spectrum, like the one after conv+ReLU
+    s = torch.randn(2 * c, h, w // 2 + 1, generator=g)
+    z = torch.complex(s.view(c, 2, h, -1)[:, 0].contiguous(), s.view(c, 2, h, -1)[:, 1].contiguous())
+    ref = torch.fft.irfftn(z, s=(h, w), dim=(-2, -1), norm="ortho")
+    _close(eng.irfft2(s, w), ref, 2e-5, what=f"irfft2 {h}x{w}")
+
+
+def test_fft_impulse_and_roundtrip(eng):
+    x = torch.zeros(2, 24, 20)
+    x[0, 0, 0] = 1.0
+    x[1, 5, 7] = 2.0
+    spec = eng.rfft2(x).cpu()
+    assert (spec[0] - 1 / (24 * 20) ** 0.5).abs().max() < 1e-6 and spec[1].abs().max() < 1e-6   # flat real spectrum
+    _close(eng.irfft2(spec, 20), x, 2e-6, what="fft round trip")
+
+
+def test_attention(eng):
+    g = torch.Generator().manual_seed(9)
+    n, t, heads, hd = 3, 57, 8, 40
+    d = heads * hd
+    qk = torch.randn(n * t, 2 * d, generator=g)
+    v = torch.randn(n * t, d, generator=g)
+    q = qk[:, :d].view(n, t, heads, hd).transpose(1, 2)
+    k = qk[:, d:].view(n, t, heads, hd).transpose(1, 2)
+    vv = v.view(n, t, heads, hd).transpose(1, 2)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, -1) @ vv).transpose(1, 2).reshape(n * t, d)
+    _close(eng.attention(qk, v, n, t, heads, hd), ref, 2e-5, what="attention")
+
+
+def test_bilateral17_matches_cv2(eng):
+    import cv2
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (150, 203, 3), dtype=np.uint8)
+    smooth = cv2.GaussianBlur(img, (0, 0), 3)
+    for im in (img, smooth):
+        ref = cv2.bilateralFilter(im, 17, 80, 80)
+        out = eng.bilateral17(im).cpu().numpy()
+        diff = np.abs(out.astype(int) - ref.astype(int))
+        assert diff.max() <= 1 and (diff != 0).mean() < 1e-4, (diff.max(), (diff != 0).sum())
