@@ -1,0 +1,47 @@
+"""LaMa masked positional encoding tables on the host (behaviour of LamaFourier.load_masked_position_encoding,
+inpainting/inpainting_lama_mpe.py:751-815) with binary morphology instead of float filter2D passes:
+the mask is reduced to 256x256 (INTER_AREA, any coverage counts), the known region is dilated 3x3 step by step;
+pos = step at which a hole pixel is reached, direct[k] = reached from the k-th 2x2 diagonal neighbourhood."""
+from __future__ import annotations
+
+import cv2
+import numpy as np
+
+_BOX = np.ones((3, 3), np.uint8)
+_CORNERS = [np.array(k, np.uint8) for k in (
+    [[1, 1, 0], [1, 1, 0], [0, 0, 0]], [[0, 0, 0], [1, 1, 0], [1, 1, 0]],
+    [[0, 1, 1], [0, 1, 1], [0, 0, 0]], [[0, 0, 0], [0, 1, 1], [0, 1, 1]])]
+
+
+def _grow(known: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    # correlation with a 0/1 kernel followed by ">0" == cv2.dilate with the same kernel; borders REFLECT_101 like filter2D
+    p = cv2.copyMakeBorder(known, 1, 1, 1, 1, cv2.BORDER_REFLECT_101)
+    return cv2.dilate(p, kernel, borderType=cv2.BORDER_CONSTANT, borderValue=0)[1:-1, 1:-1]
+
+
+def mpe_tables(mask01: np.ndarray):
+    """mask01 [H,W] with 1 inside the hole -> (rel_pos int32 [H,W] in [0,127], direct int32 [H,W,4] in {0,1})."""
+    m = (np.asarray(mask01, dtype=np.float32) * 255).astype(np.uint8)
+    H, W = m.shape
+    small = cv2.resize(m, (256, 256), interpolation=cv2.INTER_AREA)
+    known = (small == 0).astype(np.uint8)
+    pos = np.zeros((256, 256), np.int32)
+    direct = np.zeros((256, 256, 4), np.int32)
+    step = 0
+    if known.any():
+        while not known.all():
+            step += 1
+            grown = _grow(known, _BOX)
+            fresh = (grown > 0) & (known == 0)
+            pos[fresh] = step
+            for k, ker in enumerate(_CORNERS):
+                direct[(_grow(known, ker) > 0) & (known == 0), k] = 1
+            known = grown
+    rel = np.clip((pos / 128.0 * 128).astype(np.int32), 0, 127)
+    if (H, W) != (256, 256):
+        rel = cv2.resize(rel, (W, H), interpolation=cv2.INTER_NEAREST)
+        direct = cv2.resize(direct, (W, H), interpolation=cv2.INTER_NEAREST)
+        hole = m != 0
+        rel = np.where(hole, rel, 0)
+        direct = np.where(hole[..., None], direct, 0)
+    return rel.astype(np.int32), direct.astype(np.int32)
