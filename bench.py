@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Headline benchmark: pages/sec for detect (DBNet-ConvNeXt) + OCR (48px CTC, 32 lines/page) + inpaint (LaMa-MPE) on
+synthetic 2048x1536 RGB pages -- BASELINE.json `metric`, workload = configs[1] (32 pages per GPU; under torchrun every
+rank takes 32 pages of the round-robin shard, i.e. configs[2] at 8 GPUs; weak scaling).
+
+  python bench.py --gpus N --steps K --warmup W                      # ours (hand-written CUDA through the C ABI)
+  python bench.py --impl reference --gpus N --steps K --warmup W     # CPU restatement of the reference path (oracle/)
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs staged in HBM, CUDA-event timed, max over
+ranks); `e2e` = the same pages through the plugin `infer` calls with pinned HOST buffers (H2D/D2H and host glue inside
+the timed region); `roofline` = dominant kernel class from per-launch CUDA events recorded during the timed region;
+`cpu_baseline` = the oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "manga-image-translator_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PAGE_H, PAGE_W, LINES = 2048, 1536, 32
+PAGES_PER_GPU = 32
+VOCAB = 46000
+METRIC = "pages/sec (2048x1536, detect+OCR+inpaint)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def build_weights():
+    from oracle import weights
+    db = weights.dbnet_weights()
+    db = {k: v.clone() for k, v in db.items()}
+    # random weights emit per-pixel noise; bias the binarize head so that the detector's host post-processing sees a sparse
+    # map (tens of candidate blobs, like a real page) instead of ~10^6 one-pixel contours.  Parity tests use unbiased weights.
+    db["conv_db.binarize.4.bias"] -= 8.0
+    return dict(dbnet=db, ocr=weights.ocr_weights(VOCAB), dictionary=weights.synthetic_dictionary(VOCAB),
+                lama=weights.lama_weights(9), mpe=weights.mpe_weights())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_page(W, page, boxes, mask):
+    """One page through the CPU restatement of the reference path (all host threads).  Returns seconds."""
+    from mit_b200 import synth
+    from oracle import pipeline_ref
+    t0 = time.perf_counter()
+    pipeline_ref.detector_infer(W["dbnet"], page, 2048, 0.5, 0.7, 2.3)
+    pipeline_ref.ocr_infer(W["ocr"], W["dictionary"], page, synth.make_quads(boxes), 0.0)
+    pipeline_ref.lama_infer(W["lama"], W["mpe"], page, mask, 2048)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from mit_b200 import synth
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    W = build_weights()
+    page, boxes, mask = synth.make_page(0, PAGE_H, PAGE_W, LINES)
+    for _ in range(args.warmup):
+        cpu_reference_page(W, page, boxes, mask)
+    t = [cpu_reference_page(W, *synth.make_page(i, PAGE_H, PAGE_W, LINES)) for i in range(args.steps)]
+    total = sum(t)
+    value = args.steps / total
+    sample = "1 page (detect+32-line OCR+inpaint) per step; oracle port of the reference CPU path, torch CPU fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "2048x1536 pages, dbnet_convnext+48px_ctc(32 lines)+lama_mpe; bounded sample: 1 page per step"},
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from mit_b200 import synth
+    from mit_b200.pipeline import HotPath, gather_results, shard_indices
+    torch.set_grad_enabled(False)
+    dev = f"cuda:{local_rank}"
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    W = build_weights()
+    hp = HotPath(dev, W["dbnet"], W["ocr"], W["dictionary"], W["lama"], W["mpe"])
+    eng = hp.engine
+    n_pages = args.pages
+    idxs = shard_indices(n_pages * world, rank, world)
+    t0 = time.time()
+    pages = []
+    for i in idxs:
+        p, b, m = synth.make_page(i, PAGE_H, PAGE_W, LINES)
+        # pinned host buffers: the e2e path copies from these every step
+        pp = torch.empty(p.shape, dtype=torch.uint8).pin_memory(); pp.copy_(torch.from_numpy(p))
+        pm = torch.empty(m.shape, dtype=torch.uint8).pin_memory(); pm.copy_(torch.from_numpy(m))
+        pages.append((pp.numpy(), b, pm.numpy()))
+    staged = [hp.stage(p, synth.make_quads(b), m) for p, b, m in pages]
+    staged_bytes = sum(s.bytes for s in staged)
+    log(f"[rank {rank}] {len(pages)} pages generated+staged in {time.time() - t0:.1f}s ({staged_bytes / 1e9:.2f} GB resident)")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    result_buf = torch.empty((len(pages), PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
+
+    def resident_step():
+        for i, sp in enumerate(staged):
+            db, dmask, ocr, out = hp.run_resident(sp)
+        return out
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    eng.lib.mitb_profile_enable(eng._h, 1)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        resident_step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    launches = eng.launches - launches0
+    prof = json.loads(eng.lib.mitb_profile_report(eng._h).decode())
+    eng.lib.mitb_profile_enable(eng._h, 0)
+    value = args.steps * n_pages * world / (ms_total / 1e3)
+
+    # ---------------- end-to-end through the plugin API with host buffers (`e2e`)
+    def e2e_step():
+        outs = []
+        for (p, b, m) in pages:
+            r = hp.process_page(p, synth.make_quads(b), m)
+            outs.append(r)
+        if world > 1:   # results back to every rank (rank 0 consumes them): inpainted pages + raw masks over NCCL
+            for i, r in enumerate(outs):
+                result_buf[i].copy_(torch.from_numpy(r.inpainted), non_blocking=True)
+            gather_results(result_buf, world)
+        return outs
+
+    e2e_warm = min(args.warmup, 1) if args.fast_e2e else args.warmup
+    for _ in range(e2e_warm):
+        e2e_step()
+    barrier()
+    eng.h2d_bytes = eng.d2h_bytes = 0
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
+    e2e_value = args.steps * n_pages * world / (e2e_ms / 1e3)
+    h2d, d2h = eng.h2d_bytes / args.steps, eng.d2h_bytes / args.steps
+
+    # ---------------- roofline of the dominant kernel class (CUDA events recorded per launch during the timed region)
+    peaks = load_peaks()
+    roof = None
+    if prof:
+        total_kernel_ms = sum(v["ms"] for v in prof.values())
+        name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        sec = top["ms"] / 1e3
+        tensor_bound = name.startswith("conv")
+        if tensor_bound:
+            achieved, peak, unit = top["flops"] / sec / 1e12, peaks["tf_sust"], "TFLOP/s"
+        else:
+            achieved, peak, unit = top["bytes"] / sec / 1e9, peaks["hbm"], "GB/s"
+        roof = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": achieved / peak, "traffic": None, "peak_source": peaks["src"] + (" bf16 sustained" if tensor_bound else " copy"),
+                "launches": top["launches"], "avg_launch_ms": top["ms"] / max(1, top["launches"]),
+                "share_of_kernel_time": top["ms"] / total_kernel_ms,
+                "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                                "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+
+    # ---------------- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        p, b, m = pages[0]
+        sec = cpu_reference_page(W, p, b, m)
+        cpu = {"value": 1.0 / sec, "unit": "pages/s", "cores": cores, "kind": "port",
+               "sample": "1 of the 32 pages (detect incl. cv2 bilateral + 32-line OCR + LaMa-MPE), oracle port of the reference CPU path, one run"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{n_pages} pages 2048x1536 per GPU, dbnet_convnext + 48px_ctc ({LINES} lines/page, V={VOCAB}) + lama_mpe, "
+                                   f"round-robin sharded over {world} GPU(s)", "pages_per_step": n_pages * world,
+                       "l2": f"inputs larger than L2 ({staged_bytes / 1e9:.1f} GB of staged pages per step)",
+                       "weights": "seeded random (no checkpoints offline)"},
+            "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }), flush=True)
+    hp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pages", type=int, default=PAGES_PER_GPU, help="pages per GPU per step (BASELINE configs[1]: 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast-e2e", action="store_true", help="one warm-up step for the e2e leg (development only)")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

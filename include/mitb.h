@@ -43,6 +43,12 @@ const char* mitb_version(void);
 long long mitb_launch_count(const mitb_ctx* ctx);      /* kernels launched by this context so far */
 size_t mitb_workspace_bytes(const mitb_ctx* ctx);      /* current activation workspace size */
 
+/* Per-launch CUDA-event timing aggregated per kernel class (for bench.py's roofline block). report() synchronises the
+ * recorded events, clears them and returns a JSON object {"class": {"launches","ms","flops","bytes"}, ...} valid until
+ * the next call. */
+int mitb_profile_enable(mitb_ctx* ctx, int on);
+const char* mitb_profile_report(mitb_ctx* ctx);
+
 /* ---- DBNet-ConvNeXt text detector (state_dict keys of DBNetConvNext, dbnet_convnext.py:450-472) ---- */
 int mitb_dbnet_load(mitb_ctx* ctx, const mitb_tensor* weights, int n_weights);
 int mitb_dbnet_unload(mitb_ctx* ctx);
@@ -75,6 +81,12 @@ int mitb_lama_unload(mitb_ctx* ctx);
  * (NULL for the large model); out [n,3,h,w] = pred*mask + (1-mask)*img. */
 int mitb_lama_forward(mitb_ctx* ctx, const float* img, const float* mask, const int32_t* rel_pos,
                       const int32_t* direct, int n, int h, int w, float* out, void* stream);
+
+/* Same, with the MPE tables at the 256x256 working resolution of load_masked_position_encoding (:751-815): rel_pos256
+ * [n,256,256], direct256 [n,256,256,4]; the INTER_NEAREST upsampling and the zeroing outside the hole (:807-813) happen
+ * inside the kernel that adds the embeddings. */
+int mitb_lama_forward_mpe256(mitb_ctx* ctx, const float* img, const float* mask, const int32_t* rel_pos256,
+                             const int32_t* direct256, int n, int h, int w, float* out, void* stream);
 
 /* ---- standalone operators (parity tests and micro-benchmarks; same kernels the networks use) ---- */
 /* General conv through the implicit-GEMM kernel.  x [n,cin,h,w], wt PyTorch layout [cout,cin,kh,kw], y [n,cout,ho,wo]

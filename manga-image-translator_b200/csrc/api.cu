@@ -18,7 +18,7 @@ static thread_local std::string g_create_error;
 #define API_END(ctx)                                                       \
     return 0;                                                              \
   } catch (const std::exception& ex) {                                     \
-    (ctx)->c.err = ex.what(); g_launch_counter = nullptr;                  \
+    (ctx)->c.err = ex.what(); g_launch_counter = nullptr; g_prof = nullptr;                  \
     (ctx)->c.ws.dry = false;                                               \
     cudaGetLastError();                                                    \
     return 2;                                                              \
@@ -68,6 +68,18 @@ void mitb_destroy(mitb_ctx* ctx) {
 const char* mitb_last_error(const mitb_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_error.c_str(); }
 long long mitb_launch_count(const mitb_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 size_t mitb_workspace_bytes(const mitb_ctx* ctx) { return ctx ? ctx->c.ws.cap : 0; }
+
+int mitb_profile_enable(mitb_ctx* ctx, int on) {
+  API_BEGIN(ctx)
+  ctx->c.prof.on = on != 0;
+  API_END(ctx)
+}
+const char* mitb_profile_report(mitb_ctx* ctx) {
+  if (!ctx) return "{}";
+  cudaSetDevice(ctx->c.device);
+  ctx->c.prof_json = profiler_report(ctx->c.prof);
+  return ctx->c.prof_json.c_str();
+}
 
 int mitb_dbnet_load(mitb_ctx* ctx, const mitb_tensor* w, int n) {
   API_BEGIN(ctx)
@@ -144,7 +156,15 @@ int mitb_lama_forward(mitb_ctx* ctx, const float* img, const float* mask, const 
   API_BEGIN(ctx)
   MITB_CHECK(ctx->c.lama, "lama: forward before load");
   MITB_CHECK(img && mask && out, "lama: null buffer");
-  lama_run(ctx->c, *ctx->c.lama, img, mask, rel_pos, direct, n, h, w, out, (cudaStream_t)stream);
+  lama_run(ctx->c, *ctx->c.lama, img, mask, rel_pos, direct, h, w, n, h, w, out, (cudaStream_t)stream);
+  API_END(ctx)
+}
+int mitb_lama_forward_mpe256(mitb_ctx* ctx, const float* img, const float* mask, const int32_t* rel_pos256,
+                             const int32_t* direct256, int n, int h, int w, float* out, void* stream) {
+  API_BEGIN(ctx)
+  MITB_CHECK(ctx->c.lama, "lama: forward before load");
+  MITB_CHECK(img && mask && out && rel_pos256 && direct256, "lama: null buffer");
+  lama_run(ctx->c, *ctx->c.lama, img, mask, rel_pos256, direct256, 256, 256, n, h, w, out, (cudaStream_t)stream);
   API_END(ctx)
 }
 

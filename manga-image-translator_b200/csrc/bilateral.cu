@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(BTX * BTY) bilateral17_kernel(const uint8_t* i
 void launch_bilateral17(const uint8_t* img, int h, int w, uint8_t* out, cudaStream_t st) {
   bilateral_init();
   dim3 block(BTX, BTY), grid((w + BTX - 1) / BTX, (h + BTY - 1) / BTY);
+  ProfScope ps("bilateral17", 197.0 * 12 * h * w, 6.0 * h * w, st);
   bilateral17_kernel<<<grid, block, 0, st>>>(img, h, w, out, g_bilateral_n);
   count_launch();
   CUDA_OK(cudaGetLastError());

@@ -451,10 +451,15 @@ void launch_conv(const ConvOp& op, cudaStream_t st) {
     for (int t = 0; t < op.ntaps; ++t)
       MITB_CHECK(-op.tdy[t] < op.in.H && -op.tdx[t] < op.in.W, "reflect padding wider than the image");
   }
-  if (!op.stat_max && conv_tc_supported(op)) { launch_conv_tc(op, st); return; }
   ConvKParams p; fill_params(op, p);
   if (p.M == 0) return;
   const int Cout = op.out.C;
+  // algorithmic work of this launch: 2*M*K*Cout flops; bytes = input view + weights + output (+ fused residual reads)
+  const double flops = 2.0 * p.M * (double)p.K * Cout;
+  const double bytes = 4.0 * ((double)op.in.pixels() * op.in.C + (double)p.K * Cout +
+                              (double)p.M * Cout * ((op.stat_max ? 0 : 1) + (op.add0.p ? 1 : 0) + (op.add1.p ? 1 : 0)));
+  if (!op.stat_max && conv_tc_supported(op)) { ProfScope ps("conv_tc", flops, bytes, st); launch_conv_tc(op, st); return; }
+  ProfScope ps(op.stat_max ? "conv_simt_rowstat" : (Cout <= 4 && !op.in.planar && op.ldw == 4) ? "conv_fewout" : "conv_simt", flops, bytes, st);
   if (op.stat_max) {
     MITB_CHECK(!op.in.planar, "row-stat epilogue expects NHWC input");
     dim3 grid((p.M + BM - 1) / BM, (Cout + 127) / 128);

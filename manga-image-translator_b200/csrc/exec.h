@@ -46,9 +46,9 @@ void run_with_workspace(Ctx& ctx, cudaStream_t st, F body) {
   ws.dry = false; ws.off = 0;
   ctx.ensure_ws(need);
   ws.peak = 0;
-  g_launch_counter = &ctx.launches;
+  g_launch_counter = &ctx.launches; g_prof = &ctx.prof;
   { Exec e{ctx, st, false}; body(e); }
-  g_launch_counter = nullptr;
+  g_launch_counter = nullptr; g_prof = nullptr;
 }
 
 }  // namespace mitb

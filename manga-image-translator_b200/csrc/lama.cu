@@ -121,8 +121,8 @@ void run_ffc_layer(Exec& e, const FfcLayer& l, const View& X, const View& Y, con
   ws.release(mk);
 }
 
-void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const int* rel_pos, const int* direct, int n, int h,
-              int w, float* out, cudaStream_t st) {
+void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const int* rel_pos, const int* direct, int th,
+              int tw, int n, int h, int w, float* out, cudaStream_t st) {
   MITB_CHECK(n >= 1 && h % 8 == 0 && w % 8 == 0 && h >= 32 && w >= 32, "lama: input %dx%d must be a multiple of 8 (>=32)", h, w);
   MITB_CHECK(!m.use_mpe || (rel_pos && direct), "lama_mpe needs the rel_pos/direct tables");
   run_with_workspace(ctx, st, [&](Exec& e) {
@@ -134,7 +134,7 @@ void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const
       View x4 = ws.view(n, h, w, 4), s1 = ws.view(n, h, w, 64), s2 = ws.view(n, h / 2, w / 2, 128), s3 = ws.view(n, h / 4, w / 4, 256);
       if (!e.dry) launch_lama_pack_input(img, mask, n, h, w, x4, st);
       { ConvOp op = Exec::op_from(m.stem, x4, s1, 1, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
-      if (m.use_mpe && !e.dry) launch_mpe_add(s1, rel_pos, direct, m.mpe_table, m.mpe_dirw, m.a5, m.a6, st);
+      if (m.use_mpe && !e.dry) launch_mpe_add(s1, rel_pos, direct, th, tw, mask, m.mpe_table, m.mpe_dirw, m.a5, m.a6, st);
       { ConvOp op = Exec::op_from(m.d1, s1, s2, 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
       { ConvOp op = Exec::op_from(m.d2, s2, s3, 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
       { ConvOp op = Exec::op_from(m.d3l, s3, X.slice(0, 128), 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }

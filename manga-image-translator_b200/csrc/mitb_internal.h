@@ -101,8 +101,8 @@ void launch_attention(const float* qk /*[N*T,2D]*/, const float* v /*[N*T,D]*/, 
                       int N, int T, int heads, int hd, cudaStream_t st);
 void launch_lama_pack_input(const float* img, const float* mask, int N, int H, int W, const View& dst, cudaStream_t st);
 void launch_lama_blend(const View& pred, const float* img, const float* mask, float* out, cudaStream_t st);
-void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, const float* table, const float* dirw,
-                    float a5, float a6, cudaStream_t st);
+void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, int th, int tw, const float* mask,
+                    const float* table, const float* dirw, float a5, float a6, cudaStream_t st);
 
 // real 2-D FFT of planar tensors, norm='ortho' (spectrum planes interleaved c0_re,c0_im,c1_re,...)
 struct FftPlan;
@@ -167,11 +167,25 @@ void ocr_run(Ctx&, OcrModel&, const float* x_nchw, const uint8_t* x_u8, int n, i
 int ocr_vocab(const OcrModel&);
 LamaModel* lama_build(Ctx&, const Weights&);
 void lama_free(LamaModel*);
-void lama_run(Ctx&, LamaModel&, const float* img, const float* mask, const int* rel_pos, const int* direct, int n,
-              int h, int w, float* out, cudaStream_t st);
+void lama_run(Ctx&, LamaModel&, const float* img, const float* mask, const int* rel_pos, const int* direct, int th,
+              int tw, int n, int h, int w, float* out, cudaStream_t st);
+
+struct Profiler {
+  struct Rec { const char* kind; double flops, bytes; cudaEvent_t a, b; };
+  bool on = false; std::vector<Rec> recs; std::vector<cudaEvent_t> pool;
+};
+extern thread_local Profiler* g_prof;
+struct ProfScope {          // records an event pair around the launches issued in its scope (no-op unless profiling)
+  ProfScope(const char* kind, double flops, double bytes, cudaStream_t st);
+  ~ProfScope();
+  Profiler* p_; cudaStream_t st_;
+};
+std::string profiler_report(Profiler& p);
 
 struct Ctx {
   int device = 0;
+  Profiler prof;
+  std::string prof_json;
   std::string err;
   Arena ws;
   DbnetModel* dbnet = nullptr; OcrModel* ocr = nullptr; LamaModel* lama = nullptr;

@@ -53,6 +53,7 @@ void launch_layernorm(const View& in, const View& out, const float* w, const flo
   MITB_CHECK(C <= 1024 && out.C == C, "layernorm: C=%d unsupported", C);
   const int per = (C + 31) / 32;
   dim3 grid((unsigned)((rows + 7) / 8));
+  ProfScope ps("layernorm", 8.0 * rows * C, 8.0 * rows * C, st);
   float* o2 = out2 ? out2->p : nullptr; int o2cs = out2 ? out2->cs : 0, o2off = out2 ? out2->coff : 0;
 #define LN_CASE(P) layernorm_kernel<P><<<grid, 256, 0, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, w, b, eps, rows, C, pe, o2, o2cs, o2off, T)
   if (per <= 4) LN_CASE(4); else if (per <= 8) LN_CASE(8); else if (per <= 10) LN_CASE(10);
@@ -165,6 +166,7 @@ void launch_dwconv7_ln(const View& in, const View& out, const float* wdw, const 
   int py = 256 / tx; if (py < 1) py = 1;
   dim3 block(tx, py), grid((in.W + DW_TX - 1) / DW_TX, (in.H + py - 1) / py, in.N);
   const size_t smem = (size_t)py * (tx / 32) * DW_TX * sizeof(float);
+  ProfScope ps("dwconv7_ln", (98.0 + 8.0) * in.pixels() * C, 8.0 * in.pixels() * C + 4.0 * 51 * C, st);
   dwconv7_ln_kernel<<<grid, block, smem, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, wdw, bdw, lnw, lnb, eps,
                                                in.N, in.H, in.W, C);
   LAUNCH_END();
@@ -338,6 +340,7 @@ void launch_attention(const float* qk, const float* v, float* out, int N, int T,
   MITB_CHECK(smem <= 200 * 1024, "attention: sequence too long (T=%d)", T);
   static bool attr_set = false;
   if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+  ProfScope ps("attention", 4.0 * N * heads * (double)T * T * hd, 16.0 * N * T * heads * hd, st);
   attention_kernel<<<N * heads, threads, smem, st>>>(qk, v, out, T, heads, hd, 1.0f / sqrtf((float)hd));
   LAUNCH_END();
 }
@@ -381,14 +384,30 @@ void launch_lama_blend(const View& pred, const float* img, const float* mask, fl
   LAUNCH_END();
 }
 
-// x_l += table[rel_pos]*alpha5 ; x_l += (direct @ W)*alpha6  (inpainting_lama_mpe.py:609-612, 625-632)
-__global__ void mpe_add_kernel(float* x, int cs, int coff, long npix, const int* rel_pos, const int* direct,
-                               const float* table, const float* dirw, float a5, float a6) {
+// x_l += table[rel_pos]*alpha5 ; x_l += (direct @ W)*alpha6  (inpainting_lama_mpe.py:609-612, 625-632).
+// The integer tables may be given at the 256x256 working resolution of load_masked_position_encoding (:751-815); the
+// kernel then does its INTER_NEAREST upsampling (sx = min(floor(x * 1/(W/tw)), tw-1), cv2 semantics) and the
+// "zero outside the hole" step (:809-813) on the fly instead of materialising 5 full-resolution int planes on the host.
+__global__ void mpe_add_kernel(float* x, int cs, int coff, int N, int H, int W, const int* rel_pos, const int* direct, int th,
+                               int tw, const float* mask, const float* table, const float* dirw, float a5, float a6) {
+  const long npix = (long)N * H * W;
   const long total = npix * 16;                  // 64 channels = 16 float4 per pixel
+  const bool lowres = th != H || tw != W;
+  const double ify = 1.0 / ((double)H / (double)th), ifx = 1.0 / ((double)W / (double)tw);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i & 15) * 4; const long pix = i >> 4;
-    const int rp = rel_pos[pix];
-    const int4 d = *reinterpret_cast<const int4*>(direct + pix * 4);
+    long tpix = pix;
+    bool hole = true;
+    if (lowres) {
+      const int n = (int)(pix / ((long)H * W)); const long r = pix - (long)n * H * W;
+      const int y = (int)(r / W), xx = (int)(r - (long)y * W);
+      const int sy = min((int)floor((double)y * ify), th - 1), sx = min((int)floor((double)xx * ifx), tw - 1);
+      tpix = ((long)n * th + sy) * tw + sx;
+      hole = mask[pix] != 0.f;
+    }
+    const int rp = hole ? rel_pos[tpix] : 0;
+    int4 d = make_int4(0, 0, 0, 0);
+    if (hole) d = *reinterpret_cast<const int4*>(direct + tpix * 4);
     float4 v = *reinterpret_cast<float4*>(x + pix * cs + coff + c);
     const float4 e = *reinterpret_cast<const float4*>(table + rp * 64 + c);
     const float4 w0 = *reinterpret_cast<const float4*>(dirw + 0 * 64 + c), w1 = *reinterpret_cast<const float4*>(dirw + 1 * 64 + c);
@@ -402,12 +421,12 @@ __global__ void mpe_add_kernel(float* x, int cs, int coff, long npix, const int*
     *reinterpret_cast<float4*>(x + pix * cs + coff + c) = v;
   }
 }
-void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, const float* table, const float* dirw, float a5,
-                    float a6, cudaStream_t st) {
+void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, int th, int tw, const float* mask, const float* table,
+                    const float* dirw, float a5, float a6, cudaStream_t st) {
   MITB_CHECK(x.C == 64 && x.cs % 4 == 0 && x.coff % 4 == 0, "mpe_add expects the 64-channel stem output");
   const long total = (long)x.pixels() * 16;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  mpe_add_kernel<<<blocks, 256, 0, st>>>(x.p, x.cs, x.coff, (long)x.pixels(), rel_pos, direct, table, dirw, a5, a6);
+  mpe_add_kernel<<<blocks, 256, 0, st>>>(x.p, x.cs, x.coff, x.N, x.H, x.W, rel_pos, direct, th, tw, mask, table, dirw, a5, a6);
   LAUNCH_END();
 }
 

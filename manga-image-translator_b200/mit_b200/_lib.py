@@ -31,6 +31,8 @@ SIGNATURES = {
     "mitb_version": (C.c_char_p, []),
     "mitb_launch_count": (C.c_longlong, [P]),
     "mitb_workspace_bytes": (C.c_size_t, [P]),
+    "mitb_profile_enable": (I, [P, I]),
+    "mitb_profile_report": (C.c_char_p, [P]),
     "mitb_dbnet_load": (I, [P, C.POINTER(MitbTensor), I]),
     "mitb_dbnet_unload": (I, [P]),
     "mitb_dbnet_forward": (I, [P, P, I, I, I, P, P, P]),
@@ -43,6 +45,7 @@ SIGNATURES = {
     "mitb_lama_load": (I, [P, C.POINTER(MitbTensor), I]),
     "mitb_lama_unload": (I, [P]),
     "mitb_lama_forward": (I, [P, P, P, P, P, I, I, I, P, P]),
+    "mitb_lama_forward_mpe256": (I, [P, P, P, P, P, I, I, I, P, P]),
     "mitb_op_conv2d": (I, [P, P, I, I, I, I, P, I, I, I, I, I, I, I, I, P, I, P, P, I, P, P]),
     "mitb_op_conv_transpose2d": (I, [P, P, I, I, I, I, P, I, I, I, I, P, I, P, P]),
     "mitb_op_dwconv7_ln": (I, [P, P, I, I, I, I, P, P, P, P, F, P, P]),

@@ -33,6 +33,20 @@ class Engine:
             raise MitbError(self.lib.mitb_last_error(None).decode())
         self._h = h
         self._keep = {}
+        self.h2d_bytes = 0      # bytes moved host->device / device->host through h2d()/d2h() (bench.py e2e accounting)
+        self.d2h_bytes = 0
+
+    def h2d(self, t, dtype=None) -> torch.Tensor:
+        """Host array/tensor -> device tensor (async when the source is pinned); counts the bytes."""
+        t = torch.as_tensor(t)
+        if t.device.type == "cpu":
+            self.h2d_bytes += t.numel() * t.element_size()
+        t = t.to(self.device, non_blocking=True)
+        return t if dtype is None else t.to(dtype)
+
+    def d2h(self, t: torch.Tensor) -> np.ndarray:
+        self.d2h_bytes += t.numel() * t.element_size()
+        return t.cpu().numpy()
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -138,7 +152,8 @@ class Engine:
     def unload_lama(self):
         self._check(self.lib.mitb_lama_unload(self._h))
 
-    def lama_forward(self, img: torch.Tensor, mask: torch.Tensor, rel_pos=None, direct=None):
+    def lama_forward(self, img: torch.Tensor, mask: torch.Tensor, rel_pos=None, direct=None, tables256=False):
+        """rel_pos/direct: full-resolution MPE tables [n,h,w]/[n,h,w,4], or (tables256=True) the 256x256 ones."""
         img = img.to(self.device, torch.float32).contiguous()
         mask = mask.to(self.device, torch.float32).contiguous()
         n, _, h, w = img.shape
@@ -146,8 +161,8 @@ class Engine:
             rel_pos = torch.as_tensor(rel_pos).to(self.device, torch.int32).contiguous()
             direct = torch.as_tensor(direct).to(self.device, torch.int32).contiguous()
         out = torch.empty_like(img)
-        self._check(self.lib.mitb_lama_forward(self._h, _ptr(img), _ptr(mask), _ptr(rel_pos), _ptr(direct), n, h, w,
-                                               _ptr(out), self._stream()))
+        fn = self.lib.mitb_lama_forward_mpe256 if (tables256 and rel_pos is not None) else self.lib.mitb_lama_forward
+        self._check(fn(self._h, _ptr(img), _ptr(mask), _ptr(rel_pos), _ptr(direct), n, h, w, _ptr(out), self._stream()))
         return out
 
     # ------------------------------------------------------------------ standalone operators (tests / micro-benchmarks)

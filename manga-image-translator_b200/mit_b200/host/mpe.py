@@ -19,10 +19,14 @@ def _grow(known: np.ndarray, kernel: np.ndarray) -> np.ndarray:
     return cv2.dilate(p, kernel, borderType=cv2.BORDER_CONSTANT, borderValue=0)[1:-1, 1:-1]
 
 
-def mpe_tables(mask01: np.ndarray):
-    """mask01 [H,W] with 1 inside the hole -> (rel_pos int32 [H,W] in [0,127], direct int32 [H,W,4] in {0,1})."""
+def mpe_tables_256(mask01: np.ndarray):
+    """The tables at the 256x256 working resolution (before the reference's INTER_NEAREST upsampling, which libmitb does on
+    the device): (rel_pos int32 [256,256] in [0,127], direct int32 [256,256,4])."""
     m = (np.asarray(mask01, dtype=np.float32) * 255).astype(np.uint8)
-    H, W = m.shape
+    return _tables_256(m)
+
+
+def _tables_256(m: np.ndarray):
     small = cv2.resize(m, (256, 256), interpolation=cv2.INTER_AREA)
     known = (small == 0).astype(np.uint8)
     pos = np.zeros((256, 256), np.int32)
@@ -38,6 +42,14 @@ def mpe_tables(mask01: np.ndarray):
                 direct[(_grow(known, ker) > 0) & (known == 0), k] = 1
             known = grown
     rel = np.clip((pos / 128.0 * 128).astype(np.int32), 0, 127)
+    return rel.astype(np.int32), direct
+
+
+def mpe_tables(mask01: np.ndarray):
+    """mask01 [H,W] with 1 inside the hole -> (rel_pos int32 [H,W] in [0,127], direct int32 [H,W,4] in {0,1})."""
+    m = (np.asarray(mask01, dtype=np.float32) * 255).astype(np.uint8)
+    H, W = m.shape
+    rel, direct = _tables_256(m)
     if (H, W) != (256, 256):
         rel = cv2.resize(rel, (W, H), interpolation=cv2.INTER_NEAREST)
         direct = cv2.resize(direct, (W, H), interpolation=cv2.INTER_NEAREST)

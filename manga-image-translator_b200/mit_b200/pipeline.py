@@ -1,0 +1,121 @@
+"""Page-level driver of the hot path: detect -> OCR -> inpaint for a list of pages on ONE GPU, plus the multi-GPU
+sharding used by bench.py (round-robin page scatter, results all-gathered to every rank over NCCL; the reference itself
+runs pages strictly one at a time, manga_translator/manga_translator.py:1491-1519).
+
+Two entry points per page:
+  * ``process_page``      -- the user-facing path: host numpy in, host results out, through the three plugin ``infer`` calls
+                             (what `dispatch()` does in the reference, detection/__init__.py:35-40 etc.);
+  * ``run_resident``      -- the same device work with inputs already staged in HBM (kernel-throughput measurement).
+"""
+from __future__ import annotations
+
+import asyncio
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import plugins, synth
+from .compat import InpainterConfig, OcrConfig, chunks
+from .engine import get_engine
+from .host import mpe
+
+
+@dataclass
+class PageResult:
+    textlines: list
+    raw_mask: np.ndarray
+    ocr_lines: list
+    inpainted: np.ndarray
+
+
+@dataclass
+class StagedPage:
+    page_u8: torch.Tensor                   # [H,W,3] uint8 on device
+    ocr_chunks: List[torch.Tensor]          # uint8 [n,48,wp,3] on device
+    img: torch.Tensor                       # [1,3,H,W] fp32, pre-masked
+    mask: torch.Tensor                      # [1,1,H,W] fp32 {0,1}
+    rel_pos: Optional[torch.Tensor]
+    direct: Optional[torch.Tensor]
+    bytes: int = 0
+
+
+class HotPath:
+    """The three plugins bound to one CUDA device, constructed with injected (seeded) weights or checkpoint files."""
+
+    def __init__(self, device: str, dbnet_sd=None, ocr_sd=None, dictionary=None, lama_sd=None, mpe_sd=None, large=False,
+                 detect_size=2048, inpainting_size=2048):
+        self.device = device
+        self.detect_size, self.inpainting_size = detect_size, inpainting_size
+        if dbnet_sd is not None:
+            plugins.DBConvNextDetector.set_state_dict(dbnet_sd)
+        if ocr_sd is not None:
+            plugins.Model48pxCTCOCR.set_state_dict(ocr_sd)
+            plugins.Model48pxCTCOCR.set_dictionary(dictionary)
+        inp_cls = plugins.LamaLargeInpainter if large else plugins.LamaMPEInpainter
+        if lama_sd is not None:
+            inp_cls.set_state_dict({"gen_state_dict": lama_sd, "str_state_dict": mpe_sd})
+        self.det, self.ocr, self.inp = plugins.DBConvNextDetector(), plugins.Model48pxCTCOCR(), inp_cls()
+        self.use_mpe = not large
+        for p in (self.det, self.ocr, self.inp):
+            asyncio.run(p.load(device))
+        self.engine = get_engine(device)
+
+    def close(self):
+        for p in (self.det, self.ocr, self.inp):
+            asyncio.run(p.unload())
+
+    # ------------------------------------------------------------------ user-facing path (host buffers)
+    def process_page(self, page: np.ndarray, quads, mask: np.ndarray) -> PageResult:
+        textlines, raw_mask, _ = asyncio.run(self.det.infer(page, self.detect_size, 0.5, 0.7, 2.3))
+        lines = asyncio.run(self.ocr.infer(page, quads, OcrConfig(prob=0.0)))
+        out = asyncio.run(self.inp.infer(page, mask, InpainterConfig(), self.inpainting_size))
+        return PageResult(textlines, raw_mask, lines, out)
+
+    # ------------------------------------------------------------------ device-resident path
+    def stage(self, page: np.ndarray, quads, mask: np.ndarray) -> StagedPage:
+        eng = self.engine
+        dev = eng.device
+        regions = [q.get_transformed_region(page, q.direction, 48) for q in quads]
+        perm = sorted(range(len(regions)), key=lambda i: regions[i].shape[1])
+        chunks_dev = []
+        for indices in chunks(perm, 16):
+            widths = [regions[i].shape[1] for i in indices]
+            canvas = np.zeros((len(indices), 48, max(widths) + 7 + 128, 3), np.uint8)
+            for i, idx in enumerate(indices):
+                canvas[i, :, :widths[i]] = regions[idx]
+            chunks_dev.append(torch.from_numpy(canvas).to(dev))
+        m = (torch.from_numpy(mask).float() / 255.0 >= 0.5).float()[None, None]
+        img = torch.from_numpy(page).permute(2, 0, 1)[None].float() / 255.0 * (1 - m)
+        rel = direct = None
+        if self.use_mpe:
+            r, d = mpe.mpe_tables_256(m[0, 0].numpy())
+            rel, direct = torch.from_numpy(r[None]).to(dev), torch.from_numpy(d[None]).to(dev)
+        sp = StagedPage(torch.from_numpy(page).to(dev), chunks_dev, img.to(dev), m.to(dev), rel, direct)
+        sp.bytes = sum(t.numel() * t.element_size() for t in [sp.page_u8, sp.img, sp.mask] + chunks_dev +
+                       ([rel, direct] if rel is not None else []))
+        return sp
+
+    def run_resident(self, sp: StagedPage):
+        eng = self.engine
+        filt = eng.bilateral17(sp.page_u8)
+        db, dmask = eng.dbnet_forward(filt[None])
+        ocr = [eng.ocr_forward(c) for c in sp.ocr_chunks]
+        out = eng.lama_forward(sp.img, sp.mask, sp.rel_pos, sp.direct, tables256=True)
+        return db, dmask, ocr, out
+
+
+def shard_indices(n_pages_total: int, rank: int, world: int) -> List[int]:
+    """Round-robin page scatter: page i is processed by rank i mod world."""
+    return list(range(rank, n_pages_total, world))
+
+
+def gather_results(local_u8: torch.Tensor, world: int) -> Optional[torch.Tensor]:
+    """All-gather equal-size per-rank result buffers over NCCL (NVLink); returns [world, ...] on every rank."""
+    import torch.distributed as dist
+    if world == 1:
+        return local_u8[None]
+    out = torch.empty((world,) + tuple(local_u8.shape), dtype=local_u8.dtype, device=local_u8.device)
+    dist.all_gather_into_tensor(out, local_u8.contiguous())
+    return out

@@ -1,0 +1,298 @@
+"""Drop-in plugin classes for the three dense-inference stages, same names / signatures / return types as the reference:
+
+  DBConvNextDetector   manga_translator/detection/dbnet_convnext.py:512-588
+  Model48pxCTCOCR      manga_translator/ocr/model_48px_ctc.py:18-160
+  LamaMPEInpainter     manga_translator/inpainting/inpainting_lama_mpe.py:26-118
+  LamaLargeInpainter   manga_translator/inpainting/inpainting_lama_mpe.py:121-136
+
+``register()`` swaps them into the reference registries (detection/__init__.py:12-20, ocr/__init__.py:11-18,
+inpainting/__init__.py:13-22).  All tensor math runs in libmitb (hand-written CUDA through the C ABI); torch tensors are
+device-memory containers only.  CUDA only: any other device string raises (no CPU fallback).
+
+Weights: the same checkpoint files and key layouts as the reference (``sd['model']``|``sd``; ``gen_state_dict`` +
+``str_state_dict``).  Because no checkpoint is downloadable offline, tests and the bench may inject a state_dict with
+``Plugin.set_state_dict(...)`` instead of writing a file.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, List, Optional
+
+import cv2
+import numpy as np
+import torch
+
+from . import compat
+from .compat import InpainterConfig, OcrConfig, OfflineDetector, OfflineInpainter, OfflineOCR, Quadrilateral, chunks
+from .engine import Engine, get_engine
+from ._lib import MitbError
+from .host import det_post, mpe, rearrange
+
+
+def _require_cuda(device: str) -> str:
+    if not str(device).startswith("cuda"):
+        raise MitbError(f"mit_b200 plugins run on CUDA (B200) only; got device '{device}'. "
+                        f"Use the reference classes for CPU execution.")
+    return "cuda:0" if device == "cuda" else device
+
+
+class _InjectableWeights:
+    _injected: Optional[dict] = None
+
+    @classmethod
+    def set_state_dict(cls, sd: Optional[dict]):
+        """Use an in-memory state_dict instead of the checkpoint file (tests / bench; pass None to reset)."""
+        cls._injected = sd
+
+
+# ----------------------------------------------------------------------------------------------- detector
+class DBConvNextDetector(_InjectableWeights, OfflineDetector):
+    # The reference mapping carries an empty URL, which its own ModelWrapper rejects: file-only here.
+    _MODEL_MAPPING = {}
+    _CKPT = "dbnet_convnext.ckpt"
+
+    async def _load(self, device: str):
+        self.device = _require_cuda(device)
+        self.engine: Engine = get_engine(self.device)
+        sd = self._injected
+        if sd is None:
+            sd = torch.load(self._get_file_path(self._CKPT), map_location="cpu")
+        self.engine.load_dbnet(sd["model"] if "model" in sd else sd)
+
+    async def _unload(self):
+        self.engine.unload_dbnet()
+
+    def _batch_forward(self, batch_u8: np.ndarray):
+        """det_batch_forward_default (dbnet_convnext.py:499-509) on uint8 NHWC: normalise + forward + sigmoid on device."""
+        db, mask = self.engine.dbnet_forward(self.engine.h2d(np.ascontiguousarray(batch_u8)))
+        return self.engine.d2h(db), self.engine.d2h(mask)
+
+    async def _infer(self, image: np.ndarray, detect_size: int, text_threshold: float, box_threshold: float,
+                     unclip_ratio: float, verbose: bool = False):
+        eng = self.engine
+        db, mask = rearrange.rearrange_forward(image, self._batch_forward, detect_size, 4)
+        if db is None:
+            # cv2.bilateralFilter(image, 17, 80, 80) on the GPU (dbnet_convnext.py:549)
+            img_dev = eng.h2d(np.ascontiguousarray(image))
+            filt = eng.bilateral17(img_dev)
+            h, w = image.shape[:2]
+            ratio = detect_size / max(h, w)
+            th, tw = int(round(h * ratio)), int(round(w * ratio))
+            if (th, tw) == (h, w) and th % 256 == 0 and tw % 256 == 0:
+                batch, pad_w, pad_h, target_ratio = filt[None], 0, 0, ratio     # stays on the device
+                rh, rw = h, w
+            else:
+                resized, target_ratio, _, pad_w, pad_h = det_post.resize_aspect_ratio(eng.d2h(filt), detect_size,
+                                                                                       cv2.INTER_LINEAR, mag_ratio=1)
+                rh, rw = resized.shape[:2]
+                batch = eng.h2d(resized[None])
+            ratio_h = ratio_w = 1 / target_ratio
+            db_t, mask_t = eng.dbnet_forward(batch)
+            db, mask = eng.d2h(db_t[:, :1].contiguous()), eng.d2h(mask_t)
+            img_resized_h, img_resized_w = rh, rw
+        else:
+            img_resized_h, img_resized_w = image.shape[:2]
+            ratio_w = ratio_h = 1
+            pad_h = pad_w = 0
+        self.logger.info(f"Detection resolution: {img_resized_w}x{img_resized_h}")
+
+        mask = mask[0, 0, :, :]
+        boxes, scores = det_post.boxes_from_prob(db[0, 0], text_threshold, box_threshold, unclip_ratio, img_resized_w, img_resized_h)
+        polys = det_post.polys_from_boxes(boxes, scores, ratio_w, ratio_h)
+        textlines = [Quadrilateral(pts.astype(int), "", score) for pts, score in zip(polys, scores)]
+        textlines = list(filter(lambda q: q.area > 16, textlines))
+        mask_resized = cv2.resize(mask, (mask.shape[1] * 2, mask.shape[0] * 2), interpolation=cv2.INTER_LINEAR)
+        if pad_h > 0:
+            mask_resized = mask_resized[:-pad_h, :]
+        elif pad_w > 0:
+            mask_resized = mask_resized[:, :-pad_w]
+        raw_mask = np.clip(mask_resized * 255, 0, 255).astype(np.uint8)
+        return textlines, raw_mask, None
+
+
+# ----------------------------------------------------------------------------------------------- OCR
+def _pe_table(max_len: int = 2048, d: int = 320) -> torch.Tensor:
+    """PositionalEncoding buffer, computed with the same torch ops as the reference (model_48px_ctc.py:168-174) so the
+    table is bit-identical to the one its modules hold."""
+    pe = torch.zeros(max_len, d)
+    position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d, 2).float() * (-math.log(10000.0) / d))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def ctc_collapse(idx: np.ndarray, blank: int = 0):
+    """Greedy CTC collapse over all timesteps (model_48px_ctc.py:464-493), vectorised: returns per line the kept timesteps."""
+    prev = np.concatenate([np.full((idx.shape[0], 1), blank, idx.dtype), idx[:, :-1]], axis=1)
+    keep = (idx != prev) & (idx != blank)
+    return [np.nonzero(k)[0] for k in keep]
+
+
+class Model48pxCTCOCR(_InjectableWeights, OfflineOCR):
+    _MODEL_MAPPING = {}
+    _CKPT = "ocr-ctc.ckpt"
+    _DICT = "alphabet-all-v5.txt"
+    _injected_dictionary: Optional[List[str]] = None
+
+    @classmethod
+    def set_dictionary(cls, dictionary: Optional[List[str]]):
+        cls._injected_dictionary = dictionary
+
+    async def _load(self, device: str):
+        self.device = _require_cuda(device)
+        self.engine: Engine = get_engine(self.device)
+        if self._injected_dictionary is not None:
+            self.dictionary = list(self._injected_dictionary)
+        else:
+            with open(self._get_file_path(self._DICT), "r", encoding="utf-8") as fp:
+                self.dictionary = [s[:-1] for s in fp.readlines()]
+        sd = self._injected
+        if sd is None:
+            sd = torch.load(self._get_file_path(self._CKPT), map_location="cpu")
+        sd = sd["model"] if "model" in sd else sd
+        sd = {k: v for k, v in sd.items() if not k.endswith(".pe.pe")}
+        if sd["char_pred.weight"].shape[0] != len(self.dictionary):
+            raise MitbError(f"dictionary has {len(self.dictionary)} entries, char_pred has {sd['char_pred.weight'].shape[0]}")
+        self.engine.load_ocr(sd, _pe_table())
+
+    async def _unload(self):
+        self.engine.unload_ocr()
+
+    async def _infer(self, image: np.ndarray, textlines: List[Quadrilateral], config: OcrConfig, verbose: bool = False):
+        text_height, max_chunk_size = 48, 16
+        ignore_bubble = getattr(config, "ignore_bubble", 0)
+        threshold = 0.5 if getattr(config, "prob", None) is None else config.prob
+        quadrilaterals = list(self._generate_text_direction(textlines))
+        region_imgs = [q.get_transformed_region(image, d, text_height) for q, d in quadrilaterals]
+        out_regions = []
+        perm = range(len(region_imgs))
+        is_quadrilaterals = False
+        if len(quadrilaterals) > 0 and isinstance(quadrilaterals[0][0], Quadrilateral):
+            is_quadrilaterals = True
+            perm = sorted(range(len(region_imgs)), key=lambda x: region_imgs[x].shape[1])
+        if 1 <= ignore_bubble <= 50:
+            if not compat.HAVE_REFERENCE:
+                raise NotImplementedError("ignore_bubble needs manga_translator.utils.bubble.is_ignore")
+            from manga_translator.utils.bubble import is_ignore  # type: ignore
+        for indices in chunks(perm, max_chunk_size):
+            N = len(indices)
+            widths = [region_imgs[i].shape[1] for i in indices]
+            max_width = (4 * (max(widths) + 7) // 4) + 128
+            region = np.zeros((N, text_height, max_width, 3), dtype=np.uint8)
+            for i, idx in enumerate(indices):
+                if 1 <= ignore_bubble <= 50 and is_ignore(region_imgs[idx], ignore_bubble):
+                    continue
+                region[i, :, :widths[i], :] = region_imgs[idx]
+            # (x-127.5)/127.5 normalisation, network, log-softmax/argmax and colour clamp all run on the device
+            eng = self.engine
+            pred, logprob, colors = eng.ocr_forward(eng.h2d(region))
+            pred, logprob, colors = eng.d2h(pred), eng.d2h(logprob), eng.d2h(colors)
+            for i, steps in enumerate(ctc_collapse(pred)):
+                if len(steps) == 0:
+                    continue
+                chars = [self.dictionary[c] for c in pred[i, steps]]
+                chars = [" " if ch == "<SP>" else ch for ch in chars]
+                prob = np.exp(np.mean([float(v) for v in logprob[i, steps]]))
+                if prob < threshold:
+                    continue
+                txt = "".join(chars)
+                sel = [s for s, ch in zip(steps, chars) if ch != " "]
+                cols = [0] * 6
+                if sel:
+                    ints = np.array([[int(float(v) * 255) for v in colors[i, s]] for s in sel])
+                    cols = [int(ints[:, k].sum() / len(sel)) for k in range(6)]
+                fr, fg, fb, br, bg, bb = cols
+                self.logger.info(f"prob: {prob} {txt} fg: ({fr}, {fg}, {fb}) bg: ({br}, {bg}, {bb})")
+                cur_region = quadrilaterals[indices[i]][0]
+                if isinstance(cur_region, Quadrilateral):
+                    cur_region.text = txt
+                    cur_region.prob = prob
+                    cur_region.fg_r, cur_region.fg_g, cur_region.fg_b = fr, fg, fb
+                    cur_region.bg_r, cur_region.bg_g, cur_region.bg_b = br, bg, bb
+                else:
+                    cur_region.text.append(txt)
+                    cur_region.update_font_colors(np.array([fr, fg, fb]), np.array([br, bg, bb]))
+                out_regions.append(cur_region)
+        if is_quadrilaterals:
+            return out_regions
+        return textlines
+
+
+# ----------------------------------------------------------------------------------------------- inpainter
+class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
+    _MODEL_MAPPING = {}
+    _CKPT = "inpainting_lama_mpe.ckpt"
+    _USE_MPE = True
+
+    async def _load(self, device: str):
+        self.device = _require_cuda(device)
+        self.engine: Engine = get_engine(self.device)
+        sd = self._injected
+        if sd is None:
+            sd = torch.load(self._get_file_path(self._CKPT), map_location="cpu")
+        self.engine.load_lama(sd["gen_state_dict"], sd["str_state_dict"] if self._USE_MPE else None)
+
+    async def _unload(self):
+        self.engine.unload_lama()
+
+    async def _infer(self, image: np.ndarray, mask: np.ndarray, config: InpainterConfig, inpainting_size: int = 1024,
+                     verbose: bool = False) -> np.ndarray:
+        img_original = np.copy(image)
+        mask_original = np.copy(mask)
+        mask_original[mask_original < 127] = 0
+        mask_original[mask_original >= 127] = 1
+        mask_original = mask_original[:, :, None]
+        height, width, _ = image.shape
+        if max(image.shape[0:2]) > inpainting_size:
+            r = float(inpainting_size) / max(image.shape[0], image.shape[1])
+            size = (round(image.shape[1] * r), round(image.shape[0] * r))
+            image = cv2.resize(image, size, interpolation=cv2.INTER_LINEAR_EXACT)
+            mask = cv2.resize(mask, size, interpolation=cv2.INTER_LINEAR_EXACT)
+        h, w, _ = image.shape
+        new_h = h if h % 8 == 0 else h + (8 - h % 8)
+        new_w = w if w % 8 == 0 else w + (8 - w % 8)
+        if new_h != h or new_w != w:
+            image = cv2.resize(image, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+            mask = cv2.resize(mask, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+        self.logger.info(f"Inpainting resolution: {new_w}x{new_h}")
+        img_t = torch.from_numpy(image).permute(2, 0, 1).unsqueeze_(0).float() / 255.0
+        mask_t = torch.from_numpy(mask).unsqueeze_(0).unsqueeze_(0).float() / 255.0
+        mask_t[mask_t < 0.5] = 0
+        mask_t[mask_t >= 0.5] = 1
+        img_t *= (1 - mask_t)
+        rel_pos = direct = None
+        if self._USE_MPE:
+            rel_pos, direct = mpe.mpe_tables_256(mask_t[0, 0].numpy())     # upsampled inside the kernel
+            rel_pos, direct = rel_pos[None], direct[None]
+        eng = self.engine
+        if rel_pos is not None:
+            rel_pos, direct = eng.h2d(rel_pos), eng.h2d(direct)
+        out = eng.lama_forward(eng.h2d(img_t), eng.h2d(mask_t), rel_pos, direct, tables256=True)
+        img_inpainted = (torch.from_numpy(eng.d2h(out)).squeeze_(0).permute(1, 2, 0).numpy() * 255.0).astype(np.uint8)
+        if new_h != height or new_w != width:
+            img_inpainted = cv2.resize(img_inpainted, (width, height), interpolation=cv2.INTER_LINEAR)
+        return img_inpainted * mask_original + img_original * (1 - mask_original)
+
+
+class LamaLargeInpainter(LamaMPEInpainter):
+    _CKPT = "lama_large_512px.ckpt"
+    _USE_MPE = False
+
+
+# ----------------------------------------------------------------------------------------------- registration
+def register():
+    """Replace the reference registry entries with the B200 plugins (needs the real manga_translator package)."""
+    if not compat.HAVE_REFERENCE:
+        raise MitbError("register() needs an importable manga_translator package; see INTEGRATION.md")
+    from manga_translator import detection, inpainting, ocr  # type: ignore
+    from manga_translator.config import Detector, Inpainter, Ocr  # type: ignore
+    detection.DETECTORS[Detector.dbconvnext] = DBConvNextDetector
+    ocr.OCRS[Ocr.ocr48px_ctc] = Model48pxCTCOCR
+    inpainting.INPAINTERS[Inpainter.lama_mpe] = LamaMPEInpainter
+    inpainting.INPAINTERS[Inpainter.lama_large] = LamaLargeInpainter
+    detection.detector_cache.pop(Detector.dbconvnext, None)
+    ocr.ocr_cache.pop(Ocr.ocr48px_ctc, None)
+    inpainting.inpainter_cache.pop(Inpainter.lama_mpe, None)
+    inpainting.inpainter_cache.pop(Inpainter.lama_large, None)

@@ -155,3 +155,17 @@ def test_lama_full_size_properties(eng):
     keep = (mask == 0).expand_as(a)
     assert torch.equal(a[keep], img[keep])
     eng.unload_lama()
+
+
+def test_lama_mpe256_tables_equal_full_resolution_tables(eng):
+    """The in-kernel INTER_NEAREST upsampling of the 256x256 MPE tables reproduces the host-upsampled full-size tables."""
+    from mit_b200.host import mpe
+    eng.load_lama(weights.lama_weights(9), weights.mpe_weights())
+    for (h, w) in ((128, 96), (200, 312), (520, 264)):
+        img, mask = cases.lama_case(h, w, seed=h)
+        rel, direct = mpe.mpe_tables(mask[0, 0].numpy())
+        rel2, direct2 = mpe.mpe_tables_256(mask[0, 0].numpy())
+        a = eng.lama_forward(img, mask, rel[None], direct[None])
+        b = eng.lama_forward(img, mask, rel2[None], direct2[None], tables256=True)
+        assert torch.equal(a, b), (h, w, (a - b).abs().max().item())
+    eng.unload_lama()

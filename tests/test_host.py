@@ -1,0 +1,172 @@
+"""Host-side logic (no GPU): geometry / detector post-processing / MPE tables / CTC collapse / rearrangement / the C ABI
+surface.  Where the reference helper is importable here (build container) it is the checker; otherwise the oracle is."""
+import asyncio
+import ctypes
+import os
+import re
+import warnings
+
+import cv2
+import numpy as np
+import pytest
+
+from mit_b200 import synth
+from mit_b200.host import det_post, geometry, mpe, rearrange
+from oracle import nets, refload
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not refload.available(), reason="/root/reference not present")
+
+
+def test_abi_header_and_library_agree():
+    """Every function declared in include/mitb.h is exported by libmitb.so and bound in mit_b200._lib (no compute calls)."""
+    from mit_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mitb.h")).read()
+    declared = set(re.findall(r"\b(mitb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"mitb_ctx", "mitb_tensor"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.mitb_ocr_timesteps(647) == 160 and lib.mitb_ocr_timesteps(512) == 127
+    assert b"sm_100a" in lib.mitb_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device context creation fails loudly (and the plugins refuse non-CUDA devices)."""
+    import torch
+    from mit_b200 import MitbError, plugins
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mit_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.mitb_create(0, ctypes.byref(h)) != 0
+    assert b"no CPU fallback" in lib.mitb_last_error(None)
+    det = plugins.DBConvNextDetector()
+    with pytest.raises(MitbError):
+        asyncio.run(det.load("cpu"))
+    with pytest.raises(Exception):
+        asyncio.run(det.infer(np.zeros((8, 8, 3), np.uint8), 2048, 0.5, 0.7, 2.3))   # infer before load
+
+
+def test_mpe_tables_match_oracle():
+    rng = np.random.default_rng(1)
+    for (h, w) in ((256, 256), (120, 312), (64, 48)):
+        m = np.zeros((h, w), np.float32)
+        for _ in range(4):
+            y, x = rng.integers(0, h - 8), rng.integers(0, w - 8)
+            m[y:y + rng.integers(4, h // 2), x:x + rng.integers(4, w // 2)] = 1
+        a, b = mpe.mpe_tables(m), nets.mpe_tables(m)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for m in (np.zeros((40, 40), np.float32), np.ones((40, 40), np.float32)):
+        a, b = mpe.mpe_tables(m), nets.mpe_tables(m)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_ctc_collapse_matches_oracle():
+    from mit_b200.plugins import ctc_collapse
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, 4, (5, 60))
+    steps = ctc_collapse(idx)
+    ref = nets.ctc_greedy(idx, np.zeros(idx.shape, np.float32), np.zeros(idx.shape + (6,), np.float32))
+    assert [[int(idx[b, t]) for t in s] for b, s in enumerate(steps)] == [[c[0] for c in l] for l in ref]
+    assert [len(s) for s in ctc_collapse(np.zeros((2, 7), np.int64))] == [0, 0]
+
+
+def test_polygon_helpers():
+    sq = np.array([[0, 0], [4, 0], [4, 3], [0, 3]])
+    assert geometry.polygon_area(sq) == 12 and geometry.polygon_perimeter(sq) == 14
+    assert geometry.hull_area(np.array([[0, 0], [4, 0], [2, 1], [4, 3], [0, 3]])) == 12
+    far = sq + np.array([10, 0])
+    assert abs(geometry.polygon_distance(sq, far) - 6) < 1e-9
+    assert geometry.polygon_distance(sq, sq + 1) == 0 and geometry.polygon_distance(sq, np.array([[1, 1], [2, 1], [2, 2], [1, 2]])) == 0
+    diag = np.array([[7, 7], [9, 7], [9, 9], [7, 9]])
+    assert abs(geometry.polygon_distance(sq, diag) - 5) < 1e-9        # corner to corner (4,3)->(7,7)
+
+
+def test_unclip_and_boxes_on_synthetic_prob_map():
+    prob = np.zeros((200, 300), np.float32)
+    prob[50:80, 40:200] = 0.9
+    prob[120:124, 10:14] = 0.9     # too small after unclip filter? (short side 4 -> kept only if >= 3)
+    boxes, scores = det_post.boxes_from_prob(prob, 0.5, 0.7, 2.3, 300, 200)
+    polys = det_post.polys_from_boxes(boxes, scores, 1.0, 1.0)
+    big = [p for p in polys if (p[:, 0].max() - p[:, 0].min()) > 100]
+    assert len(big) == 1
+    p = big[0]
+    # rectangle 160x30 (contour spans 159x29): distance = A*r/L
+    d = (159 * 29) * 2.3 / (2 * (159 + 29))
+    assert abs((p[:, 0].max() - p[:, 0].min()) - (159 + 2 * d)) <= 2 and abs((p[:, 1].max() - p[:, 1].min()) - (29 + 2 * d)) <= 2
+    assert p.sum(axis=1).argmin() == 0                              # starts at the top-left corner
+
+
+def test_synthetic_page_is_deterministic():
+    p1, b1, m1 = synth.make_page(3, 512, 384, 6)
+    p2, b2, m2 = synth.make_page(3, 512, 384, 6)
+    assert np.array_equal(p1, p2) and np.array_equal(m1, m2) and len(b1) == 6
+    assert all(np.array_equal(a, b) for a, b in zip(b1, b2))
+    q = synth.make_quads(b1)
+    assert [x.direction for x in q] == ["h"] * 3 + ["v"] * 3
+
+
+@needs_ref
+def test_quadrilateral_matches_reference():
+    warnings.filterwarnings("ignore")
+    U = refload.load()["utils"]
+    rng = np.random.default_rng(4)
+    page, boxes, _ = synth.make_page(1, 1024, 768, 10)
+    for b in boxes + [np.array([[100, 100], [400, 130], [390, 190], [95, 160]]), np.array([[50, 50], [90, 60], [70, 400], [30, 390]])]:
+        b = b[rng.permutation(4)]
+        mine, ref = geometry.Quadrilateral(b, "", 1.0), U.Quadrilateral(b, "", 1.0)
+        assert np.array_equal(mine.pts, ref.pts) and mine.direction == ref.direction
+        assert abs(mine.aspect_ratio - ref.aspect_ratio) < 1e-6 and abs(mine.font_size - ref.font_size) < 1e-6
+        assert tuple(mine.aabb) == (ref.aabb.x, ref.aabb.y, ref.aabb.w, ref.aabb.h)
+        assert mine.is_approximate_axis_aligned == ref.is_approximate_axis_aligned and abs(mine.angle - ref.angle) < 1e-6
+        for d in ("h", "v"):
+            assert np.array_equal(mine.get_transformed_region(page, d, 48), ref.get_transformed_region(page, d, 48))
+
+
+@needs_ref
+def test_rearrange_matches_reference():
+    warnings.filterwarnings("ignore")
+    U = refload.load()["utils"]
+
+    def fwd(batch, device=None):
+        batch = np.asarray(batch).astype(np.float32)
+        s = batch.shape[1]
+        db = np.stack([batch[..., 0] / 255.0, batch[..., 1] / 255.0], 1).astype(np.float32)
+        mask = np.stack([cv2.resize(b[..., 2], (s // 2, s // 2)) / 255.0 for b in batch])[:, None].astype(np.float32)
+        return db, mask
+    rng = np.random.default_rng(0)
+    for shape in ((3000, 500, 3), (500, 3300, 3), (1024, 768, 3)):
+        img = cv2.GaussianBlur(rng.integers(0, 256, shape, dtype=np.uint8), (0, 0), 5)
+        r = U.det_rearrange_forward(img, fwd, 1024, 4)
+        o = rearrange.rearrange_forward(img, fwd, 1024, 4)
+        if r[0] is None:
+            assert o[0] is None
+        else:
+            assert np.array_equal(r[0], o[0]) and np.array_equal(r[1], o[1])
+
+
+@needs_ref
+def test_detector_helpers_match_reference():
+    warnings.filterwarnings("ignore")
+    refload.load()
+    import importlib
+    du = importlib.import_module("manga_translator.detection.default_utils.dbnet_utils")
+    ip = importlib.import_module("manga_translator.detection.default_utils.imgproc")
+    rep = du.SegDetectorRepresenter(0.5, 0.7, unclip_ratio=2.3)
+    rng = np.random.default_rng(5)
+    prob = cv2.GaussianBlur(rng.random((120, 160)).astype(np.float32), (0, 0), 4)
+    cnts, _ = cv2.findContours(((prob > prob.mean()) * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    for c in cnts[:10]:
+        c = c.squeeze(1)
+        if len(c) < 3:
+            continue
+        a, b = det_post.mini_box(c), rep.get_mini_boxes(c)
+        assert np.allclose(np.array(a[0]), np.array(b[0])) and a[1] == b[1]
+        assert abs(det_post.box_score(prob, c) - rep.box_score_fast(prob, c)) < 1e-12
+    img = rng.integers(0, 256, (300, 200, 3), dtype=np.uint8)
+    for size in (512, 256, 300):
+        a, b = det_post.resize_aspect_ratio(img, size, cv2.INTER_LINEAR), ip.resize_aspect_ratio(img, size, cv2.INTER_LINEAR, mag_ratio=1)
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
