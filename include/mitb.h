@@ -43,6 +43,10 @@ const char* mitb_version(void);
 long long mitb_launch_count(const mitb_ctx* ctx);      /* kernels launched by this context so far */
 size_t mitb_workspace_bytes(const mitb_ctx* ctx);      /* current activation workspace size */
 
+/* Process-wide switch between the tcgen05 (bf16x3 split, ~1e-5 relative) and the exact-fp32 SIMT convolution kernels.
+ * Default on.  The SIMT kernels are the parity anchor of the tensor-core path (tests run both). */
+int mitb_set_tensor_cores(int on);
+
 /* Per-launch CUDA-event timing aggregated per kernel class (for bench.py's roofline block). report() synchronises the
  * recorded events, clears them and returns a JSON object {"class": {"launches","ms","flops","bytes"}, ...} valid until
  * the next call. */

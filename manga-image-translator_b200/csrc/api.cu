@@ -69,6 +69,8 @@ const char* mitb_last_error(const mitb_ctx* ctx) { return ctx ? ctx->c.err.c_str
 long long mitb_launch_count(const mitb_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 size_t mitb_workspace_bytes(const mitb_ctx* ctx) { return ctx ? ctx->c.ws.cap : 0; }
 
+int mitb_set_tensor_cores(int on) { conv_tc_set_enabled(on != 0); return 0; }
+
 int mitb_profile_enable(mitb_ctx* ctx, int on) {
   API_BEGIN(ctx)
   ctx->c.prof.on = on != 0;

@@ -1,6 +1,441 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a -- placeholder until the kernel lands.
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a.
+//
+// Same contract as the SIMT kernel in conv_simt.cu (tap list, zero/reflect padding, strided output mapping for the
+// transposed-conv phases, BN+ReLU prologue, fused epilogue), but the contraction runs on the tensor cores:
+//
+//   * 128-pixel x BN-channel output tile per CTA, accumulator in TMEM (128 lanes x BN fp32 columns).
+//   * fp32 accuracy from bf16 tensor cores by operand splitting ("bf16x3"): x = hi + mid with hi = bf16(x),
+//     mid = bf16(x - hi); D += A_hi*B_hi + A_hi*B_mid + A_mid*B_hi.  The dropped terms are <= ~3*2^-18 relative
+//     (about 1e-5), far inside the 1e-3 parity budget, at 1/3 of the bf16 tensor rate (2x a 3xTF32 scheme).
+//   * K is consumed in blocks of 64 (one 128-byte swizzle row of bf16).  Warp-specialised:
+//       warps 0-3  gather the activation tile from the NHWC (or planar) view, apply the optional BN+ReLU prologue,
+//                  split hi/mid and store both tiles into shared memory in the UMMA K-major SWIZZLE_128B layout;
+//       warps 5-8  stream the pre-split, K-major bf16 weight tiles (hi/mid) into shared memory;
+//       warp  4    one elected thread issues tcgen05.mma (12 per K block) and commits to the stage's "empty" mbarrier;
+//     full/empty mbarrier ring, producers signal after fence.proxy.async (generic-proxy stores -> async-proxy reads).
+//   * Epilogue: warps 0-3 read their 32 TMEM lanes with tcgen05.ld (one output pixel per thread), apply
+//     (+add0) * scale + shift -> activation -> * mul1 -> + add1 and store NHWC (or planar) fp32.
+#include <cuda_bf16.h>
 #include "mitb_internal.h"
+
 namespace mitb {
-bool conv_tc_supported(const ConvOp&) { return false; }
-void launch_conv_tc(const ConvOp&, cudaStream_t) { MITB_CHECK(false, "tcgen05 conv path not built"); }
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_THREADS = 288;               // 4 A-producer warps + 1 MMA warp + 4 B-producer warps
+
+struct TcParams {
+  const float* in; int N, H, W, in_cs, in_coff, Cin, in_planar;
+  const uint16_t* wh; const uint16_t* wm; int kpad, npad;     // weights [npad][kpad] bf16, K-major, zero padded
+  int ntaps; int8_t tdy[kMaxTaps], tdx[kMaxTaps];
+  int sy, sx, pad, Ho, Wo;
+  float* out; int oH, oW, out_cs, out_coff, Cout, out_planar, oy_mul, oy_add, ox_mul, ox_add;
+  const float* in_scale; const float* in_shift; int in_relu;
+  const float* add0; int add0_cs, add0_coff, add0_planar;
+  const float* add1; int add1_cs, add1_coff, add1_planar;
+  const float* scale; const float* shift; const float* mul1; int act;
+  int M, K, BN, stages, tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();          // ~2 s at 2 GHz: far beyond any legitimate wait
+    }
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart.
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1) | [32,46) stride byte
+//   offset >> 4 (1024 >> 4) | [46,48) descriptor version 1 (sm_100) | [61,64) layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float apply_act_tc(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case ACT_SILU: return v / (1.f + expf(-v));
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case ACT_SIGMOID2: { float s = 1.f / (1.f + expf(-v)); return 1.f / (1.f + expf(-s)); }
+    case ACT_CLAMP01: return fminf(fmaxf(v, 0.f), 1.f);
+    default: return v;
+  }
+}
+__device__ __forceinline__ int reflect_tc(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+// split 8 fp32 values into bf16 hi / mid packs (16 bytes each)
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mid) {
+  uint32_t h[4], m[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat16 m0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 m1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    m[i] = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  mid = make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stage][A_hi 16K | A_mid 16K | B_hi BN*128 | B_mid BN*128], then barriers
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN, S = p.stages;
+  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)BN * 128;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);     // full[S], empty[S], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * S);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int nkb = p.kpad / TC_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 256); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================== A producer: one output pixel (GEMM row) per thread ===========================
+    const int r = tid;
+    const int m = m0 + r;
+    const bool row_ok = m < p.M;
+    const int HoWo = p.Ho * p.Wo, HW = p.H * p.W;
+    int nimg = 0, iy0 = 0, ix0 = 0, pix = 0;
+    if (row_ok) {
+      nimg = m / HoWo; const int rr = m - nimg * HoWo;
+      const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+      iy0 = oy * p.sy; ix0 = ox * p.sx; pix = rr;
+    }
+    int tap = 0, ci = 0;                       // cursor of the next 8-channel chunk
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      float v[8][8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = kb * TC_BK + c * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[c][e] = 0.f;
+        if (row_ok && k < p.K) {
+          if (!p.in_planar) {
+            int iy = iy0 + p.tdy[tap], ix = ix0 + p.tdx[tap];
+            bool inb = true;
+            if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
+            else inb = (iy >= 0) & (iy < p.H) & (ix >= 0) & (ix < p.W);
+            if (inb) {
+              const float* src = p.in + ((size_t)(nimg * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci;
+              const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+              if (p.in_scale) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float t = v[c][e] * p.in_scale[ci + e] + p.in_shift[ci + e];
+                  v[c][e] = p.in_relu ? fmaxf(t, 0.f) : t;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = k + e;
+              if (ch < p.K) {
+                float t = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + ch) * HW + pix);
+                if (p.in_scale) { t = t * p.in_scale[ch] + p.in_shift[ch]; if (p.in_relu) t = fmaxf(t, 0.f); }
+                v[c][e] = t;
+              }
+            }
+          }
+        }
+        ci += 8;
+        while (ci >= p.Cin && !p.in_planar) { ci -= p.Cin; ++tap; }
+      }
+      mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
+      uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+      uint8_t* a_mid = a_hi + a_bytes;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 hi, mid;
+        split8(v[c], hi, mid);
+        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        *reinterpret_cast<uint4*>(a_mid + off) = mid;
+      }
+      fence_async_smem();
+      mbar_arrive(full_bar(s));
+    }
+    // =========================== epilogue: TMEM -> registers -> global ===========================
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int py = row_ok ? ((pix / p.Wo) * p.oy_mul + p.oy_add) : 0;
+    const int px = row_ok ? ((pix % p.Wo) * p.ox_mul + p.ox_add) : 0;
+    const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
+    const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int cb = 0; cb < BN; cb += 16) {
+      uint32_t raw[16];
+      tmem_ld16(taddr_row + (uint32_t)cb, raw);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int c0 = n0 + cb;
+      if (c0 >= p.Cout) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cq = c0 + q * 4;
+        if (cq >= p.Cout) break;
+        float v4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v4[e] = __uint_as_float(raw[q * 4 + e]);
+        const bool full = cq + 3 < p.Cout;
+        auto fetch = [&](const float* base, int cs, int coff, int planar, float* dst) {
+          if (!planar && full && ((cs | coff) & 3) == 0) {
+            const float4 t = *reinterpret_cast<const float4*>(base + opix * cs + coff + cq);
+            dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              dst[e] = 0.f;
+              if (cq + e < p.Cout)
+                dst[e] = planar ? base[((size_t)nimg * cs + coff + cq + e) * oplane + opl_pix] : base[opix * cs + coff + cq + e];
+            }
+          }
+        };
+        if (p.add0) { float t[4]; fetch(p.add0, p.add0_cs, p.add0_coff, p.add0_planar, t);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v4[e] += t[e]; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = cq + e;
+          if (c < p.Cout) {
+            float x = v4[e];
+            if (p.scale) x *= p.scale[c];
+            if (p.shift) x += p.shift[c];
+            x = apply_act_tc(x, p.act);
+            if (p.mul1) x *= p.mul1[c];
+            v4[e] = x;
+          }
+        }
+        if (p.add1) { float t[4]; fetch(p.add1, p.add1_cs, p.add1_coff, p.add1_planar, t);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v4[e] += t[e]; }
+        if (!p.out_planar && full && ((p.out_cs | p.out_coff) & 3) == 0) {
+          *reinterpret_cast<float4*>(p.out + opix * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (cq + e < p.Cout) {
+              if (p.out_planar) p.out[((size_t)nimg * p.out_cs + p.out_coff + cq + e) * oplane + opl_pix] = v4[e];
+              else p.out[opix * p.out_cs + p.out_coff + cq + e] = v4[e];
+            }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================== MMA issuer (one elected thread) ===========================
+    if (lane == 0) {
+      // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9 / 10-12 = 1), K-major A and B,
+      // N>>3 at bits 17-22, M>>4 at bits 24-28
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        mbar_wait(full_bar(s), (kb / S) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+        const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+        const uint64_t dah = make_desc_sw128(a_hi), dam = make_desc_sw128(a_mid), dbh = make_desc_sw128(b_hi), dbm = make_desc_sw128(b_mid);
+#pragma unroll
+        for (int j = 0; j < TC_BK / 16; ++j) {
+          const uint64_t adv = (uint64_t)(j * 2);                  // 16 bf16 = 32 bytes = 2 x 16-byte units inside the swizzle row
+          umma_bf16(tmem_base, dah + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+          umma_bf16(tmem_base, dah + adv, dbm + adv, idesc, 1u);
+          umma_bf16(tmem_base, dam + adv, dbh + adv, idesc, 1u);
+        }
+        umma_commit(empty_bar(s));            // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    // =========================== B producer: pre-split K-major bf16 weights ===========================
+    const int t = tid - 160;                   // 0..127
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
+      uint8_t* b_hi = smem + (size_t)s * stage_bytes + 2 * a_bytes;
+      uint8_t* b_mid = b_hi + b_bytes;
+      // BN rows x 8 chunks per array; consecutive threads take consecutive chunks of a row (coalesced 128 B rows)
+      for (int i = t; i < BN * 8; i += 128) {
+        const int row = i >> 3, c = i & 7;
+        const size_t g = ((size_t)(n0 + row) * p.kpad + (size_t)kb * TC_BK) * 2 + (size_t)c * 16;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.wh) + g));
+        const uint4 mm = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.wm) + g));
+        const uint32_t off = (uint32_t)row * 128u + (((uint32_t)c ^ (uint32_t)(row & 7)) << 4);
+        *reinterpret_cast<uint4*>(b_hi + off) = h;
+        *reinterpret_cast<uint4*>(b_mid + off) = mm;
+      }
+      fence_async_smem();
+      mbar_arrive(full_bar(s));
+    }
+  }
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// fp32 K-major [K][ldw] (the SIMT layout) -> bf16 hi/mid [npad][kpad] K-major, zero padded
+__global__ void split_weights_kernel(const float* w, int K, int Cout, int ldw, uint16_t* wh, uint16_t* wm, int kpad, int npad) {
+  const long total = (long)npad * kpad;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kpad), n = (int)(i / kpad);
+    float x = (k < K && n < Cout) ? w[(size_t)k * ldw + n] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 m = __float2bfloat16_rn(x - __bfloat162float(h));
+    wh[i] = __bfloat16_as_ushort(h); wm[i] = __bfloat16_as_ushort(m);
+  }
+}
+
+int pick_bn(int Cout) {
+  const int tiles = (Cout + 255) / 256;
+  int bn = (Cout + tiles - 1) / tiles;
+  bn = (bn + 15) & ~15;
+  if (bn < 16) bn = 16;
+  return bn;
+}
+
+}  // namespace
+
+static bool g_tc_enabled = true;
+void conv_tc_set_enabled(bool on) { g_tc_enabled = on; }
+
+// Build the tensor-core weight copies for a conv (called at load time by the Loader)
+void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
+  const int K = cw.ntaps * cw.Cin;
+  const int bn = pick_bn(cw.Cout);
+  const int ntiles = (cw.Cout + bn - 1) / bn;
+  cw.tc_bn = bn; cw.tc_kpad = (K + TC_BK - 1) / TC_BK * TC_BK; cw.tc_npad = ntiles * bn;
+  const size_t n = (size_t)cw.tc_npad * cw.tc_kpad;
+  uint16_t* wh = (uint16_t*)blob.alloc_f((n + 1) / 2 + 4);
+  uint16_t* wm = (uint16_t*)blob.alloc_f((n + 1) / 2 + 4);
+  int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  split_weights_kernel<<<blocks, 256, 0, st>>>(cw.w, K, cw.Cout, cw.ldw, wh, wm, cw.tc_kpad, cw.tc_npad);
+  CUDA_OK(cudaGetLastError());
+  cw.wh = wh; cw.wm = wm;
+}
+
+bool conv_tc_supported(const ConvOp& op) {
+  if (!g_tc_enabled || !op.wh || !op.wm) return false;
+  if (op.stat_max) return false;
+  const int K = op.ntaps * op.in.C;
+  if (op.out.C < 16 || K < 32) return false;
+  if (op.in.planar) return op.ntaps == 1;
+  return op.in.C % 8 == 0 && op.in.cs % 4 == 0 && op.in.coff % 4 == 0;
+}
+
+void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
+  TcParams p;
+  p.in = op.in.p; p.N = op.in.N; p.H = op.in.H; p.W = op.in.W; p.in_cs = op.in.cs; p.in_coff = op.in.coff; p.Cin = op.in.C;
+  p.in_planar = op.in.planar;
+  p.wh = op.wh; p.wm = op.wm; p.kpad = op.tc_kpad; p.npad = op.tc_npad;
+  p.ntaps = op.ntaps;
+  for (int t = 0; t < op.ntaps; ++t) { p.tdy[t] = op.tdy[t]; p.tdx[t] = op.tdx[t]; }
+  p.sy = op.sy; p.sx = op.sx; p.pad = op.pad; p.Ho = op.Ho; p.Wo = op.Wo;
+  p.out = op.out.p; p.oH = op.out.H; p.oW = op.out.W; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C;
+  p.out_planar = op.out.planar; p.oy_mul = op.oy_mul; p.oy_add = op.oy_add; p.ox_mul = op.ox_mul; p.ox_add = op.ox_add;
+  p.in_scale = op.in_scale; p.in_shift = op.in_shift; p.in_relu = op.in_relu;
+  p.add0 = op.add0.p; p.add0_cs = op.add0.cs; p.add0_coff = op.add0.coff; p.add0_planar = op.add0.planar;
+  p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
+  p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
+  p.M = op.in.N * op.Ho * op.Wo; p.K = op.ntaps * op.in.C; p.BN = op.tc_bn;
+  MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tc conv: bad BN %d", p.BN);
+  MITB_CHECK(p.in_planar || p.Cin % 8 == 0, "tc conv: Cin must be a multiple of 8");
+  int cols = 32; while (cols < p.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)p.BN * 128;
+  int stages = (int)((200 * 1024) / stage_bytes); if (stages > 4) stages = 4;
+  MITB_CHECK(stages >= 2, "tc conv: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) { CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  dim3 grid((p.M + TC_BM - 1) / TC_BM, p.npad / p.BN);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  count_launch();
+  CUDA_OK(cudaGetLastError());
+}
+
 }  // namespace mitb

@@ -35,6 +35,7 @@ ConvW Loader::conv_cat_cin(const std::vector<std::string>& wnames, int pad_y, in
   if (wnames.size() == 1) {
     launch_repack(dst, t0.data, Cout, Cin, cw.ntaps, ky.data(), kx.data(), (long)Cin * kh * kw, (long)kh * kw, kw, 1, cw.ldw, st);
     cw.w = dst;
+    conv_tc_prepare(cw, blob, st);
     return cw;
   }
   for (auto& nm : wnames) {
@@ -48,6 +49,7 @@ ConvW Loader::conv_cat_cin(const std::vector<std::string>& wnames, int pad_y, in
     c0 += ci;
   }
   cw.w = dst;
+  conv_tc_prepare(cw, blob, st);
   return cw;
 }
 
@@ -73,6 +75,7 @@ ConvW Loader::convT_phase(const std::string& wname, int k, int pad, int py, int 
   // src index: ci*(Cout*k*k) + co*(k*k) + ky*k + kx
   launch_repack(dst, t.data, Cout, Cin, cw.ntaps, ky.data(), kx.data(), (long)k * k, (long)Cout * k * k, k, 1, cw.ldw, st);
   cw.w = dst;
+  conv_tc_prepare(cw, blob, st);
   return cw;
 }
 
@@ -85,6 +88,7 @@ ConvW Loader::linear_rows(const std::string& wname, int r0, int nr) {
   int z = 0;
   launch_repack(dst, t.data + (size_t)r0 * Cin, nr, Cin, 1, &z, &z, Cin, 1, 0, 0, cw.ldw, st);
   cw.w = dst;
+  conv_tc_prepare(cw, blob, st);
   return cw;
 }
 
@@ -109,6 +113,7 @@ ConvW Loader::conv_padcin(const std::string& wname, int pad, int cin_pad) {
     launch_repack(dst + (size_t)tp * cin_pad * cw.ldw, t.data, Cout, ci, 1, &ky, &kx, (long)ci * kh * kw, (long)kh * kw, kw, 1, cw.ldw, st);
   }
   cw.w = dst;
+  conv_tc_prepare(cw, blob, st);
   return cw;
 }
 

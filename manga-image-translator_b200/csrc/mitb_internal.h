@@ -72,6 +72,8 @@ struct ConvOp {
   View add0, add1;                    // same pixel grid as out; p==nullptr when unused
   const float* scale = nullptr; const float* shift = nullptr; const float* mul1 = nullptr;
   int act = ACT_NONE;
+  // tensor-core copies of the weights (conv_tc.cu): bf16 hi/mid [tc_npad][tc_kpad], K-major; null -> SIMT path only
+  const uint16_t* wh = nullptr; const uint16_t* wm = nullptr; int tc_bn = 0, tc_kpad = 0, tc_npad = 0;
   // optional fused row statistics (vocabulary head): no tensor output, per (row, column-block) partials
   float* stat_max = nullptr; float* stat_sum = nullptr; int* stat_idx = nullptr; int stat_ld = 0;
 };
@@ -133,7 +135,11 @@ struct ConvW {
   const float* w = nullptr; int ldw = 0, Cin = 0, Cout = 0, ntaps = 1;
   int8_t tdy[kMaxTaps] = {0}, tdx[kMaxTaps] = {0};
   const float* scale = nullptr; const float* shift = nullptr;   // folded BN / bias (may be null)
+  const uint16_t* wh = nullptr; const uint16_t* wm = nullptr; int tc_bn = 0, tc_kpad = 0, tc_npad = 0;
 };
+struct DevBlob;
+void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st);   // build the bf16 hi/mid tensor-core weight copies
+void conv_tc_set_enabled(bool on);
 
 struct Loader {                        // helpers used by the network builders at load time
   const Weights& W; DevBlob& blob; cudaStream_t st;

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mitb_version": (C.c_char_p, []),
     "mitb_launch_count": (C.c_longlong, [P]),
     "mitb_workspace_bytes": (C.c_size_t, [P]),
+    "mitb_set_tensor_cores": (I, [I]),
     "mitb_profile_enable": (I, [P, I]),
     "mitb_profile_report": (C.c_char_p, [P]),
     "mitb_dbnet_load": (I, [P, C.POINTER(MitbTensor), I]),

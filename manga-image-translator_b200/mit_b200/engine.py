@@ -67,6 +67,17 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_tensor_cores(self, on: bool):
+        """Process-wide: route eligible convolutions to the tcgen05 kernel (default) or keep everything on the fp32 SIMT kernel."""
+        self.lib.mitb_set_tensor_cores(1 if on else 0)
+
+    def profile(self, on: bool):
+        self._check(self.lib.mitb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_report(self) -> dict:
+        import json
+        return json.loads(self.lib.mitb_profile_report(self._h).decode())
+
     @property
     def launches(self) -> int:
         return int(self.lib.mitb_launch_count(self._h))
