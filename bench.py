@@ -200,10 +200,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- end-to-end through the plugin API with host buffers (`e2e`)
     def e2e_step():
-        outs = []
-        for (p, b, m) in pages:
-            r = hp.process_page(p, synth.make_quads(b), m)
-            outs.append(r)
+        outs = hp.process_pages([(p, synth.make_quads(b), m) for (p, b, m) in pages], workers=args.workers)
         if world > 1:   # results back to every rank (rank 0 consumes them): inpainted pages + raw masks over NCCL
             for i, r in enumerate(outs):
                 result_buf[i].copy_(torch.from_numpy(r.inpainted), non_blocking=True)
@@ -281,6 +278,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pages", type=int, default=PAGES_PER_GPU, help="pages per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workers", type=int, default=4, help="host threads of the page pipeline in the e2e leg")
     ap.add_argument("--fast-e2e", action="store_true", help="one warm-up step for the e2e leg (development only)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

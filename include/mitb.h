@@ -92,6 +92,14 @@ int mitb_lama_forward(mitb_ctx* ctx, const float* img, const float* mask, const 
 int mitb_lama_forward_mpe256(mitb_ctx* ctx, const float* img, const float* mask, const int32_t* rel_pos256,
                              const int32_t* direct256, int n, int h, int w, float* out, void* stream);
 
+/* uint8 entry covering the whole device part of LamaMPEInpainter._infer (inpainting_lama_mpe.py:82-117) for one image:
+ * img uint8 [h,w,3] and mask uint8 [h,w] on the device (already resized to the network resolution, multiples of 8);
+ * normalisation (/255), mask binarisation (>=0.5), pre-masking, the network, pred*mask+(1-mask)*img, (x*255) truncation to
+ * uint8 and -- when composite != 0 -- `ans = inpainted*m0 + img*(1-m0)` with m0 = (mask >= 127) all run in kernels.
+ * rel_pos256/direct256: the 256x256 MPE tables (NULL for the large model). out: uint8 [h,w,3]. */
+int mitb_lama_infer_u8(mitb_ctx* ctx, const uint8_t* img, const uint8_t* mask, const int32_t* rel_pos256,
+                       const int32_t* direct256, int h, int w, int composite, uint8_t* out, void* stream);
+
 /* ---- standalone operators (parity tests and micro-benchmarks; same kernels the networks use) ---- */
 /* General conv through the implicit-GEMM kernel.  x [n,cin,h,w], wt PyTorch layout [cout,cin,kh,kw], y [n,cout,ho,wo]
  * (all NCHW device fp32).  pad_mode 0 zero / 1 reflect; act 0 none,1 relu,2 gelu(erf),3 silu,4 sigmoid.

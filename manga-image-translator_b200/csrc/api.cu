@@ -170,6 +170,16 @@ int mitb_lama_forward_mpe256(mitb_ctx* ctx, const float* img, const float* mask,
   API_END(ctx)
 }
 
+int mitb_lama_infer_u8(mitb_ctx* ctx, const uint8_t* img, const uint8_t* mask, const int32_t* rel_pos256, const int32_t* direct256,
+                       int h, int w, int composite, uint8_t* out, void* stream) {
+  API_BEGIN(ctx)
+  MITB_CHECK(ctx->c.lama, "lama: forward before load");
+  MITB_CHECK(img && mask && out, "lama: null buffer");
+  LamaU8Io io; io.img = img; io.mask = mask; io.out = out; io.composite = composite;
+  lama_run(ctx->c, *ctx->c.lama, nullptr, nullptr, rel_pos256, direct256, 256, 256, 1, h, w, nullptr, (cudaStream_t)stream, &io);
+  API_END(ctx)
+}
+
 // ------------------------------------------------------------------ standalone operators
 static View nhwc_tmp(Arena& ws, int n, int h, int w, int c) { return ws.view(n, h, w, (c + 3) & ~3).slice(0, c); }
 

@@ -414,10 +414,13 @@ void launch_repack(float* dst, const float* src, int Cout, int Cin, int ntaps, c
   CUDA_OK(cudaFree(d));
 }
 
-int conv_stat_blocks(int Cout) { return (Cout + 127) / 128; }
+
 
 bool conv_tc_supported(const ConvOp& op);            // conv_tc.cu
+int conv_tc_stat_blocks(const ConvOp& op);
 void launch_conv_tc(const ConvOp& op, cudaStream_t st);
+
+int conv_stat_blocks(const ConvOp& op) { return conv_tc_supported(op) ? conv_tc_stat_blocks(op) : (op.out.C + 127) / 128; }
 
 static void fill_params(const ConvOp& op, ConvKParams& p) {
   p.in = op.in.p; p.N = op.in.N; p.H = op.in.H; p.W = op.in.W; p.in_cs = op.in.cs; p.in_coff = op.in.coff;
@@ -458,7 +461,7 @@ void launch_conv(const ConvOp& op, cudaStream_t st) {
   const double flops = 2.0 * p.M * (double)p.K * Cout;
   const double bytes = 4.0 * ((double)op.in.pixels() * op.in.C + (double)p.K * Cout +
                               (double)p.M * Cout * ((op.stat_max ? 0 : 1) + (op.add0.p ? 1 : 0) + (op.add1.p ? 1 : 0)));
-  if (!op.stat_max && conv_tc_supported(op)) { ProfScope ps("conv_tc", flops, bytes, st); launch_conv_tc(op, st); return; }
+  if (conv_tc_supported(op)) { ProfScope ps(op.stat_max ? "conv_tc_rowstat" : "conv_tc", flops, bytes, st); launch_conv_tc(op, st); return; }
   ProfScope ps(op.stat_max ? "conv_simt_rowstat" : (Cout <= 4 && !op.in.planar && op.ldw == 4) ? "conv_fewout" : "conv_simt", flops, bytes, st);
   if (op.stat_max) {
     MITB_CHECK(!op.in.planar, "row-stat epilogue expects NHWC input");

@@ -35,6 +35,7 @@ struct TcParams {
   const float* add0; int add0_cs, add0_coff, add0_planar;
   const float* add1; int add1_cs, add1_coff, add1_planar;
   const float* scale; const float* shift; const float* mul1; int act;
+  float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;     // fused log-softmax/argmax partials (vocabulary head)
   int M, K, BN, stages, tmem_cols;
 };
 
@@ -247,6 +248,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
     const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (p.stat_max) {
+      // vocabulary head: online (max, first argmax, sum exp) over this tile's columns; one thread owns one row, so no
+      // cross-thread reduction is needed.  The logits never leave TMEM (model_48px_ctc.py:460-461).
+      float bm = -INFINITY, bs = 0.f; int bi = 0x7fffffff;
+      for (int cb = 0; cb < BN; cb += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr_row + (uint32_t)cb, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int c = n0 + cb + e;
+          if (c < p.Cout) {
+            const float x = __uint_as_float(raw[e]) + (p.shift ? p.shift[c] : 0.f);
+            if (x > bm) { bs = bs * expf(bm - x) + 1.f; bm = x; bi = c; }
+            else bs += expf(x - bm);
+          }
+        }
+      }
+      if (row_ok) {
+        const size_t o = (size_t)m * p.stat_ld + blockIdx.y;
+        p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
+      }
+    } else
     for (int cb = 0; cb < BN; cb += 16) {
       uint32_t raw[16];
       tmem_ld16(taddr_row + (uint32_t)cb, raw);
@@ -397,11 +421,12 @@ void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
   cw.wh = wh; cw.wm = wm;
 }
 
+int conv_tc_stat_blocks(const ConvOp& op) { return op.tc_npad / op.tc_bn; }
+
 bool conv_tc_supported(const ConvOp& op) {
   if (!g_tc_enabled || !op.wh || !op.wm) return false;
-  if (op.stat_max) return false;
   const int K = op.ntaps * op.in.C;
-  if (op.out.C < 16 || K < 32) return false;
+  if (K < 32) return false;
   if (op.in.planar) return op.ntaps == 1;
   return op.in.C % 8 == 0 && op.in.cs % 4 == 0 && op.in.coff % 4 == 0;
 }
@@ -420,6 +445,8 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   p.add0 = op.add0.p; p.add0_cs = op.add0.cs; p.add0_coff = op.add0.coff; p.add0_planar = op.add0.planar;
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
+  p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
+  MITB_CHECK(!op.stat_max || op.stat_ld == op.tc_npad / op.tc_bn, "tc conv: stat_ld must equal conv_stat_blocks(op)");
   p.M = op.in.N * op.Ho * op.Wo; p.K = op.ntaps * op.in.C; p.BN = op.tc_bn;
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tc conv: bad BN %d", p.BN);
   MITB_CHECK(p.in_planar || p.Cin % 8 == 0, "tc conv: Cin must be a multiple of 8");

@@ -51,7 +51,7 @@ LamaModel* lama_build(Ctx& ctx, const Weights& W) {
     Loader L{W, m->blob, 0};
     while (W.has("model." + std::to_string(5 + m->n_blocks) + ".conv1.ffc.convl2l.weight")) ++m->n_blocks;
     MITB_CHECK(m->n_blocks > 0, "lama: no FFC res-blocks found in the state_dict");
-    m->stem = L.conv("model.1.ffc.convl2l.weight", 3, 3); L.bn_fold("model.1.bn_l.", kBnEps, &m->stem.scale, &m->stem.shift);
+    m->stem = L.conv_padcin("model.1.ffc.convl2l.weight", 3, 8); L.bn_fold("model.1.bn_l.", kBnEps, &m->stem.scale, &m->stem.shift);
     m->d1 = L.conv("model.2.ffc.convl2l.weight", 1, 1); L.bn_fold("model.2.bn_l.", kBnEps, &m->d1.scale, &m->d1.shift);
     m->d2 = L.conv("model.3.ffc.convl2l.weight", 1, 1); L.bn_fold("model.3.bn_l.", kBnEps, &m->d2.scale, &m->d2.shift);
     m->d3l = L.conv("model.4.ffc.convl2l.weight", 1, 1); L.bn_fold("model.4.bn_l.", kBnEps, &m->d3l.scale, &m->d3l.shift);
@@ -122,19 +122,24 @@ void run_ffc_layer(Exec& e, const FfcLayer& l, const View& X, const View& Y, con
 }
 
 void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const int* rel_pos, const int* direct, int th,
-              int tw, int n, int h, int w, float* out, cudaStream_t st) {
+              int tw, int n, int h, int w, float* out, cudaStream_t st, const LamaU8Io* u8) {
   MITB_CHECK(n >= 1 && h % 8 == 0 && w % 8 == 0 && h >= 32 && w >= 32, "lama: input %dx%d must be a multiple of 8 (>=32)", h, w);
   MITB_CHECK(!m.use_mpe || (rel_pos && direct), "lama_mpe needs the rel_pos/direct tables");
   run_with_workspace(ctx, st, [&](Exec& e) {
     Arena& ws = e.ws();
     const int h8 = h / 8, w8 = w / 8;
     View X = ws.view(n, h8, w8, 512), Y = ws.view(n, h8, w8, 512), Z = ws.view(n, h8, w8, 512);
+    float* maskf = nullptr;            // planar fp32 {0,1} mask when the input arrives as uint8
+    MITB_CHECK(!u8 || n == 1, "lama uint8 entry handles one image per call");
     {
       const size_t mk = ws.mark();
-      View x4 = ws.view(n, h, w, 4), s1 = ws.view(n, h, w, 64), s2 = ws.view(n, h / 2, w / 2, 128), s3 = ws.view(n, h / 4, w / 4, 256);
-      if (!e.dry) launch_lama_pack_input(img, mask, n, h, w, x4, st);
+      View x4 = ws.view(n, h, w, 8), s1 = ws.view(n, h, w, 64), s2 = ws.view(n, h / 2, w / 2, 128), s3 = ws.view(n, h / 4, w / 4, 256);
+      if (u8) {
+        maskf = ws.alloc_f((size_t)h * w);
+        if (!e.dry) launch_lama_pack_u8(u8->img, u8->mask, h, w, x4, maskf, st);
+      } else if (!e.dry) launch_lama_pack_input(img, mask, n, h, w, x4, st);
       { ConvOp op = Exec::op_from(m.stem, x4, s1, 1, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
-      if (m.use_mpe && !e.dry) launch_mpe_add(s1, rel_pos, direct, th, tw, mask, m.mpe_table, m.mpe_dirw, m.a5, m.a6, st);
+      if (m.use_mpe && !e.dry) launch_mpe_add(s1, rel_pos, direct, th, tw, u8 ? maskf : mask, m.mpe_table, m.mpe_dirw, m.a5, m.a6, st);
       { ConvOp op = Exec::op_from(m.d1, s1, s2, 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
       { ConvOp op = Exec::op_from(m.d2, s2, s3, 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
       { ConvOp op = Exec::op_from(m.d3l, s3, X.slice(0, 128), 2, PAD_REFLECT); op.act = ACT_RELU; e.conv(op); }
@@ -154,7 +159,10 @@ void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const
     e.convT2(m.up[2].ph, u2, u3, [](ConvOp& op) { op.act = ACT_RELU; });
     View pred = ws.view(n, h, w, 3, true);
     { ConvOp op = Exec::op_from(m.outc, u3, pred, 1, PAD_REFLECT); op.act = ACT_SIGMOID; e.conv(op); }
-    if (!e.dry) launch_lama_blend(pred, img, mask, out, st);
+    if (!e.dry) {
+      if (u8) launch_lama_blend_u8(pred, u8->img, u8->mask, u8->out, u8->composite, st);
+      else launch_lama_blend(pred, img, mask, out, st);
+    }
   });
 }
 

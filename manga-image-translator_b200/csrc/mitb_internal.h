@@ -79,7 +79,7 @@ struct ConvOp {
 };
 
 void launch_conv(const ConvOp& op, cudaStream_t st);
-int conv_stat_blocks(int Cout);       // number of column blocks the row-stat epilogue writes per row
+int conv_stat_blocks(const ConvOp& op);   // number of column blocks the row-stat epilogue writes per row
 void launch_rowstat_final(const float* pmax, const float* psum, const int* pidx, int rows, int nblk,
                           int* idx, float* logprob, cudaStream_t st);
 
@@ -103,6 +103,8 @@ void launch_attention(const float* qk /*[N*T,2D]*/, const float* v /*[N*T,D]*/, 
                       int N, int T, int heads, int hd, cudaStream_t st);
 void launch_lama_pack_input(const float* img, const float* mask, int N, int H, int W, const View& dst, cudaStream_t st);
 void launch_lama_blend(const View& pred, const float* img, const float* mask, float* out, cudaStream_t st);
+void launch_lama_pack_u8(const uint8_t* img, const uint8_t* mask, int H, int W, const View& dst, float* maskf, cudaStream_t st);
+void launch_lama_blend_u8(const View& pred, const uint8_t* img, const uint8_t* mask, uint8_t* out, int composite, cudaStream_t st);
 void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, int th, int tw, const float* mask,
                     const float* table, const float* dirw, float a5, float a6, cudaStream_t st);
 
@@ -173,8 +175,9 @@ void ocr_run(Ctx&, OcrModel&, const float* x_nchw, const uint8_t* x_u8, int n, i
 int ocr_vocab(const OcrModel&);
 LamaModel* lama_build(Ctx&, const Weights&);
 void lama_free(LamaModel*);
+struct LamaU8Io { const uint8_t* img = nullptr; const uint8_t* mask = nullptr; uint8_t* out = nullptr; int composite = 0; };
 void lama_run(Ctx&, LamaModel&, const float* img, const float* mask, const int* rel_pos, const int* direct, int th,
-              int tw, int n, int h, int w, float* out, cudaStream_t st);
+              int tw, int n, int h, int w, float* out, cudaStream_t st, const LamaU8Io* u8 = nullptr);
 
 struct Profiler {
   struct Rec { const char* kind; double flops, bytes; cudaEvent_t a, b; };

@@ -186,15 +186,14 @@ void ocr_run(Ctx& ctx, OcrModel& m, const float* x_nchw, const uint8_t* x_u8, in
     { ConvOp op = Exec::op_from(m.color, x, cv); op.act = ACT_CLAMP01; e.conv(op); }
     e.layernorm(x, z, m.cpn_w, m.cpn_b, kLnEps5);
     if (!e.dry) launch_affine_act(z, z, nullptr, nullptr, ACT_GELU, st);
-    const int rows = n * T, nblk = conv_stat_blocks(m.vocab);
+    const int rows = n * T;
+    View dummy = z; dummy.C = m.vocab; dummy.cs = m.vocab; dummy.p = nullptr;
+    ConvOp vop = Exec::op_from(m.char_pred, z, dummy);
+    const int nblk = conv_stat_blocks(vop);
     float* pmax = ws.alloc_f((size_t)rows * nblk); float* psum = ws.alloc_f((size_t)rows * nblk);
     int* pidx = (int*)ws.alloc((size_t)rows * nblk * sizeof(int));
-    {
-      View dummy = z; dummy.C = m.vocab; dummy.cs = m.vocab; dummy.p = nullptr;
-      ConvOp op = Exec::op_from(m.char_pred, z, dummy);
-      op.stat_max = pmax; op.stat_sum = psum; op.stat_idx = pidx; op.stat_ld = nblk;
-      e.conv(op);
-    }
+    vop.stat_max = pmax; vop.stat_sum = psum; vop.stat_idx = pidx; vop.stat_ld = nblk;
+    e.conv(vop);
     if (!e.dry) launch_rowstat_final(pmax, psum, pidx, rows, nblk, idx, logprob, st);
   });
 }

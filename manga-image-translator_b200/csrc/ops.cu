@@ -347,7 +347,7 @@ void launch_attention(const float* qk, const float* v, float* out, int N, int T,
 
 // ---------------------------------------------------------------------------------------------------
 // LaMa glue.  pack: cat(img*(1-mask), mask) NCHW -> NHWC 4 channels (inpainting_lama_mpe.py:604).
-__global__ void lama_pack_kernel(const float* img, const float* mask, int N, long HW, float* dst, int cs, int coff) {
+__global__ void lama_pack_kernel(const float* img, const float* mask, int N, long HW, float* dst, int cs, int coff, int Cv) {
   const long total = (long)N * HW;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long pix = i % HW; const int n = (int)(i / HW);
@@ -358,12 +358,13 @@ __global__ void lama_pack_kernel(const float* img, const float* mask, int N, lon
     v.z = img[((size_t)n * 3 + 2) * HW + pix] * (1.f - m);
     v.w = m;
     *reinterpret_cast<float4*>(dst + i * cs + coff) = v;
+    if (Cv == 8) *reinterpret_cast<float4*>(dst + i * cs + coff + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 void launch_lama_pack_input(const float* img, const float* mask, int N, int H, int W, const View& dst, cudaStream_t st) {
   const long total = (long)N * H * W;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
-  lama_pack_kernel<<<blocks, 256, 0, st>>>(img, mask, N, (long)H * W, dst.p, dst.cs, dst.coff);
+  lama_pack_kernel<<<blocks, 256, 0, st>>>(img, mask, N, (long)H * W, dst.p, dst.cs, dst.coff, dst.C);
   LAUNCH_END();
 }
 
@@ -381,6 +382,54 @@ void launch_lama_blend(const View& pred, const float* img, const float* mask, fl
   const long total = (long)pred.N * 3 * pred.H * pred.W;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
   lama_blend_kernel<<<blocks, 256, 0, st>>>(pred.p, img, mask, out, pred.N, (long)pred.H * pred.W);
+  LAUNCH_END();
+}
+
+// uint8 front/back end of LamaMPEInpainter._infer fused on the device (inpainting_lama_mpe.py:82-92 and :109-117):
+//   front: img/255 (fp32 division), mask/255 >= 0.5 -> {0,1}, img *= 1-mask, cat(img*(1-mask), mask) -> NHWC view, + planar mask
+//   back : pred*mask + (1-mask)*img -> (x*255).astype(uint8) (truncation) -> optional composite with the original page where
+//          the ORIGINAL mask >= 127 (the two thresholds differ at mask value 127, kept as in the reference)
+__global__ void lama_pack_u8_kernel(const uint8_t* img, const uint8_t* mask, long npix, float* dst, int cs, int coff, int Cv,
+                                    float* maskf) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+    const float m = __fdiv_rn((float)mask[i], 255.f) >= 0.5f ? 1.f : 0.f;
+    const float k = 1.f - m;
+    float4 v;
+    v.x = __fdiv_rn((float)img[i * 3 + 0], 255.f) * k * k;     // premask in _infer (:92) and again in the generator (:604)
+    v.y = __fdiv_rn((float)img[i * 3 + 1], 255.f) * k * k;
+    v.z = __fdiv_rn((float)img[i * 3 + 2], 255.f) * k * k;
+    v.w = m;
+    *reinterpret_cast<float4*>(dst + i * cs + coff) = v;
+    if (Cv == 8) *reinterpret_cast<float4*>(dst + i * cs + coff + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    maskf[i] = m;
+  }
+}
+void launch_lama_pack_u8(const uint8_t* img, const uint8_t* mask, int H, int W, const View& dst, float* maskf, cudaStream_t st) {
+  const long total = (long)H * W;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  lama_pack_u8_kernel<<<blocks, 256, 0, st>>>(img, mask, total, dst.p, dst.cs, dst.coff, dst.C, maskf);
+  LAUNCH_END();
+}
+
+__global__ void lama_blend_u8_kernel(const float* pred, const uint8_t* img, const uint8_t* mask, uint8_t* out, long HW, int composite) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < HW; i += (long)gridDim.x * blockDim.x) {
+    const uint8_t mv = mask[i];
+    const bool hole = __fdiv_rn((float)mv, 255.f) >= 0.5f;
+    const bool keep_orig = composite && mv < 127;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint8_t o = img[i * 3 + c];
+      const float x = hole ? pred[(size_t)c * HW + i] : __fdiv_rn((float)o, 255.f);
+      const uint8_t q = (uint8_t)(int)__fmul_rn(x, 255.f);                 // numpy float32 -> uint8: truncation
+      out[i * 3 + c] = keep_orig ? o : q;
+    }
+  }
+}
+void launch_lama_blend_u8(const View& pred, const uint8_t* img, const uint8_t* mask, uint8_t* out, int composite, cudaStream_t st) {
+  MITB_CHECK(pred.planar && pred.C == 3 && pred.cs == 3 && pred.coff == 0 && pred.N == 1, "blend_u8 expects one planar 3-channel prediction");
+  const long total = (long)pred.H * pred.W;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  lama_blend_u8_kernel<<<blocks, 256, 0, st>>>(pred.p, img, mask, out, total, composite);
   LAUNCH_END();
 }
 

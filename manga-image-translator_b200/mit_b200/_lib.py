@@ -47,6 +47,7 @@ SIGNATURES = {
     "mitb_lama_unload": (I, [P]),
     "mitb_lama_forward": (I, [P, P, P, P, P, I, I, I, P, P]),
     "mitb_lama_forward_mpe256": (I, [P, P, P, P, P, I, I, I, P, P]),
+    "mitb_lama_infer_u8": (I, [P, P, P, P, P, I, I, I, P, P]),
     "mitb_op_conv2d": (I, [P, P, I, I, I, I, P, I, I, I, I, I, I, I, I, P, I, P, P, I, P, P]),
     "mitb_op_conv_transpose2d": (I, [P, P, I, I, I, I, P, I, I, I, I, P, I, P, P]),
     "mitb_op_dwconv7_ln": (I, [P, P, I, I, I, I, P, P, P, P, F, P, P]),

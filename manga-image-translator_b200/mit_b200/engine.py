@@ -3,6 +3,7 @@ memory containers) to the library and returns torch tensors.  No arithmetic of t
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Dict, Optional
 
 import numpy as np
@@ -33,6 +34,7 @@ class Engine:
             raise MitbError(self.lib.mitb_last_error(None).decode())
         self._h = h
         self._keep = {}
+        self._lock = threading.RLock()   # the context is not re-entrant: page-pipeline threads serialise their ENQUEUES here
         self.h2d_bytes = 0      # bytes moved host->device / device->host through h2d()/d2h() (bench.py e2e accounting)
         self.d2h_bytes = 0
 
@@ -64,6 +66,10 @@ class Engine:
         if rc != 0:
             raise MitbError(self.lib.mitb_last_error(self._h).decode())
 
+    def _call(self, fn, *args):
+        with self._lock:
+            self._check(fn(self._h, *args))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -72,7 +78,7 @@ class Engine:
         self.lib.mitb_set_tensor_cores(1 if on else 0)
 
     def profile(self, on: bool):
-        self._check(self.lib.mitb_profile_enable(self._h, 1 if on else 0))
+        self._call(self.lib.mitb_profile_enable, 1 if on else 0)
 
     def profile_report(self) -> dict:
         import json
@@ -105,7 +111,7 @@ class Engine:
     # ------------------------------------------------------------------ models
     def load_dbnet(self, state_dict):
         arr, keep = self._tensors(self._float_sd(state_dict))
-        self._check(self.lib.mitb_dbnet_load(self._h, arr, len(arr)))
+        self._call(self.lib.mitb_dbnet_load, arr, len(arr))
         torch.cuda.synchronize(self.device)
 
     def unload_dbnet(self):
@@ -121,7 +127,7 @@ class Engine:
         db = torch.empty((n, 2, h, w), dtype=torch.float32, device=self.device)
         mask = torch.empty((n, 1, h // 2, w // 2), dtype=torch.float32, device=self.device)
         fn = self.lib.mitb_dbnet_forward_u8 if x.dtype == torch.uint8 else self.lib.mitb_dbnet_forward
-        self._check(fn(self._h, _ptr(x), n, h, w, _ptr(db), _ptr(mask), self._stream()))
+        self._call(fn, _ptr(x), n, h, w, _ptr(db), _ptr(mask), self._stream())
         return db, mask
 
     def load_ocr(self, state_dict, pe_table: Optional[torch.Tensor] = None):
@@ -130,7 +136,7 @@ class Engine:
         if pe_table is not None:
             sd["pe.table"] = pe_table
         arr, keep = self._tensors(sd)
-        self._check(self.lib.mitb_ocr_load(self._h, arr, len(arr)))
+        self._call(self.lib.mitb_ocr_load, arr, len(arr))
         torch.cuda.synchronize(self.device)
 
     def unload_ocr(self):
@@ -148,7 +154,7 @@ class Engine:
         lp = torch.empty((n, T), dtype=torch.float32, device=self.device)
         col = torch.empty((n, T, 6), dtype=torch.float32, device=self.device)
         fn = self.lib.mitb_ocr_forward_u8 if x.dtype == torch.uint8 else self.lib.mitb_ocr_forward
-        self._check(fn(self._h, _ptr(x), n, wp, _ptr(idx), _ptr(lp), _ptr(col), self._stream()))
+        self._call(fn, _ptr(x), n, wp, _ptr(idx), _ptr(lp), _ptr(col), self._stream())
         return idx, lp, col
 
     def load_lama(self, gen_state_dict, mpe_state_dict=None):
@@ -157,7 +163,7 @@ class Engine:
             for k, v in mpe_state_dict.items():
                 sd["mpe." + k] = v
         arr, keep = self._tensors(sd)
-        self._check(self.lib.mitb_lama_load(self._h, arr, len(arr)))
+        self._call(self.lib.mitb_lama_load, arr, len(arr))
         torch.cuda.synchronize(self.device)
 
     def unload_lama(self):
@@ -173,7 +179,15 @@ class Engine:
             direct = torch.as_tensor(direct).to(self.device, torch.int32).contiguous()
         out = torch.empty_like(img)
         fn = self.lib.mitb_lama_forward_mpe256 if (tables256 and rel_pos is not None) else self.lib.mitb_lama_forward
-        self._check(fn(self._h, _ptr(img), _ptr(mask), _ptr(rel_pos), _ptr(direct), n, h, w, _ptr(out), self._stream()))
+        self._call(fn, _ptr(img), _ptr(mask), _ptr(rel_pos), _ptr(direct), n, h, w, _ptr(out), self._stream())
+        return out
+
+    def lama_infer_u8(self, img_u8: torch.Tensor, mask_u8: torch.Tensor, rel256=None, direct256=None, composite=True):
+        """Device part of LamaMPEInpainter._infer on uint8 data: img [h,w,3], mask [h,w] (device, network resolution)."""
+        h, w, _ = img_u8.shape
+        out = torch.empty_like(img_u8)
+        self._call(self.lib.mitb_lama_infer_u8, _ptr(img_u8), _ptr(mask_u8), _ptr(rel256), _ptr(direct256), h, w,
+                                                1 if composite else 0, _ptr(out), self._stream())
         return out
 
     # ------------------------------------------------------------------ standalone operators (tests / micro-benchmarks)
@@ -188,9 +202,9 @@ class Engine:
         ho = (h + 2 * padding[0] - kh) // stride[0] + 1
         wo = (wd + 2 * padding[1] - kw) // stride[1] + 1
         y = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=self.device)
-        self._check(self.lib.mitb_op_conv2d(self._h, _ptr(x), n, cin, h, wd, _ptr(w), cout, kh, kw, stride[0], stride[1],
+        self._call(self.lib.mitb_op_conv2d, _ptr(x), n, cin, h, wd, _ptr(w), cout, kh, kw, stride[0], stride[1],
                                             padding[0], padding[1], 1 if pad_mode == "reflect" else 0, _ptr(bias), act,
-                                            _ptr(in_scale), _ptr(in_shift), int(in_relu), _ptr(y), self._stream()))
+                                            _ptr(in_scale), _ptr(in_shift), int(in_relu), _ptr(y), self._stream())
         return y
 
     def conv_transpose2d(self, x, w, bias=None, k=2, pad=0, out_pad=0, act=0):
@@ -198,50 +212,50 @@ class Engine:
         n, cin, h, wd = x.shape
         cout = w.shape[1]
         y = torch.empty((n, cout, 2 * h, 2 * wd), dtype=torch.float32, device=self.device)
-        self._check(self.lib.mitb_op_conv_transpose2d(self._h, _ptr(x), n, cin, h, wd, _ptr(w), cout, k, pad, out_pad,
-                                                      _ptr(bias), act, _ptr(y), self._stream()))
+        self._call(self.lib.mitb_op_conv_transpose2d, _ptr(x), n, cin, h, wd, _ptr(w), cout, k, pad, out_pad,
+                                                      _ptr(bias), act, _ptr(y), self._stream())
         return y
 
     def dwconv7_ln(self, x, wdw, bdw, lnw, lnb, eps=1e-6):
         x, wdw, bdw, lnw, lnb = map(self._dev, (x, wdw, bdw, lnw, lnb))
         n, c, h, w = x.shape
         y = torch.empty_like(x)
-        self._check(self.lib.mitb_op_dwconv7_ln(self._h, _ptr(x), n, c, h, w, _ptr(wdw), _ptr(bdw), _ptr(lnw), _ptr(lnb),
-                                                eps, _ptr(y), self._stream()))
+        self._call(self.lib.mitb_op_dwconv7_ln, _ptr(x), n, c, h, w, _ptr(wdw), _ptr(bdw), _ptr(lnw), _ptr(lnb),
+                                                eps, _ptr(y), self._stream())
         return y
 
     def layernorm(self, x, w, b, eps):
         x, w, b = map(self._dev, (x, w, b))
         rows, c = x.shape
         y = torch.empty_like(x)
-        self._check(self.lib.mitb_op_layernorm(self._h, _ptr(x), rows, c, _ptr(w), _ptr(b), eps, _ptr(y), self._stream()))
+        self._call(self.lib.mitb_op_layernorm, _ptr(x), rows, c, _ptr(w), _ptr(b), eps, _ptr(y), self._stream())
         return y
 
     def rfft2(self, x):
         x = self._dev(x)
         c, h, w = x.shape
         spec = torch.empty((2 * c, h, w // 2 + 1), dtype=torch.float32, device=self.device)
-        self._check(self.lib.mitb_op_rfft2(self._h, _ptr(x), c, h, w, _ptr(spec), self._stream()))
+        self._call(self.lib.mitb_op_rfft2, _ptr(x), c, h, w, _ptr(spec), self._stream())
         return spec
 
     def irfft2(self, spec, w):
         spec = self._dev(spec)
         c2, h, _ = spec.shape
         y = torch.empty((c2 // 2, h, w), dtype=torch.float32, device=self.device)
-        self._check(self.lib.mitb_op_irfft2(self._h, _ptr(spec), c2 // 2, h, w, _ptr(y), self._stream()))
+        self._call(self.lib.mitb_op_irfft2, _ptr(spec), c2 // 2, h, w, _ptr(y), self._stream())
         return y
 
     def attention(self, qk, v, n, t, heads, hd):
         qk, v = map(self._dev, (qk, v))
         out = torch.empty_like(v)
-        self._check(self.lib.mitb_op_attention(self._h, _ptr(qk), _ptr(v), n, t, heads, hd, _ptr(out), self._stream()))
+        self._call(self.lib.mitb_op_attention, _ptr(qk), _ptr(v), n, t, heads, hd, _ptr(out), self._stream())
         return out
 
     def bilateral17(self, img_u8):
         img = torch.as_tensor(img_u8).to(self.device, torch.uint8).contiguous()
         h, w, _ = img.shape
         out = torch.empty_like(img)
-        self._check(self.lib.mitb_op_bilateral17(self._h, _ptr(img), h, w, _ptr(out), self._stream()))
+        self._call(self.lib.mitb_op_bilateral17, _ptr(img), h, w, _ptr(out), self._stream())
         return out
 
 

@@ -207,6 +207,11 @@ def can_merge_region(a: Quadrilateral, b: Quadrilateral, ratio=1.9, discard_conn
     """Whether two text lines belong to one region (generic.py:653-698)."""
     (x1, y1, w1, h1), (x2, y2, w2, h2) = a.aabb, b.aabb
     char_size = min(a.font_size, b.font_size)
+    # exact early-out: the AABB gap is a lower bound of the polygon distance
+    gx = max(0, max(x1, x2) - min(x1 + w1, x2 + w2))
+    gy = max(0, max(y1, y2) - min(y1 + h1, y2 + h2))
+    if (gx * gx + gy * gy) ** 0.5 > discard_connection_gap * char_size:
+        return False
     dist = polygon_distance(a.pts, b.pts)
     if dist > discard_connection_gap * char_size:
         return False

@@ -34,8 +34,7 @@ class PageResult:
 class StagedPage:
     page_u8: torch.Tensor                   # [H,W,3] uint8 on device
     ocr_chunks: List[torch.Tensor]          # uint8 [n,48,wp,3] on device
-    img: torch.Tensor                       # [1,3,H,W] fp32, pre-masked
-    mask: torch.Tensor                      # [1,1,H,W] fp32 {0,1}
+    mask_u8: torch.Tensor                   # [H,W] uint8 on device
     rel_pos: Optional[torch.Tensor]
     direct: Optional[torch.Tensor]
     bytes: int = 0
@@ -73,6 +72,16 @@ class HotPath:
         out = asyncio.run(self.inp.infer(page, mask, InpainterConfig(), self.inpainting_size))
         return PageResult(textlines, raw_mask, lines, out)
 
+    def process_pages(self, items, workers: int = 4) -> List[PageResult]:
+        """A batch of (page, quads, mask) through the same three ``infer`` calls per page, with `workers` host threads so one
+        page's host work (H2D/D2H, contours, crops, CTC collapse) overlaps other pages' kernels.  GPU submissions are
+        serialised by the engine lock and execute in stream order; results come back in input order."""
+        if workers <= 1 or len(items) <= 1:
+            return [self.process_page(*it) for it in items]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            return list(ex.map(lambda it: self.process_page(*it), items))
+
     # ------------------------------------------------------------------ device-resident path
     def stage(self, page: np.ndarray, quads, mask: np.ndarray) -> StagedPage:
         eng = self.engine
@@ -86,14 +95,12 @@ class HotPath:
             for i, idx in enumerate(indices):
                 canvas[i, :, :widths[i]] = regions[idx]
             chunks_dev.append(torch.from_numpy(canvas).to(dev))
-        m = (torch.from_numpy(mask).float() / 255.0 >= 0.5).float()[None, None]
-        img = torch.from_numpy(page).permute(2, 0, 1)[None].float() / 255.0 * (1 - m)
         rel = direct = None
         if self.use_mpe:
-            r, d = mpe.mpe_tables_256(m[0, 0].numpy())
+            r, d = mpe.mpe_tables_256(((mask.astype(np.float32) / 255.0) >= 0.5).astype(np.float32))
             rel, direct = torch.from_numpy(r[None]).to(dev), torch.from_numpy(d[None]).to(dev)
-        sp = StagedPage(torch.from_numpy(page).to(dev), chunks_dev, img.to(dev), m.to(dev), rel, direct)
-        sp.bytes = sum(t.numel() * t.element_size() for t in [sp.page_u8, sp.img, sp.mask] + chunks_dev +
+        sp = StagedPage(torch.from_numpy(page).to(dev), chunks_dev, torch.from_numpy(mask).to(dev), rel, direct)
+        sp.bytes = sum(t.numel() * t.element_size() for t in [sp.page_u8, sp.mask_u8] + chunks_dev +
                        ([rel, direct] if rel is not None else []))
         return sp
 
@@ -102,7 +109,7 @@ class HotPath:
         filt = eng.bilateral17(sp.page_u8)
         db, dmask = eng.dbnet_forward(filt[None])
         ocr = [eng.ocr_forward(c) for c in sp.ocr_chunks]
-        out = eng.lama_forward(sp.img, sp.mask, sp.rel_pos, sp.direct, tables256=True)
+        out = eng.lama_infer_u8(sp.page_u8, sp.mask_u8, sp.rel_pos, sp.direct, composite=True)
         return db, dmask, ocr, out
 
 

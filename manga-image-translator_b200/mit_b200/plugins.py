@@ -257,20 +257,21 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
             image = cv2.resize(image, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
             mask = cv2.resize(mask, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
         self.logger.info(f"Inpainting resolution: {new_w}x{new_h}")
-        img_t = torch.from_numpy(image).permute(2, 0, 1).unsqueeze_(0).float() / 255.0
-        mask_t = torch.from_numpy(mask).unsqueeze_(0).unsqueeze_(0).float() / 255.0
-        mask_t[mask_t < 0.5] = 0
-        mask_t[mask_t >= 0.5] = 1
-        img_t *= (1 - mask_t)
+        eng = self.engine
+        resized = (new_h, new_w) != (height, width)
         rel_pos = direct = None
         if self._USE_MPE:
-            rel_pos, direct = mpe.mpe_tables_256(mask_t[0, 0].numpy())     # upsampled inside the kernel
-            rel_pos, direct = rel_pos[None], direct[None]
-        eng = self.engine
-        if rel_pos is not None:
-            rel_pos, direct = eng.h2d(rel_pos), eng.h2d(direct)
-        out = eng.lama_forward(eng.h2d(img_t), eng.h2d(mask_t), rel_pos, direct, tables256=True)
-        img_inpainted = (torch.from_numpy(eng.d2h(out)).squeeze_(0).permute(1, 2, 0).numpy() * 255.0).astype(np.uint8)
+            # 256x256 tables on the host (binary morphology on a tiny image); upsampled inside the kernel
+            mask01 = ((mask.astype(np.float32) / 255.0) >= 0.5).astype(np.float32)
+            rel_pos, direct = mpe.mpe_tables_256(mask01)
+            rel_pos, direct = eng.h2d(rel_pos[None]), eng.h2d(direct[None])
+        # /255, mask binarisation, pre-masking, network, blend, (x*255) truncation and (when no resize happened) the final
+        # composite with the original page all run on the device; only uint8 crosses the bus.
+        out_dev = eng.lama_infer_u8(eng.h2d(np.ascontiguousarray(image)), eng.h2d(np.ascontiguousarray(mask)), rel_pos, direct,
+                                    composite=not resized)
+        img_inpainted = eng.d2h(out_dev)
+        if not resized:
+            return img_inpainted
         if new_h != height or new_w != width:
             img_inpainted = cv2.resize(img_inpainted, (width, height), interpolation=cv2.INTER_LINEAR)
         return img_inpainted * mask_original + img_original * (1 - mask_original)
