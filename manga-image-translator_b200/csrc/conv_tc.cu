@@ -8,13 +8,17 @@
 //     mid = bf16(x - hi); D += A_hi*B_hi + A_hi*B_mid + A_mid*B_hi.  The dropped terms are <= ~3*2^-18 relative
 //     (about 1e-5), far inside the 1e-3 parity budget, at 1/3 of the bf16 tensor rate (2x a 3xTF32 scheme).
 //   * K is consumed in blocks of 64 (one 128-byte swizzle row of bf16).  Warp-specialised:
-//       warps 0-3  gather the activation tile from the NHWC (or planar) view, apply the optional BN+ReLU prologue,
-//                  split hi/mid and store both tiles into shared memory in the UMMA K-major SWIZZLE_128B layout;
-//       warps 5-8  stream the pre-split, K-major bf16 weight tiles (hi/mid) into shared memory;
-//       warp  4    one elected thread issues tcgen05.mma (12 per K block) and commits to the stage's "empty" mbarrier;
+//       warps 0-7  gather the activation tile from the NHWC (or planar) view (two threads per GEMM row, register
+//                  prefetch of the next K block), apply the optional BN+ReLU prologue, split hi/mid and store both
+//                  tiles into shared memory in the UMMA K-major SWIZZLE_128B layout;
+//       warp  9    one thread streams the pre-split K-major bf16 weight tiles (hi/mid) with TMA (cp.async.bulk.tensor,
+//                  128B swizzle) straight into the stage, completing on the stage's "full" mbarrier (expect_tx);
+//       warp  8    one elected thread issues tcgen05.mma (12 per K block) and commits to the stage's "empty" mbarrier;
 //     full/empty mbarrier ring, producers signal after fence.proxy.async (generic-proxy stores -> async-proxy reads).
-//   * Epilogue: warps 0-3 read their 32 TMEM lanes with tcgen05.ld (one output pixel per thread), apply
-//     (+add0) * scale + shift -> activation -> * mul1 -> + add1 and store NHWC (or planar) fp32.
+//   * Epilogue: warps 0-7 read their 32 TMEM lanes with tcgen05.ld (one output pixel per thread, two warps share a
+//     lane quarter and split the columns), apply (+add0)*scale+shift -> activation -> *mul1 -> +add1 and store fp32.
+#include <cuda.h>
+#include <string.h>
 #include <cuda_bf16.h>
 #include "mitb_internal.h"
 
@@ -23,11 +27,13 @@ namespace mitb {
 namespace {
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TC_THREADS = 288;               // 4 A-producer warps + 1 MMA warp + 4 B-producer warps
+constexpr int TC_THREADS = 320;               // 8 A-producer/epilogue warps + 1 MMA warp + 1 TMA warp
+constexpr int TC_AWARPS = 8;
 
 struct TcParams {
   const float* in; int N, H, W, in_cs, in_coff, Cin, in_planar;
-  const uint16_t* wh; const uint16_t* wm; int kpad, npad;     // weights [npad][kpad] bf16, K-major, zero padded
+  CUtensorMap tmh, tmm;                                       // TMA descriptors of the hi / mid weight matrices
+  int kpad, npad;                                             // weights [npad][kpad] bf16, K-major, zero padded
   int ntaps; int8_t tdy[kMaxTaps], tdx[kMaxTaps];
   int sy, sx, pad, Ho, Wo;
   float* out; int oH, oW, out_cs, out_coff, Cout, out_planar, oy_mul, oy_add, ox_mul, ox_add;
@@ -69,6 +75,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       else if (now - t0 > 4000000000ll) __trap();          // ~2 s at 2 GHz: far beyond any legitimate wait
     }
   }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -140,7 +153,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mi
   mid = make_uint4(m[0], m[1], m[2], m[3]);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A_hi 16K | A_mid 16K | B_hi BN*128 | B_mid BN*128], then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -160,19 +173,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
   const int nkb = p.kpad / TC_BK;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 256); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_AWARPS * 32 + 1); mbar_init(empty_bar(s), 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == TC_AWARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // =========================== A producer: one output pixel (GEMM row) per thread ===========================
-    const int r = tid;
+  if (warp < TC_AWARPS) {
+    // =========================== A producer: two threads per output pixel (GEMM row), 4 chunks of 8 k each ===========
+    const int r = tid & 127, half = tid >> 7;
     const int m = m0 + r;
     const bool row_ok = m < p.M;
     const int HoWo = p.Ho * p.Wo, HW = p.H * p.W;
@@ -182,17 +195,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
       iy0 = oy * p.sy; ix0 = ox * p.sx; pix = rr;
     }
-    int tap = 0, ci = 0;                       // cursor of the next 8-channel chunk
+    int tap = 0, ci = half * 32;               // cursor of this thread's next 8-channel chunk
+    if (!p.in_planar) while (ci >= p.Cin) { ci -= p.Cin; ++tap; }
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % S;
-      float v[8][8];
+    float nxt[4][8];
+
+    auto load_block = [&](int kb) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int k = kb * TC_BK + c * 8;
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb * TC_BK + half * 32 + j * 8;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[c][e] = 0.f;
+        for (int e = 0; e < 8; ++e) nxt[j][e] = 0.f;
         if (row_ok && k < p.K) {
           if (!p.in_planar) {
             int iy = iy0 + p.tdy[tap], ix = ix0 + p.tdx[tap];
@@ -202,12 +216,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             if (inb) {
               const float* src = p.in + ((size_t)(nimg * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci;
               const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-              v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+              nxt[j][0] = a.x; nxt[j][1] = a.y; nxt[j][2] = a.z; nxt[j][3] = a.w;
+              nxt[j][4] = b.x; nxt[j][5] = b.y; nxt[j][6] = b.z; nxt[j][7] = b.w;
               if (p.in_scale) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  float t = v[c][e] * p.in_scale[ci + e] + p.in_shift[ci + e];
-                  v[c][e] = p.in_relu ? fmaxf(t, 0.f) : t;
+                  const float t = nxt[j][e] * __ldg(p.in_scale + ci + e) + __ldg(p.in_shift + ci + e);
+                  nxt[j][e] = p.in_relu ? fmaxf(t, 0.f) : t;
                 }
               }
             }
@@ -217,25 +232,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
               const int ch = k + e;
               if (ch < p.K) {
                 float t = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + ch) * HW + pix);
-                if (p.in_scale) { t = t * p.in_scale[ch] + p.in_shift[ch]; if (p.in_relu) t = fmaxf(t, 0.f); }
-                v[c][e] = t;
+                if (p.in_scale) { t = t * __ldg(p.in_scale + ch) + __ldg(p.in_shift + ch); if (p.in_relu) t = fmaxf(t, 0.f); }
+                nxt[j][e] = t;
               }
             }
           }
         }
-        ci += 8;
-        while (ci >= p.Cin && !p.in_planar) { ci -= p.Cin; ++tap; }
+        if (!p.in_planar) { ci += 8; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
       }
+      // skip the other half-row's 32 channels
+      if (!p.in_planar) { ci += 32; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
+    };
+
+    load_block(0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      uint4 hi[4], mid[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split8(nxt[j], hi[j], mid[j]);
+      if (kb + 1 < nkb) load_block(kb + 1);            // global loads of the next block fly while we wait / store
       mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
       uint8_t* a_hi = smem + (size_t)s * stage_bytes;
       uint8_t* a_mid = a_hi + a_bytes;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 hi, mid;
-        split8(v[c], hi, mid);
-        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
-        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-        *reinterpret_cast<uint4*>(a_mid + off) = mid;
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = (uint32_t)(half * 4 + j);
+        const uint32_t off = row_off + ((c ^ sw) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off) = hi[j];
+        *reinterpret_cast<uint4*>(a_mid + off) = mid[j];
       }
       fence_async_smem();
       mbar_arrive(full_bar(s));
@@ -247,12 +271,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     const int px = row_ok ? ((pix % p.Wo) * p.ox_mul + p.ox_add) : 0;
     const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
     const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int nchunks = BN / 16, h0 = (nchunks + 1) / 2;
+    const int cb_lo = (half == 0 ? 0 : h0) * 16, cb_hi = (half == 0 ? h0 : nchunks) * 16;
     if (p.stat_max) {
-      // vocabulary head: online (max, first argmax, sum exp) over this tile's columns; one thread owns one row, so no
-      // cross-thread reduction is needed.  The logits never leave TMEM (model_48px_ctc.py:460-461).
+      // vocabulary head: online (max, first argmax, sum exp) over this thread's columns of its row; the logits never
+      // leave TMEM (model_48px_ctc.py:460-461).  Two partials per N tile (one per column half).
       float bm = -INFINITY, bs = 0.f; int bi = 0x7fffffff;
-      for (int cb = 0; cb < BN; cb += 16) {
+      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
         uint32_t raw[16];
         tmem_ld16(taddr_row + (uint32_t)cb, raw);
         tmem_ld_wait();
@@ -260,18 +286,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         for (int e = 0; e < 16; ++e) {
           const int c = n0 + cb + e;
           if (c < p.Cout) {
-            const float x = __uint_as_float(raw[e]) + (p.shift ? p.shift[c] : 0.f);
+            const float x = __uint_as_float(raw[e]) + (p.shift ? __ldg(p.shift + c) : 0.f);
             if (x > bm) { bs = bs * expf(bm - x) + 1.f; bm = x; bi = c; }
             else bs += expf(x - bm);
           }
         }
       }
       if (row_ok) {
-        const size_t o = (size_t)m * p.stat_ld + blockIdx.y;
+        const size_t o = (size_t)m * p.stat_ld + blockIdx.y * 2 + half;
         p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
       }
     } else
-    for (int cb = 0; cb < BN; cb += 16) {
+    for (int cb = cb_lo; cb < cb_hi; cb += 16) {
       uint32_t raw[16];
       tmem_ld16(taddr_row + (uint32_t)cb, raw);
       tmem_ld_wait();
@@ -307,10 +333,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
           const int c = cq + e;
           if (c < p.Cout) {
             float x = v4[e];
-            if (p.scale) x *= p.scale[c];
-            if (p.shift) x += p.shift[c];
+            if (p.scale) x *= __ldg(p.scale + c);
+            if (p.shift) x += __ldg(p.shift + c);
             x = apply_act_tc(x, p.act);
-            if (p.mul1) x *= p.mul1[c];
+            if (p.mul1) x *= __ldg(p.mul1 + c);
             v4[e] = x;
           }
         }
@@ -330,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == TC_AWARPS) {
     // =========================== MMA issuer (one elected thread) ===========================
     if (lane == 0) {
       // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9 / 10-12 = 1), K-major A and B,
@@ -356,30 +382,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     }
     __syncwarp();
   } else {
-    // =========================== B producer: pre-split K-major bf16 weights ===========================
-    const int t = tid - 160;                   // 0..127
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % S;
-      mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
-      uint8_t* b_hi = smem + (size_t)s * stage_bytes + 2 * a_bytes;
-      uint8_t* b_mid = b_hi + b_bytes;
-      // BN rows x 8 chunks per array; consecutive threads take consecutive chunks of a row (coalesced 128 B rows)
-      for (int i = t; i < BN * 8; i += 128) {
-        const int row = i >> 3, c = i & 7;
-        const size_t g = ((size_t)(n0 + row) * p.kpad + (size_t)kb * TC_BK) * 2 + (size_t)c * 16;
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.wh) + g));
-        const uint4 mm = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.wm) + g));
-        const uint32_t off = (uint32_t)row * 128u + (((uint32_t)c ^ (uint32_t)(row & 7)) << 4);
-        *reinterpret_cast<uint4*>(b_hi + off) = h;
-        *reinterpret_cast<uint4*>(b_mid + off) = mm;
+    // =========================== B producer: TMA of the pre-split K-major bf16 weight tiles ===========================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
+        const uint32_t b_hi = smem_base + (uint32_t)s * stage_bytes + 2 * a_bytes, b_mid = b_hi + b_bytes;
+        mbar_arrive_expect_tx(full_bar(s), 2 * b_bytes);
+        tma_load_2d(b_hi, &p.tmh, full_bar(s), kb * TC_BK, n0);
+        tma_load_2d(b_mid, &p.tmm, full_bar(s), kb * TC_BK, n0);
       }
-      fence_async_smem();
-      mbar_arrive(full_bar(s));
     }
+    __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+  if (warp == TC_AWARPS) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
+
 
 // fp32 K-major [K][ldw] (the SIMT layout) -> bf16 hi/mid [npad][kpad] K-major, zero padded
 __global__ void split_weights_kernel(const float* w, int K, int Cout, int ldw, uint16_t* wh, uint16_t* wm, int kpad, int npad) {
@@ -406,6 +425,33 @@ int pick_bn(int Cout) {
 static bool g_tc_enabled = true;
 void conv_tc_set_enabled(bool on) { g_tc_enabled = on; }
 
+// TMA descriptor of a K-major bf16 weight matrix [npad][kpad]: box = 64 k (128 bytes, SWIZZLE_128B) x BN rows.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    MITB_CHECK(p && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static void make_weight_tmap(TmaDesc* out, const uint16_t* base, int kpad, int npad, int bn) {
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {(cuuint64_t)kpad, (cuuint64_t)npad};
+  const cuuint64_t gstride[1] = {(cuuint64_t)kpad * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstride, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MITB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%d x %d] box %d", (int)r, npad, kpad, bn);
+  memcpy(out, &m, sizeof(m));
+}
+
 // Build the tensor-core weight copies for a conv (called at load time by the Loader)
 void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
   const int K = cw.ntaps * cw.Cin;
@@ -419,9 +465,11 @@ void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
   split_weights_kernel<<<blocks, 256, 0, st>>>(cw.w, K, cw.Cout, cw.ldw, wh, wm, cw.tc_kpad, cw.tc_npad);
   CUDA_OK(cudaGetLastError());
   cw.wh = wh; cw.wm = wm;
+  make_weight_tmap(&cw.tmh, wh, cw.tc_kpad, cw.tc_npad, bn);
+  make_weight_tmap(&cw.tmm, wm, cw.tc_kpad, cw.tc_npad, bn);
 }
 
-int conv_tc_stat_blocks(const ConvOp& op) { return op.tc_npad / op.tc_bn; }
+int conv_tc_stat_blocks(const ConvOp& op) { return 2 * (op.tc_npad / op.tc_bn); }   // two column halves per N tile
 
 bool conv_tc_supported(const ConvOp& op) {
   if (!g_tc_enabled || !op.wh || !op.wm) return false;
@@ -435,7 +483,9 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   TcParams p;
   p.in = op.in.p; p.N = op.in.N; p.H = op.in.H; p.W = op.in.W; p.in_cs = op.in.cs; p.in_coff = op.in.coff; p.Cin = op.in.C;
   p.in_planar = op.in.planar;
-  p.wh = op.wh; p.wm = op.wm; p.kpad = op.tc_kpad; p.npad = op.tc_npad;
+  static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "TmaDesc must mirror CUtensorMap");
+  memcpy(&p.tmh, &op.tmh, sizeof(CUtensorMap)); memcpy(&p.tmm, &op.tmm, sizeof(CUtensorMap));
+  p.kpad = op.tc_kpad; p.npad = op.tc_npad;
   p.ntaps = op.ntaps;
   for (int t = 0; t < op.ntaps; ++t) { p.tdy[t] = op.tdy[t]; p.tdx[t] = op.tdx[t]; }
   p.sy = op.sy; p.sx = op.sx; p.pad = op.pad; p.Ho = op.Ho; p.Wo = op.Wo;
@@ -446,7 +496,7 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
   p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
-  MITB_CHECK(!op.stat_max || op.stat_ld == op.tc_npad / op.tc_bn, "tc conv: stat_ld must equal conv_stat_blocks(op)");
+  MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tc conv: stat_ld must equal conv_stat_blocks(op)");
   p.M = op.in.N * op.Ho * op.Wo; p.K = op.ntaps * op.in.C; p.BN = op.tc_bn;
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tc conv: bad BN %d", p.BN);
   MITB_CHECK(p.in_planar || p.Cin % 8 == 0, "tc conv: Cin must be a multiple of 8");

@@ -15,7 +15,7 @@ struct Exec {
     for (int t = 0; t < w.ntaps; ++t) { op.tdy[t] = w.tdy[t]; op.tdx[t] = w.tdx[t]; }
     op.sy = op.sx = stride; op.pad = pad_mode; op.Ho = out.H; op.Wo = out.W;
     op.scale = w.scale; op.shift = w.shift;
-    op.wh = w.wh; op.wm = w.wm; op.tc_bn = w.tc_bn; op.tc_kpad = w.tc_kpad; op.tc_npad = w.tc_npad;
+    op.wh = w.wh; op.wm = w.wm; op.tc_bn = w.tc_bn; op.tc_kpad = w.tc_kpad; op.tc_npad = w.tc_npad; op.tmh = w.tmh; op.tmm = w.tmm;
     return op;
   }
   void conv(const ConvOp& op) { if (!dry) launch_conv(op, st); }

@@ -58,6 +58,8 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_SIGMOID =
 enum Pad { PAD_ZERO = 0, PAD_REFLECT = 1 };
 constexpr int kMaxTaps = 49;
 
+struct alignas(64) TmaDesc { uint64_t q[16]; };   // opaque CUtensorMap (128 bytes)
+
 struct ConvOp {
   View in, out;                       // out grid may be larger than the logical (Ho,Wo) grid (transposed phases)
   const float* w = nullptr;           // [ntaps*Cin][ldw] K-major rows, ldw = round4(Cout)
@@ -74,6 +76,7 @@ struct ConvOp {
   int act = ACT_NONE;
   // tensor-core copies of the weights (conv_tc.cu): bf16 hi/mid [tc_npad][tc_kpad], K-major; null -> SIMT path only
   const uint16_t* wh = nullptr; const uint16_t* wm = nullptr; int tc_bn = 0, tc_kpad = 0, tc_npad = 0;
+  TmaDesc tmh, tmm;                   // TMA descriptors of wh / wm
   // optional fused row statistics (vocabulary head): no tensor output, per (row, column-block) partials
   float* stat_max = nullptr; float* stat_sum = nullptr; int* stat_idx = nullptr; int stat_ld = 0;
 };
@@ -138,6 +141,7 @@ struct ConvW {
   int8_t tdy[kMaxTaps] = {0}, tdx[kMaxTaps] = {0};
   const float* scale = nullptr; const float* shift = nullptr;   // folded BN / bias (may be null)
   const uint16_t* wh = nullptr; const uint16_t* wm = nullptr; int tc_bn = 0, tc_kpad = 0, tc_npad = 0;
+  TmaDesc tmh, tmm;
 };
 struct DevBlob;
 void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st);   // build the bf16 hi/mid tensor-core weight copies
