@@ -43,6 +43,7 @@ struct TcParams {
   const float* scale; const float* shift; const float* mul1; int act;
   float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;     // fused log-softmax/argmax partials (vocabulary head)
   int M, K, BN, stages, tmem_cols;
+  int splits; float* partial;                                       // split-K: partial sums [splits][M][npad]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,16 +139,18 @@ __device__ __forceinline__ int reflect_tc(int i, int n) {
   return i;
 }
 
-// split 8 fp32 values into bf16 hi / mid packs (16 bytes each)
+// split 8 fp32 values into bf16 hi / mid packs (16 bytes each): 6 instructions per pair
+// (F2FP pack-convert for hi, shift/mask to get hi back as fp32, two FADD for the remainder, F2FP for mid)
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mid) {
   uint32_t h[4], m[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 m0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 m1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    m[i] = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);     // .x (low half) = v[2i]
+    const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hb);
+    const float h0 = __uint_as_float(hbits << 16), h1 = __uint_as_float(hbits & 0xffff0000u);
+    const __nv_bfloat162 mb = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+    h[i] = hbits;
+    m[i] = *reinterpret_cast<const uint32_t*>(&mb);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   mid = make_uint4(m[0], m[1], m[2], m[3]);
@@ -171,6 +174,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
   const int nkb = p.kpad / TC_BK;
+  // split-K: blockIdx.z owns the K blocks [kb_begin, kb_end) and writes raw partial sums (reduced by splitk_reduce_kernel)
+  const int kb_begin = (int)(((long)blockIdx.z * nkb) / p.splits), kb_end = (int)(((long)(blockIdx.z + 1) * nkb) / p.splits);
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_AWARPS * 32 + 1); mbar_init(empty_bar(s), 1); }
@@ -195,18 +200,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
       iy0 = oy * p.sy; ix0 = ox * p.sx; pix = rr;
     }
-    int tap = 0, ci = half * 32;               // cursor of this thread's next 8-channel chunk
-    if (!p.in_planar) while (ci >= p.Cin) { ci -= p.Cin; ++tap; }
+    int tap = 0, ci = 0;                       // cursor of this thread's next 8-channel chunk
+    if (!p.in_planar) { const int k0 = kb_begin * TC_BK + half * 32; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
-    float nxt[4][8];
+    struct Blk { float v[4][8]; int cix[4]; };        // raw loaded values + channel index of each chunk (-1: all zero)
+    Blk R0, R1;
 
-    auto load_block = [&](int kb) {
+    auto load_block = [&](int kb, Blk& B) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = kb * TC_BK + half * 32 + j * 8;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) nxt[j][e] = 0.f;
+        for (int e = 0; e < 8; ++e) B.v[j][e] = 0.f;
+        B.cix[j] = -1;
         if (row_ok && k < p.K) {
           if (!p.in_planar) {
             int iy = iy0 + p.tdy[tap], ix = ix0 + p.tdx[tap];
@@ -216,26 +223,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (inb) {
               const float* src = p.in + ((size_t)(nimg * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci;
               const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-              nxt[j][0] = a.x; nxt[j][1] = a.y; nxt[j][2] = a.z; nxt[j][3] = a.w;
-              nxt[j][4] = b.x; nxt[j][5] = b.y; nxt[j][6] = b.z; nxt[j][7] = b.w;
-              if (p.in_scale) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float t = nxt[j][e] * __ldg(p.in_scale + ci + e) + __ldg(p.in_shift + ci + e);
-                  nxt[j][e] = p.in_relu ? fmaxf(t, 0.f) : t;
-                }
-              }
+              B.v[j][0] = a.x; B.v[j][1] = a.y; B.v[j][2] = a.z; B.v[j][3] = a.w;
+              B.v[j][4] = b.x; B.v[j][5] = b.y; B.v[j][6] = b.z; B.v[j][7] = b.w;
+              B.cix[j] = ci;
             }
           } else {
+            B.cix[j] = k;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int ch = k + e;
-              if (ch < p.K) {
-                float t = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + ch) * HW + pix);
-                if (p.in_scale) { t = t * __ldg(p.in_scale + ch) + __ldg(p.in_shift + ch); if (p.in_relu) t = fmaxf(t, 0.f); }
-                nxt[j][e] = t;
-              }
-            }
+            for (int e = 0; e < 8; ++e)
+              if (k + e < p.K) B.v[j][e] = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + k + e) * HW + pix);
           }
         }
         if (!p.in_planar) { ci += 8; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
@@ -243,15 +239,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // skip the other half-row's 32 channels
       if (!p.in_planar) { ci += 32; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
     };
-
-    load_block(0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % S;
+    // BN+ReLU prologue (applied when the data is consumed, so the loads stay in flight) + hi/mid split + swizzled stores
+    auto produce = [&](int kb, Blk& B) {
+      const int s = (kb - kb_begin) % S;
       uint4 hi[4], mid[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split8(nxt[j], hi[j], mid[j]);
-      if (kb + 1 < nkb) load_block(kb + 1);            // global loads of the next block fly while we wait / store
-      mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
+      for (int j = 0; j < 4; ++j) {
+        if (p.in_scale && B.cix[j] >= 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ch = B.cix[j] + e;
+            if (!p.in_planar || ch < p.K) {
+              const float t = B.v[j][e] * __ldg(p.in_scale + ch) + __ldg(p.in_shift + ch);
+              B.v[j][e] = p.in_relu ? fmaxf(t, 0.f) : t;
+            }
+          }
+        }
+        split8(B.v[j], hi[j], mid[j]);
+      }
+      if (kb + 2 < kb_end) load_block(kb + 2, B);       // refill this ring slot: loads stay in flight for two K blocks
+      mbar_wait(empty_bar(s), (((kb - kb_begin) / S) & 1) ^ 1);
       uint8_t* a_hi = smem + (size_t)s * stage_bytes;
       uint8_t* a_mid = a_hi + a_bytes;
 #pragma unroll
@@ -263,6 +270,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       fence_async_smem();
       mbar_arrive(full_bar(s));
+    };
+
+    load_block(kb_begin, R0);
+    if (kb_begin + 1 < kb_end) load_block(kb_begin + 1, R1);
+    for (int kb = kb_begin; kb < kb_end; kb += 2) {
+      produce(kb, R0);
+      if (kb + 1 < kb_end) produce(kb + 1, R1);
     }
     // =========================== epilogue: TMEM -> registers -> global ===========================
     mbar_wait(done_bar, 0);
@@ -295,6 +309,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (row_ok) {
         const size_t o = (size_t)m * p.stat_ld + blockIdx.y * 2 + half;
         p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
+      }
+    } else if (p.splits > 1) {
+      // split-K partial: raw accumulators to partial[z][m][npad]
+      float* dst = p.partial + ((size_t)blockIdx.z * p.M + m) * p.npad + n0;
+      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr_row + (uint32_t)cb, raw);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(dst + cb + q * 4) = make_uint4(raw[q * 4], raw[q * 4 + 1], raw[q * 4 + 2], raw[q * 4 + 3]);
       }
     } else
     for (int cb = cb_lo; cb < cb_hi; cb += 16) {
@@ -362,9 +388,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9 / 10-12 = 1), K-major A and B,
       // N>>3 at bits 17-22, M>>4 at bits 24-28
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(full_bar(s), (kb / S) & 1);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int it = kb - kb_begin, s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);
         tc_fence_after();
         const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
         const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
@@ -372,7 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < TC_BK / 16; ++j) {
           const uint64_t adv = (uint64_t)(j * 2);                  // 16 bf16 = 32 bytes = 2 x 16-byte units inside the swizzle row
-          umma_bf16(tmem_base, dah + adv, dbh + adv, idesc, (kb | j) ? 1u : 0u);
+          umma_bf16(tmem_base, dah + adv, dbh + adv, idesc, (it | j) ? 1u : 0u);
           umma_bf16(tmem_base, dah + adv, dbm + adv, idesc, 1u);
           umma_bf16(tmem_base, dam + adv, dbh + adv, idesc, 1u);
         }
@@ -384,9 +410,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else {
     // =========================== B producer: TMA of the pre-split K-major bf16 weight tiles ===========================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int it = kb - kb_begin, s = it % S;
+        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
         const uint32_t b_hi = smem_base + (uint32_t)s * stage_bytes + 2 * a_bytes, b_mid = b_hi + b_bytes;
         mbar_arrive_expect_tx(full_bar(s), 2 * b_bytes);
         tma_load_2d(b_hi, &p.tmh, full_bar(s), kb * TC_BK, n0);
@@ -399,6 +425,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == TC_AWARPS) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
+
+// split-K second pass: sum the partials and run the regular epilogue (one thread per 4 output channels of a pixel)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ TcParams p) {
+  const int nq = (p.Cout + 3) / 4;
+  const long total = (long)p.M * nq;
+  const int HoWo = p.Ho * p.Wo;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / nq), cq = (int)(i - (long)m * nq) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < p.splits; ++z) {
+      const float4 t = *reinterpret_cast<const float4*>(p.partial + ((size_t)z * p.M + m) * p.npad + cq);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    const int nimg = m / HoWo, rr = m - nimg * HoWo;
+    const int py = (rr / p.Wo) * p.oy_mul + p.oy_add, px = (rr % p.Wo) * p.ox_mul + p.ox_add;
+    const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
+    const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
+    float v4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = cq + e;
+      if (c >= p.Cout) break;
+      float x = v4[e];
+      if (p.add0) x += p.add0_planar ? p.add0[((size_t)nimg * p.add0_cs + p.add0_coff + c) * oplane + opl_pix] : p.add0[opix * p.add0_cs + p.add0_coff + c];
+      if (p.scale) x *= __ldg(p.scale + c);
+      if (p.shift) x += __ldg(p.shift + c);
+      x = apply_act_tc(x, p.act);
+      if (p.mul1) x *= __ldg(p.mul1 + c);
+      if (p.add1) x += p.add1_planar ? p.add1[((size_t)nimg * p.add1_cs + p.add1_coff + c) * oplane + opl_pix] : p.add1[opix * p.add1_cs + p.add1_coff + c];
+      if (p.out_planar) p.out[((size_t)nimg * p.out_cs + p.out_coff + c) * oplane + opl_pix] = x;
+      else p.out[opix * p.out_cs + p.out_coff + c] = x;
+    }
+  }
+}
 
 // fp32 K-major [K][ldw] (the SIMT layout) -> bf16 hi/mid [npad][kpad] K-major, zero padded
 __global__ void split_weights_kernel(const float* w, int K, int Cout, int ldw, uint16_t* wh, uint16_t* wm, int kpad, int npad) {
@@ -510,8 +570,33 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   static bool attr = false;
   if (!attr) { CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
   dim3 grid((p.M + TC_BM - 1) / TC_BM, p.npad / p.BN);
+  // split-K for layers whose tile count cannot fill the 148 SMs (deep, spatially tiny layers of the DBNet decoder)
+  const int tiles = (int)(grid.x * grid.y), nkb = p.kpad / TC_BK;
+  int splits = 1;
+  if (!op.stat_max && tiles * 2 <= 148 && nkb >= 16) {
+    splits = 148 / tiles;
+    if (splits > nkb / 4) splits = nkb / 4;
+    if (splits < 1) splits = 1;
+  }
+  p.splits = splits; p.partial = nullptr;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * p.M * p.npad * sizeof(float);
+    static float* g_partial = nullptr; static size_t g_partial_cap = 0;      // grow-only scratch, one per process
+    if (need > g_partial_cap) {
+      if (g_partial) CUDA_OK(cudaFree(g_partial));
+      CUDA_OK(cudaMalloc(&g_partial, need)); g_partial_cap = need;
+    }
+    p.partial = g_partial;
+    grid.z = splits;
+  }
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
   count_launch();
+  if (splits > 1) {
+    const long total = (long)p.M * ((p.Cout + 3) / 4);
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+    count_launch();
+  }
   CUDA_OK(cudaGetLastError());
 }
 
