@@ -15,8 +15,9 @@
 //                  128B swizzle) straight into the stage, completing on the stage's "full" mbarrier (expect_tx);
 //       warp  8    one elected thread issues tcgen05.mma (12 per K block) and commits to the stage's "empty" mbarrier;
 //     full/empty mbarrier ring, producers signal after fence.proxy.async (generic-proxy stores -> async-proxy reads).
-//   * Epilogue: warps 0-7 read their 32 TMEM lanes with tcgen05.ld (one output pixel per thread, two warps share a
-//     lane quarter and split the columns), apply (+add0)*scale+shift -> activation -> *mul1 -> +add1 and store fp32.
+//   * Persistent: one CTA per SM loops over output tiles; the accumulator is double-buffered in TMEM (2 x BN columns) so
+//     the epilogue of tile i (4 dedicated warps: tcgen05.ld, (+add0)*scale+shift -> act -> *mul1 -> +add1, fp32 stores)
+//     overlaps the MMAs of tile i+1; TMEM alloc / barrier init / descriptor fetch are paid once per SM.
 #include <cuda.h>
 #include <string.h>
 #include <cuda_bf16.h>
@@ -27,8 +28,9 @@ namespace mitb {
 namespace {
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TC_THREADS = 320;               // 8 A-producer/epilogue warps + 1 MMA warp + 1 TMA warp
-constexpr int TC_AWARPS = 8;
+constexpr int TC_AWARPS = 8;                  // A-producer warps (two threads per GEMM row)
+constexpr int TC_EWARPS = 4;                  // epilogue warps (one thread per GEMM row / TMEM lane)
+constexpr int TC_THREADS = (TC_AWARPS + 2 + TC_EWARPS) * 32;   // + MMA warp + TMA warp = 448
 
 struct TcParams {
   const float* in; int N, H, W, in_cs, in_coff, Cin, in_planar;
@@ -156,6 +158,17 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mi
   mid = make_uint4(m[0], m[1], m[2], m[3]);
 }
 
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, int act_rt) {
+  if (ACT == ACT_NONE) return v;
+  if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (ACT == ACT_SILU) return v / (1.f + expf(-v));
+  return apply_act_tc(v, act_rt);               // ACT == -1: rare activations, runtime switch
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A_hi 16K | A_mid 16K | B_hi BN*128 | B_mid BN*128], then barriers
@@ -163,23 +176,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int BN = p.BN, S = p.stages;
   const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)BN * 128;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);     // full[S], empty[S], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  const uint32_t done_bar = bar_base + 8u * (2 * S);
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
   const int nkb = p.kpad / TC_BK;
-  // split-K: blockIdx.z owns the K blocks [kb_begin, kb_end) and writes raw partial sums (reduced by splitk_reduce_kernel)
-  const int kb_begin = (int)(((long)blockIdx.z * nkb) / p.splits), kb_end = (int)(((long)(blockIdx.z + 1) * nkb) / p.splits);
+  const int mt = (p.M + TC_BM - 1) / TC_BM, nt = p.npad / BN;
+  const int total_tiles = mt * nt * p.splits;
+  const uint32_t acc_stride = (uint32_t)(p.tmem_cols >> 1);          // columns per accumulator buffer
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_AWARPS * 32 + 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(done_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_EWARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_AWARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -188,243 +202,292 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile t -> (split z, M tile, N tile); N fastest so CTAs running together share the activation rows in L2
+  auto decode = [&](int t, int& z, int& m0, int& n0, int& kb_begin, int& kb_end) {
+    z = t / (mt * nt); const int r = t - z * (mt * nt);
+    m0 = (r / nt) * TC_BM; n0 = (r % nt) * BN;
+    kb_begin = (int)(((long)z * nkb) / p.splits); kb_end = (int)(((long)(z + 1) * nkb) / p.splits);
+  };
+
   if (warp < TC_AWARPS) {
-    // =========================== A producer: two threads per output pixel (GEMM row), 4 chunks of 8 k each ===========
+    // =========================== A producers: two threads per GEMM row, 4 chunks of 8 k each ===========================
     const int r = tid & 127, half = tid >> 7;
-    const int m = m0 + r;
-    const bool row_ok = m < p.M;
     const int HoWo = p.Ho * p.Wo, HW = p.H * p.W;
-    int nimg = 0, iy0 = 0, ix0 = 0, pix = 0;
-    if (row_ok) {
-      nimg = m / HoWo; const int rr = m - nimg * HoWo;
-      const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-      iy0 = oy * p.sy; ix0 = ox * p.sx; pix = rr;
-    }
-    int tap = 0, ci = 0;                       // cursor of this thread's next 8-channel chunk
-    if (!p.in_planar) { const int k0 = kb_begin * TC_BK + half * 32; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
     struct Blk { float v[4][8]; int cix[4]; };        // raw loaded values + channel index of each chunk (-1: all zero)
     Blk R0, R1;
-
-    auto load_block = [&](int kb, Blk& B) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kb * TC_BK + half * 32 + j * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) B.v[j][e] = 0.f;
-        B.cix[j] = -1;
-        if (row_ok && k < p.K) {
-          if (!p.in_planar) {
-            int iy = iy0 + p.tdy[tap], ix = ix0 + p.tdx[tap];
-            bool inb = true;
-            if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
-            else inb = (iy >= 0) & (iy < p.H) & (ix >= 0) & (ix < p.W);
-            if (inb) {
-              const float* src = p.in + ((size_t)(nimg * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci;
-              const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-              B.v[j][0] = a.x; B.v[j][1] = a.y; B.v[j][2] = a.z; B.v[j][3] = a.w;
-              B.v[j][4] = b.x; B.v[j][5] = b.y; B.v[j][6] = b.z; B.v[j][7] = b.w;
-              B.cix[j] = ci;
-            }
-          } else {
-            B.cix[j] = k;
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (k + e < p.K) B.v[j][e] = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + k + e) * HW + pix);
-          }
-        }
-        if (!p.in_planar) { ci += 8; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
-      }
-      // skip the other half-row's 32 channels
-      if (!p.in_planar) { ci += 32; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
-    };
-    // BN+ReLU prologue (applied when the data is consumed, so the loads stay in flight) + hi/mid split + swizzled stores
-    auto produce = [&](int kb, Blk& B) {
-      const int s = (kb - kb_begin) % S;
-      uint4 hi[4], mid[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (p.in_scale && B.cix[j] >= 0) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ch = B.cix[j] + e;
-            if (!p.in_planar || ch < p.K) {
-              const float t = B.v[j][e] * __ldg(p.in_scale + ch) + __ldg(p.in_shift + ch);
-              B.v[j][e] = p.in_relu ? fmaxf(t, 0.f) : t;
-            }
-          }
-        }
-        split8(B.v[j], hi[j], mid[j]);
-      }
-      if (kb + 2 < kb_end) load_block(kb + 2, B);       // refill this ring slot: loads stay in flight for two K blocks
-      mbar_wait(empty_bar(s), (((kb - kb_begin) / S) & 1) ^ 1);
-      uint8_t* a_hi = smem + (size_t)s * stage_bytes;
-      uint8_t* a_mid = a_hi + a_bytes;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t c = (uint32_t)(half * 4 + j);
-        const uint32_t off = row_off + ((c ^ sw) << 4);
-        *reinterpret_cast<uint4*>(a_hi + off) = hi[j];
-        *reinterpret_cast<uint4*>(a_mid + off) = mid[j];
-      }
-      fence_async_smem();
-      mbar_arrive(full_bar(s));
-    };
-
-    load_block(kb_begin, R0);
-    if (kb_begin + 1 < kb_end) load_block(kb_begin + 1, R1);
-    for (int kb = kb_begin; kb < kb_end; kb += 2) {
-      produce(kb, R0);
-      if (kb + 1 < kb_end) produce(kb + 1, R1);
-    }
-    // =========================== epilogue: TMEM -> registers -> global ===========================
-    mbar_wait(done_bar, 0);
-    tc_fence_after();
-    const int py = row_ok ? ((pix / p.Wo) * p.oy_mul + p.oy_add) : 0;
-    const int px = row_ok ? ((pix % p.Wo) * p.ox_mul + p.ox_add) : 0;
-    const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
-    const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
-    const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int nchunks = BN / 16, h0 = (nchunks + 1) / 2;
-    const int cb_lo = (half == 0 ? 0 : h0) * 16, cb_hi = (half == 0 ? h0 : nchunks) * 16;
-    if (p.stat_max) {
-      // vocabulary head: online (max, first argmax, sum exp) over this thread's columns of its row; the logits never
-      // leave TMEM (model_48px_ctc.py:460-461).  Two partials per N tile (one per column half).
-      float bm = -INFINITY, bs = 0.f; int bi = 0x7fffffff;
-      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr_row + (uint32_t)cb, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int c = n0 + cb + e;
-          if (c < p.Cout) {
-            const float x = __uint_as_float(raw[e]) + (p.shift ? __ldg(p.shift + c) : 0.f);
-            if (x > bm) { bs = bs * expf(bm - x) + 1.f; bm = x; bi = c; }
-            else bs += expf(x - bm);
-          }
-        }
-      }
+    int it = 0;                                        // global K-block counter of this CTA (smem stage ring)
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int z, m0, n0, kb_begin, kb_end;
+      decode(t, z, m0, n0, kb_begin, kb_end);
+      const int m = m0 + r;
+      const bool row_ok = m < p.M;
+      int nimg = 0, iy0 = 0, ix0 = 0, pix = 0;
       if (row_ok) {
-        const size_t o = (size_t)m * p.stat_ld + blockIdx.y * 2 + half;
-        p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
+        nimg = m / HoWo; const int rr = m - nimg * HoWo;
+        const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+        iy0 = oy * p.sy; ix0 = ox * p.sx; pix = rr;
       }
-    } else if (p.splits > 1) {
-      // split-K partial: raw accumulators to partial[z][m][npad]
-      float* dst = p.partial + ((size_t)blockIdx.z * p.M + m) * p.npad + n0;
-      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr_row + (uint32_t)cb, raw);
-        tmem_ld_wait();
-        if (!row_ok) continue;
+      int tap = 0, ci = 0;                             // cursor of this thread's next 8-channel chunk
+      if (!p.in_planar) { const int k0 = kb_begin * TC_BK + half * 32; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
+
+      auto load_block = [&](int kb, Blk& B) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(dst + cb + q * 4) = make_uint4(raw[q * 4], raw[q * 4 + 1], raw[q * 4 + 2], raw[q * 4 + 3]);
-      }
-    } else
-    for (int cb = cb_lo; cb < cb_hi; cb += 16) {
-      uint32_t raw[16];
-      tmem_ld16(taddr_row + (uint32_t)cb, raw);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      const int c0 = n0 + cb;
-      if (c0 >= p.Cout) continue;
+        for (int j = 0; j < 4; ++j) {
+          const int k = kb * TC_BK + half * 32 + j * 8;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int cq = c0 + q * 4;
-        if (cq >= p.Cout) break;
-        float v4[4];
+          for (int e = 0; e < 8; ++e) B.v[j][e] = 0.f;
+          B.cix[j] = -1;
+          if (row_ok && k < p.K) {
+            if (!p.in_planar) {
+              int iy = iy0 + p.tdy[tap], ix = ix0 + p.tdx[tap];
+              bool inb = true;
+              if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
+              else inb = (iy >= 0) & (iy < p.H) & (ix >= 0) & (ix < p.W);
+              if (inb) {
+                const float* src = p.in + ((size_t)(nimg * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                B.v[j][0] = a.x; B.v[j][1] = a.y; B.v[j][2] = a.z; B.v[j][3] = a.w;
+                B.v[j][4] = b.x; B.v[j][5] = b.y; B.v[j][6] = b.z; B.v[j][7] = b.w;
+                B.cix[j] = ci;
+              }
+            } else {
+              B.cix[j] = k;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v4[e] = __uint_as_float(raw[q * 4 + e]);
-        const bool full = cq + 3 < p.Cout;
-        auto fetch = [&](const float* base, int cs, int coff, int planar, float* dst) {
-          if (!planar && full && ((cs | coff) & 3) == 0) {
-            const float4 t = *reinterpret_cast<const float4*>(base + opix * cs + coff + cq);
-            dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              dst[e] = 0.f;
-              if (cq + e < p.Cout)
-                dst[e] = planar ? base[((size_t)nimg * cs + coff + cq + e) * oplane + opl_pix] : base[opix * cs + coff + cq + e];
+              for (int e = 0; e < 8; ++e)
+                if (k + e < p.K) B.v[j][e] = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + k + e) * HW + pix);
             }
           }
-        };
-        if (p.add0) { float t[4]; fetch(p.add0, p.add0_cs, p.add0_coff, p.add0_planar, t);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v4[e] += t[e]; }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = cq + e;
-          if (c < p.Cout) {
-            float x = v4[e];
-            if (p.scale) x *= __ldg(p.scale + c);
-            if (p.shift) x += __ldg(p.shift + c);
-            x = apply_act_tc(x, p.act);
-            if (p.mul1) x *= __ldg(p.mul1 + c);
-            v4[e] = x;
-          }
+          if (!p.in_planar) { ci += 8; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
         }
-        if (p.add1) { float t[4]; fetch(p.add1, p.add1_cs, p.add1_coff, p.add1_planar, t);
+        if (!p.in_planar) { ci += 32; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }     // skip the other half-row
+      };
+      // BN+ReLU prologue (applied at consume time so the loads stay in flight) + hi/mid split + swizzled stores
+      auto produce = [&](int kb, Blk& B) {
+        const int s = it % S;
+        uint4 hi[4], mid[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v4[e] += t[e]; }
-        if (!p.out_planar && full && ((p.out_cs | p.out_coff) & 3) == 0) {
-          *reinterpret_cast<float4*>(p.out + opix * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-        } else {
+        for (int j = 0; j < 4; ++j) {
+          if (p.in_scale && B.cix[j] >= 0) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (cq + e < p.Cout) {
-              if (p.out_planar) p.out[((size_t)nimg * p.out_cs + p.out_coff + cq + e) * oplane + opl_pix] = v4[e];
-              else p.out[opix * p.out_cs + p.out_coff + cq + e] = v4[e];
+            for (int e = 0; e < 8; ++e) {
+              const int ch = B.cix[j] + e;
+              if (!p.in_planar || ch < p.K) {
+                const float tt = B.v[j][e] * __ldg(p.in_scale + ch) + __ldg(p.in_shift + ch);
+                B.v[j][e] = p.in_relu ? fmaxf(tt, 0.f) : tt;
+              }
             }
+          }
+          split8(B.v[j], hi[j], mid[j]);
         }
+        if (kb + 2 < kb_end) load_block(kb + 2, B);     // refill this ring slot: loads stay in flight for two K blocks
+        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+        uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+        uint8_t* a_mid = a_hi + a_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c = (uint32_t)(half * 4 + j);
+          const uint32_t off = row_off + ((c ^ sw) << 4);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi[j];
+          *reinterpret_cast<uint4*>(a_mid + off) = mid[j];
+        }
+        fence_async_smem();
+        mbar_arrive(full_bar(s));
+        ++it;
+      };
+      load_block(kb_begin, R0);
+      if (kb_begin + 1 < kb_end) load_block(kb_begin + 1, R1);
+      for (int kb = kb_begin; kb < kb_end; kb += 2) {
+        produce(kb, R0);
+        if (kb + 1 < kb_end) produce(kb + 1, R1);
       }
     }
-    tc_fence_before();
   } else if (warp == TC_AWARPS) {
     // =========================== MMA issuer (one elected thread) ===========================
     if (lane == 0) {
       // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9 / 10-12 = 1), K-major A and B,
       // N>>3 at bits 17-22, M>>4 at bits 24-28
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int it = kb - kb_begin, s = it % S;
-        mbar_wait(full_bar(s), (it / S) & 1);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        int z, m0, n0, kb_begin, kb_end;
+        decode(t, z, m0, n0, kb_begin, kb_end);
+        const int buf = lt & 1;
+        mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
-        const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
-        const uint64_t dah = make_desc_sw128(a_hi), dam = make_desc_sw128(a_mid), dbh = make_desc_sw128(b_hi), dbm = make_desc_sw128(b_mid);
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_stride;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(full_bar(s), (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+          const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+          const uint64_t dah = make_desc_sw128(a_hi), dam = make_desc_sw128(a_mid), dbh = make_desc_sw128(b_hi), dbm = make_desc_sw128(b_mid);
 #pragma unroll
-        for (int j = 0; j < TC_BK / 16; ++j) {
-          const uint64_t adv = (uint64_t)(j * 2);                  // 16 bf16 = 32 bytes = 2 x 16-byte units inside the swizzle row
-          umma_bf16(tmem_base, dah + adv, dbh + adv, idesc, (it | j) ? 1u : 0u);
-          umma_bf16(tmem_base, dah + adv, dbm + adv, idesc, 1u);
-          umma_bf16(tmem_base, dam + adv, dbh + adv, idesc, 1u);
+          for (int j = 0; j < TC_BK / 16; ++j) {
+            const uint64_t adv = (uint64_t)(j * 2);                  // 16 bf16 = 32 bytes = 2 x 16-byte units inside the swizzle row
+            umma_bf16(tmem_d, dah + adv, dbh + adv, idesc, (kb > kb_begin || j > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, dah + adv, dbm + adv, idesc, 1u);
+            umma_bf16(tmem_d, dam + adv, dbh + adv, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));          // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
         }
-        umma_commit(empty_bar(s));            // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
+        umma_commit(tfull_bar(buf));          // accumulator of this tile complete -> epilogue
       }
-      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else if (warp == TC_AWARPS + 1) {
+    // =========================== B producer: TMA of the pre-split K-major bf16 weight tiles ===========================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int z, m0, n0, kb_begin, kb_end;
+        decode(t, z, m0, n0, kb_begin, kb_end);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+          const uint32_t b_hi = smem_base + (uint32_t)s * stage_bytes + 2 * a_bytes, b_mid = b_hi + b_bytes;
+          mbar_arrive_expect_tx(full_bar(s), 2 * b_bytes);
+          tma_load_2d(b_hi, &p.tmh, full_bar(s), kb * TC_BK, n0);
+          tma_load_2d(b_mid, &p.tmm, full_bar(s), kb * TC_BK, n0);
+        }
+      }
     }
     __syncwarp();
   } else {
-    // =========================== B producer: TMA of the pre-split K-major bf16 weight tiles ===========================
-    if (lane == 0) {
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int it = kb - kb_begin, s = it % S;
-        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
-        const uint32_t b_hi = smem_base + (uint32_t)s * stage_bytes + 2 * a_bytes, b_mid = b_hi + b_bytes;
-        mbar_arrive_expect_tx(full_bar(s), 2 * b_bytes);
-        tma_load_2d(b_hi, &p.tmh, full_bar(s), kb * TC_BK, n0);
-        tma_load_2d(b_mid, &p.tmm, full_bar(s), kb * TC_BK, n0);
+    // =========================== epilogue warps: TMEM -> registers -> global, one GEMM row per thread ===========================
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int HoWo = p.Ho * p.Wo;
+    int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      int z, m0, n0, kb_begin, kb_end;
+      decode(t, z, m0, n0, kb_begin, kb_end);
+      const int buf = lt & 1;
+      const int m = m0 + r;
+      const bool row_ok = m < p.M;
+      int nimg = 0, pix = 0;
+      if (row_ok) { nimg = m / HoWo; pix = m - nimg * HoWo; }
+      const int py = (pix / p.Wo) * p.oy_mul + p.oy_add, px = (pix % p.Wo) * p.ox_mul + p.ox_add;
+      const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
+      const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
+      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + (uint32_t)buf * acc_stride + ((uint32_t)(q * 32) << 16);
+      if (p.stat_max) {
+        // vocabulary head: online (max, first argmax, sum exp) over the tile's columns of this thread's row; the logits
+        // never leave TMEM (model_48px_ctc.py:460-461).  One partial per N tile.
+        float bm = -INFINITY, bs = 0.f; int bi = 0x7fffffff;
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 16) {
+          uint32_t raw[16];
+          tmem_ld16(taddr_row + (uint32_t)cb, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int c = n0 + cb + e;
+            if (c < p.Cout) {
+              const float x = __uint_as_float(raw[e]) + (p.shift ? __ldg(p.shift + c) : 0.f);
+              if (x > bm) { bs = bs * expf(bm - x) + 1.f; bm = x; bi = c; }
+              else bs += expf(x - bm);
+            }
+          }
+        }
+        if (row_ok) {
+          const size_t o = (size_t)m * p.stat_ld + (n0 / BN);
+          p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
+        }
+      } else if (p.splits > 1) {
+        // split-K partial: raw accumulators to partial[z][m][npad]
+        float* dst = p.partial + ((size_t)z * p.M + m) * p.npad + n0;
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 16) {
+          uint32_t raw[16];
+          tmem_ld16(taddr_row + (uint32_t)cb, raw);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq)
+              *reinterpret_cast<uint4*>(dst + cb + qq * 4) = make_uint4(raw[qq * 4], raw[qq * 4 + 1], raw[qq * 4 + 2], raw[qq * 4 + 3]);
+          }
+        }
+      } else {
+        const bool vec_out = !p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0;
+        const bool vec0 = p.add0 && !p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0;
+        const bool vec1 = p.add1 && !p.add1_planar && ((p.add1_cs | p.add1_coff) & 3) == 0;
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 16) {
+          uint32_t raw[16];
+          tmem_ld16(taddr_row + (uint32_t)cb, raw);
+          tmem_ld_wait();
+          const int c0 = n0 + cb;
+          if (!row_ok || c0 >= p.Cout) continue;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int cq = c0 + qq * 4;
+            if (cq >= p.Cout) break;
+            float v4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v4[e] = __uint_as_float(raw[qq * 4 + e]);
+            const bool full = cq + 3 < p.Cout;
+            if (p.add0) {
+              if (vec0 && full) {
+                const float4 tt = *reinterpret_cast<const float4*>(p.add0 + opix * p.add0_cs + p.add0_coff + cq);
+                v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (cq + e < p.Cout)
+                    v4[e] += p.add0_planar ? p.add0[((size_t)nimg * p.add0_cs + p.add0_coff + cq + e) * oplane + opl_pix]
+                                           : p.add0[opix * p.add0_cs + p.add0_coff + cq + e];
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = cq + e;
+              if (c < p.Cout) {
+                float x = v4[e];
+                if (p.scale) x *= __ldg(p.scale + c);
+                if (p.shift) x += __ldg(p.shift + c);
+                x = act_t<ACT>(x, p.act);
+                if (p.mul1) x *= __ldg(p.mul1 + c);
+                v4[e] = x;
+              }
+            }
+            if (p.add1) {
+              if (vec1 && full) {
+                const float4 tt = *reinterpret_cast<const float4*>(p.add1 + opix * p.add1_cs + p.add1_coff + cq);
+                v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (cq + e < p.Cout)
+                    v4[e] += p.add1_planar ? p.add1[((size_t)nimg * p.add1_cs + p.add1_coff + cq + e) * oplane + opl_pix]
+                                           : p.add1[opix * p.add1_cs + p.add1_coff + cq + e];
+              }
+            }
+            if (vec_out && full) {
+              *reinterpret_cast<float4*>(p.out + opix * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (cq + e < p.Cout) {
+                  if (p.out_planar) p.out[((size_t)nimg * p.out_cs + p.out_coff + cq + e) * oplane + opl_pix] = v4[e];
+                  else p.out[opix * p.out_cs + p.out_coff + cq + e] = v4[e];
+                }
+            }
+          }
+        }
       }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));                     // accumulator drained -> the MMA warp may overwrite it
     }
-    __syncwarp();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == TC_AWARPS) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
-
 
 // split-K second pass: sum the partials and run the regular epilogue (one thread per 4 output channels of a pixel)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ TcParams p) {
@@ -529,7 +592,7 @@ void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
   make_weight_tmap(&cw.tmm, wm, cw.tc_kpad, cw.tc_npad, bn);
 }
 
-int conv_tc_stat_blocks(const ConvOp& op) { return 2 * (op.tc_npad / op.tc_bn); }   // two column halves per N tile
+int conv_tc_stat_blocks(const ConvOp& op) { return op.tc_npad / op.tc_bn; }   // one partial per N tile
 
 bool conv_tc_supported(const ConvOp& op) {
   if (!g_tc_enabled || !op.wh || !op.wm) return false;
@@ -556,25 +619,33 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
   p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
-  MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tc conv: stat_ld must equal conv_stat_blocks(op)");
+  MITB_CHECK(!op.stat_max || op.stat_ld == op.tc_npad / op.tc_bn, "tc conv: stat_ld must equal conv_stat_blocks(op)");
   p.M = op.in.N * op.Ho * op.Wo; p.K = op.ntaps * op.in.C; p.BN = op.tc_bn;
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tc conv: bad BN %d", p.BN);
   MITB_CHECK(p.in_planar || p.Cin % 8 == 0, "tc conv: Cin must be a multiple of 8");
   int cols = 32; while (cols < p.BN) cols <<= 1;
-  p.tmem_cols = cols;
+  p.tmem_cols = 2 * cols;                                  // double-buffered accumulator
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)p.BN * 128;
   int stages = (int)((200 * 1024) / stage_bytes); if (stages > 4) stages = 4;
   MITB_CHECK(stages >= 2, "tc conv: tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  static bool attr = false;
-  if (!attr) { CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-  dim3 grid((p.M + TC_BM - 1) / TC_BM, p.npad / p.BN);
-  // split-K for layers whose tile count cannot fill the 148 SMs (deep, spatially tiny layers of the DBNet decoder)
-  const int tiles = (int)(grid.x * grid.y), nkb = p.kpad / TC_BK;
+  const size_t smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int mt = (p.M + TC_BM - 1) / TC_BM, nt = p.npad / p.BN;
+  // split-K for layers whose tile count cannot fill the SMs (deep, spatially tiny layers of the DBNet decoder)
+  const int tiles = mt * nt, nkb = p.kpad / TC_BK;
   int splits = 1;
-  if (!op.stat_max && tiles * 2 <= 148 && nkb >= 16) {
-    splits = 148 / tiles;
+  if (!op.stat_max && tiles * 2 <= num_sms && nkb >= 16) {
+    splits = num_sms / tiles;
     if (splits > nkb / 4) splits = nkb / 4;
     if (splits < 1) splits = 1;
   }
@@ -587,9 +658,16 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
       CUDA_OK(cudaMalloc(&g_partial, need)); g_partial_cap = need;
     }
     p.partial = g_partial;
-    grid.z = splits;
   }
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  const int total_tiles = tiles * splits;
+  const int grid = total_tiles < num_sms ? total_tiles : num_sms;      // persistent: one CTA per SM
+  switch (splits > 1 || op.stat_max ? ACT_NONE : p.act) {
+    case ACT_NONE: conv_tc_kernel<ACT_NONE><<<grid, TC_THREADS, smem, st>>>(p); break;
+    case ACT_RELU: conv_tc_kernel<ACT_RELU><<<grid, TC_THREADS, smem, st>>>(p); break;
+    case ACT_GELU: conv_tc_kernel<ACT_GELU><<<grid, TC_THREADS, smem, st>>>(p); break;
+    case ACT_SILU: conv_tc_kernel<ACT_SILU><<<grid, TC_THREADS, smem, st>>>(p); break;
+    default: conv_tc_kernel<-1><<<grid, TC_THREADS, smem, st>>>(p); break;
+  }
   count_launch();
   if (splits > 1) {
     const long total = (long)p.M * ((p.Cout + 3) / 4);
