@@ -419,6 +419,8 @@ void launch_repack(float* dst, const float* src, int Cout, int Cin, int ntaps, c
 bool conv_tc_supported(const ConvOp& op);            // conv_tc.cu
 int conv_tc_stat_blocks(const ConvOp& op);
 void launch_conv_tc(const ConvOp& op, cudaStream_t st);
+bool conv_thin_supported(const ConvOp& op);          // conv_thin.cu
+void launch_conv_thin(const ConvOp& op, cudaStream_t st);
 
 int conv_stat_blocks(const ConvOp& op) { return conv_tc_supported(op) ? conv_tc_stat_blocks(op) : (op.out.C + 127) / 128; }
 
@@ -461,6 +463,7 @@ void launch_conv(const ConvOp& op, cudaStream_t st) {
   const double flops = 2.0 * p.M * (double)p.K * Cout;
   const double bytes = 4.0 * ((double)op.in.pixels() * op.in.C + (double)p.K * Cout +
                               (double)p.M * Cout * ((op.stat_max ? 0 : 1) + (op.add0.p ? 1 : 0) + (op.add1.p ? 1 : 0)));
+  if (conv_thin_supported(op)) { ProfScope ps("conv7_thin", flops, bytes, st); launch_conv_thin(op, st); return; }
   if (conv_tc_supported(op)) { ProfScope ps(op.stat_max ? "conv_tc_rowstat" : "conv_tc", flops, bytes, st); launch_conv_tc(op, st); return; }
   ProfScope ps(op.stat_max ? "conv_simt_rowstat" : (Cout <= 4 && !op.in.planar && op.ldw == 4) ? "conv_fewout" : "conv_simt", flops, bytes, st);
   if (op.stat_max) {

@@ -36,7 +36,9 @@ CONV_CASES = [
     (1, 320, 6, 33, 320, 3, 3, (2, 1), (1, 1), "zeros", 0),    # OCR conv4_1 stride (2,1)
     (1, 320, 3, 33, 320, 3, 3, (1, 1), (0, 0), "zeros", 0),    # OCR conv4_2 no padding
     (3, 128, 16, 12, 512, 1, 1, (1, 1), (0, 0), "zeros", 2),   # MLP fc1 + GELU
-    (1, 64, 30, 30, 3, 7, 7, (1, 1), (3, 3), "reflect", 4),    # LaMa output conv (thin output kernel)
+    (1, 64, 30, 30, 3, 7, 7, (1, 1), (3, 3), "reflect", 4),    # LaMa output conv (smem-tiled thin-output kernel)
+    (2, 64, 70, 150, 3, 7, 7, (1, 1), (3, 3), "reflect", 4),   # same, several tiles + ragged right/bottom edges
+    (1, 16, 21, 67, 4, 7, 7, (1, 1), (3, 3), "zeros", 1),      # thin-output kernel, zero padding, Cout = 4
     (1, 32, 25, 31, 1, 1, 1, (1, 1), (0, 0), "zeros", 4),      # mask head 1x1 -> 1 channel
     (1, 256, 8, 8, 192, 2, 2, (2, 2), (0, 0), "zeros", 3),     # downsample conv, Cout not a multiple of 64
     (2, 40, 12, 50, 80, 3, 3, (1, 1), (1, 1), "zeros", 0),
