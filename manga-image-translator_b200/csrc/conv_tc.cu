@@ -159,6 +159,16 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mi
 }
 
 
+// split 4 fp32 values into bf16 hi / mid packs (8 bytes each)
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& mid) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&h0), b1 = *reinterpret_cast<const uint32_t*>(&h1);
+  const __nv_bfloat162 m0 = __floats2bfloat162_rn(v.x - __uint_as_float(b0 << 16), v.y - __uint_as_float(b0 & 0xffff0000u));
+  const __nv_bfloat162 m1 = __floats2bfloat162_rn(v.z - __uint_as_float(b1 << 16), v.w - __uint_as_float(b1 & 0xffff0000u));
+  hi = make_uint2(b0, b1);
+  mid = make_uint2(*reinterpret_cast<const uint32_t*>(&m0), *reinterpret_cast<const uint32_t*>(&m1));
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_t(float v, int act_rt) {
   if (ACT == ACT_NONE) return v;
@@ -178,6 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  float* estage = reinterpret_cast<float*>(bars + 2 * S + 6);          // [TC_EWARPS][32 rows][36 floats] epilogue transpose buffer
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -209,8 +220,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     kb_begin = (int)(((long)z * nkb) / p.splits); kb_end = (int)(((long)(z + 1) * nkb) / p.splits);
   };
 
-  if (warp < TC_AWARPS) {
-    // =========================== A producers: two threads per GEMM row, 4 chunks of 8 k each ===========================
+  if (warp < TC_AWARPS && !p.in_planar) {
+    // =========================== A producers, NHWC input (coalesced) ===========================
+    // A K block is 64 channels = 16 float4 per GEMM row.  Thread t owns float4 column f4 = t&15 of the 8 rows rb+16i
+    // (rb = t>>4): one warp instruction reads two complete 256-byte row segments (instead of 32 scattered 16-byte
+    // pieces), and all 8 loads of a thread share one (tap, channel) cursor.
+    const int f4 = tid & 15, rb = tid >> 4;
+    const int HoWo = p.Ho * p.Wo;
+    struct Blk { float4 v[8]; int ci; uint32_t valid; };
+    Blk R0, R1;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int z, m0, n0, kb_begin, kb_end;
+      decode(t, z, m0, n0, kb_begin, kb_end);
+      int rbase[8], ryx[8]; uint32_t okmask = 0;     // per row: image row base (nimg*H), (iy0<<16 | ix0)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + rb + 16 * i;
+        rbase[i] = 0; ryx[i] = 0;
+        if (m < p.M) {
+          const int nimg = m / HoWo, rr = m - nimg * HoWo;
+          const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+          rbase[i] = nimg * p.H; ryx[i] = ((oy * p.sy) << 16) | (ox * p.sx);
+          okmask |= 1u << i;
+        }
+      }
+      int tap, ci;
+      { const int k0 = kb_begin * TC_BK + f4 * 4; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
+
+      auto load_block = [&](int kb, Blk& B) {
+        const int k = kb * TC_BK + f4 * 4;
+        B.ci = ci; B.valid = 0;
+        const bool kval = k < p.K;
+        const int dy = kval ? p.tdy[tap] : 0, dx = kval ? p.tdx[tap] : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          B.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kval && ((okmask >> i) & 1u)) {
+            int iy = (ryx[i] >> 16) + dy, ix = (ryx[i] & 0xffff) + dx;
+            bool inb = true;
+            if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
+            else inb = (iy >= 0) & (iy < p.H) & (ix >= 0) & (ix < p.W);
+            if (inb) {
+              B.v[i] = __ldg(reinterpret_cast<const float4*>(p.in + ((size_t)(rbase[i] + iy) * p.W + ix) * p.in_cs + p.in_coff + ci));
+              B.valid |= 1u << i;
+            }
+          }
+        }
+        ci += TC_BK; while (ci >= p.Cin) { ci -= p.Cin; ++tap; }
+      };
+      auto produce = [&](int kb, Blk& B) {
+        const int s = it % S;
+        uint2 hi[8], mid[8];
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.in_scale && B.valid) {
+          sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + B.ci)); sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + B.ci));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 v = B.v[i];
+          if (p.in_scale && ((B.valid >> i) & 1u)) {
+            v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+            if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          }
+          split4(v, hi[i], mid[i]);
+        }
+        if (kb + 2 < kb_end) load_block(kb + 2, B);
+        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+        uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+        uint8_t* a_mid = a_hi + a_bytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t r = (uint32_t)(rb + 16 * i);
+          const uint32_t off = r * 128u + ((((uint32_t)f4 >> 1) ^ (r & 7u)) << 4) + ((uint32_t)f4 & 1u) * 8u;
+          *reinterpret_cast<uint2*>(a_hi + off) = hi[i];
+          *reinterpret_cast<uint2*>(a_mid + off) = mid[i];
+        }
+        fence_async_smem();
+        mbar_arrive(full_bar(s));
+        ++it;
+      };
+      load_block(kb_begin, R0);
+      if (kb_begin + 1 < kb_end) load_block(kb_begin + 1, R1);
+      for (int kb = kb_begin; kb < kb_end; kb += 2) {
+        produce(kb, R0);
+        if (kb + 1 < kb_end) produce(kb + 1, R1);
+      }
+    }
+  } else if (warp < TC_AWARPS) {
+    // =========================== A producers, planar input: two threads per GEMM row (coalesced along pixels) ===========
     const int r = tid & 127, half = tid >> 7;
     const int HoWo = p.Ho * p.Wo, HW = p.H * p.W;
     const uint32_t row_off = (uint32_t)r * 128u;
@@ -412,6 +510,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               *reinterpret_cast<uint4*>(dst + cb + qq * 4) = make_uint4(raw[qq * 4], raw[qq * 4 + 1], raw[qq * 4 + 2], raw[qq * 4 + 3]);
           }
         }
+      } else if (!p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0 &&
+                 (!p.add0 || (!p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0)) &&
+                 (!p.add1 || (!p.add1_planar && ((p.add1_cs | p.add1_coff) & 3) == 0))) {
+        // ---- NHWC output: transpose 32x32 accumulator chunks through shared memory so that a warp instruction touches
+        // 4 rows x 128 contiguous bytes (residual reads and stores fully coalesced) instead of 32 scattered 16-byte pieces
+        float* st = estage + (size_t)(warp - (TC_AWARPS + 2)) * 32 * 36;
+        const int sub = lane & 7, rsel = lane >> 3;            // this thread: columns 4*sub..+3 of rows rsel + 4j
+        size_t orow[8]; uint32_t rmask = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int mm = m0 + q * 32 + rsel + 4 * j;
+          orow[j] = 0;
+          if (mm < p.M) {
+            const int ni = mm / HoWo, pp = mm - ni * HoWo;
+            orow[j] = ((size_t)ni * p.oH + (pp / p.Wo) * p.oy_mul + p.oy_add) * p.oW + (pp % p.Wo) * p.ox_mul + p.ox_add;
+            rmask |= 1u << j;
+          }
+        }
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t raw[32];
+          tmem_ld16(taddr_row + (uint32_t)cb, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+          if (cb + 16 < BN) tmem_ld16(taddr_row + (uint32_t)cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+          else {
+#pragma unroll
+            for (int e = 16; e < 32; ++e) raw[e] = 0;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(st + lane * 36 + 4 * i) = make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
+          __syncwarp();
+          const int cq = n0 + cb + 4 * sub;
+          if (cq < p.Cout) {
+            const bool full = cq + 3 < p.Cout;
+            float sc4[4] = {1.f, 1.f, 1.f, 1.f}, sh4[4] = {0.f, 0.f, 0.f, 0.f}, mu4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (cq + e < p.Cout) {
+                if (p.scale) sc4[e] = __ldg(p.scale + cq + e);
+                if (p.shift) sh4[e] = __ldg(p.shift + cq + e);
+                if (p.mul1) mu4[e] = __ldg(p.mul1 + cq + e);
+              }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (!((rmask >> j) & 1u)) continue;
+              const float4 a = *reinterpret_cast<const float4*>(st + (rsel + 4 * j) * 36 + 4 * sub);
+              float v4[4] = {a.x, a.y, a.z, a.w};
+              if (p.add0) {
+                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add0 + orow[j] * p.add0_cs + p.add0_coff + cq);
+                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
+                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add0[orow[j] * p.add0_cs + p.add0_coff + cq + e]; }
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = v4[e];
+                if (p.scale) x *= sc4[e];
+                x += sh4[e];
+                x = act_t<ACT>(x, p.act);
+                if (p.mul1) x *= mu4[e];
+                v4[e] = x;
+              }
+              if (p.add1) {
+                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add1 + orow[j] * p.add1_cs + p.add1_coff + cq);
+                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
+                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add1[orow[j] * p.add1_cs + p.add1_coff + cq + e]; }
+              }
+              if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+              else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
+            }
+          }
+          __syncwarp();
+        }
       } else {
         const bool vec_out = !p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0;
         const bool vec0 = p.add0 && !p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0;
@@ -599,7 +770,7 @@ bool conv_tc_supported(const ConvOp& op) {
   const int K = op.ntaps * op.in.C;
   if (K < 32) return false;
   if (op.in.planar) return op.ntaps == 1;
-  return op.in.C % 8 == 0 && op.in.cs % 4 == 0 && op.in.coff % 4 == 0;
+  return op.in.C % 4 == 0 && op.in.cs % 4 == 0 && op.in.coff % 4 == 0;
 }
 
 void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
@@ -622,14 +793,15 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   MITB_CHECK(!op.stat_max || op.stat_ld == op.tc_npad / op.tc_bn, "tc conv: stat_ld must equal conv_stat_blocks(op)");
   p.M = op.in.N * op.Ho * op.Wo; p.K = op.ntaps * op.in.C; p.BN = op.tc_bn;
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tc conv: bad BN %d", p.BN);
-  MITB_CHECK(p.in_planar || p.Cin % 8 == 0, "tc conv: Cin must be a multiple of 8");
+  MITB_CHECK(p.in_planar || p.Cin % 4 == 0, "tc conv: Cin must be a multiple of 4");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;                                  // double-buffered accumulator
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)p.BN * 128;
-  int stages = (int)((200 * 1024) / stage_bytes); if (stages > 4) stages = 4;
+  const size_t epi_bytes = (size_t)TC_EWARPS * 32 * 36 * sizeof(float);
+  int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes); if (stages > 4) stages = 4;
   MITB_CHECK(stages >= 2, "tc conv: tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  const size_t smem = stages * stage_bytes + (2 * stages + 6) * 8 + epi_bytes + 1024;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0; CUDA_OK(cudaGetDevice(&dev));

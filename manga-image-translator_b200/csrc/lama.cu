@@ -51,7 +51,7 @@ LamaModel* lama_build(Ctx& ctx, const Weights& W) {
     Loader L{W, m->blob, 0};
     while (W.has("model." + std::to_string(5 + m->n_blocks) + ".conv1.ffc.convl2l.weight")) ++m->n_blocks;
     MITB_CHECK(m->n_blocks > 0, "lama: no FFC res-blocks found in the state_dict");
-    m->stem = L.conv_padcin("model.1.ffc.convl2l.weight", 3, 8); L.bn_fold("model.1.bn_l.", kBnEps, &m->stem.scale, &m->stem.shift);
+    m->stem = L.conv("model.1.ffc.convl2l.weight", 3, 3); L.bn_fold("model.1.bn_l.", kBnEps, &m->stem.scale, &m->stem.shift);
     m->d1 = L.conv("model.2.ffc.convl2l.weight", 1, 1); L.bn_fold("model.2.bn_l.", kBnEps, &m->d1.scale, &m->d1.shift);
     m->d2 = L.conv("model.3.ffc.convl2l.weight", 1, 1); L.bn_fold("model.3.bn_l.", kBnEps, &m->d2.scale, &m->d2.shift);
     m->d3l = L.conv("model.4.ffc.convl2l.weight", 1, 1); L.bn_fold("model.4.bn_l.", kBnEps, &m->d3l.scale, &m->d3l.shift);
@@ -133,7 +133,7 @@ void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const
     MITB_CHECK(!u8 || n == 1, "lama uint8 entry handles one image per call");
     {
       const size_t mk = ws.mark();
-      View x4 = ws.view(n, h, w, 8), s1 = ws.view(n, h, w, 64), s2 = ws.view(n, h / 2, w / 2, 128), s3 = ws.view(n, h / 4, w / 4, 256);
+      View x4 = ws.view(n, h, w, 4), s1 = ws.view(n, h, w, 64), s2 = ws.view(n, h / 2, w / 2, 128), s3 = ws.view(n, h / 4, w / 4, 256);
       if (u8) {
         maskf = ws.alloc_f((size_t)h * w);
         if (!e.dry) launch_lama_pack_u8(u8->img, u8->mask, h, w, x4, maskf, st);
