@@ -463,8 +463,8 @@ void launch_conv(const ConvOp& op, cudaStream_t st) {
   const double flops = 2.0 * p.M * (double)p.K * Cout;
   const double bytes = 4.0 * ((double)op.in.pixels() * op.in.C + (double)p.K * Cout +
                               (double)p.M * Cout * ((op.stat_max ? 0 : 1) + (op.add0.p ? 1 : 0) + (op.add1.p ? 1 : 0)));
-  if (conv_thin_supported(op)) { ProfScope ps("conv7_thin", flops, bytes, st); launch_conv_thin(op, st); return; }
-  if (conv_tc_supported(op)) { ProfScope ps(op.stat_max ? "conv_tc_rowstat" : "conv_tc", flops, bytes, st); launch_conv_tc(op, st); return; }
+  if (conv_thin_supported(op)) { ProfScope ps("conv7_thin", flops, bytes, st, p.M, p.K, Cout); launch_conv_thin(op, st); return; }
+  if (conv_tc_supported(op)) { ProfScope ps(op.stat_max ? "conv_tc_rowstat" : "conv_tc", flops, bytes, st, p.M, p.K, Cout); launch_conv_tc(op, st); return; }
   ProfScope ps(op.stat_max ? "conv_simt_rowstat" : (Cout <= 4 && !op.in.planar && op.ldw == 4) ? "conv_fewout" : "conv_simt", flops, bytes, st);
   if (op.stat_max) {
     MITB_CHECK(!op.in.planar, "row-stat epilogue expects NHWC input");

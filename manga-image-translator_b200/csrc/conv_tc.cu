@@ -28,9 +28,9 @@ namespace mitb {
 namespace {
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TC_AWARPS = 8;                  // A-producer warps (two threads per GEMM row)
-constexpr int TC_EWARPS = 4;                  // epilogue warps (one thread per GEMM row / TMEM lane)
-constexpr int TC_THREADS = (TC_AWARPS + 2 + TC_EWARPS) * 32;   // + MMA warp + TMA warp = 448
+constexpr int TC_AWARPS = 8;                  // A-producer warps; they also run the epilogue of the tile they just produced
+constexpr int TC_MMAWARP = TC_AWARPS, TC_TMAWARP = TC_AWARPS + 1;
+constexpr int TC_THREADS = (TC_AWARPS + 2) * 32;   // 320 threads -> up to 204 registers per thread, no spills
 
 struct TcParams {
   const float* in; int N, H, W, in_cs, in_coff, Cin, in_planar;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-  float* estage = reinterpret_cast<float*>(bars + 2 * S + 6);          // [TC_EWARPS][32 rows][36 floats] epilogue transpose buffer
+  float* estage = reinterpret_cast<float*>(bars + 2 * S + 6);          // [TC_AWARPS][32 rows][20 floats] epilogue transpose buffer
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_AWARPS * 32 + 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_EWARPS * 32); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_AWARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_AWARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == TC_MMAWARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -220,6 +220,156 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     kb_begin = (int)(((long)z * nkb) / p.splits); kb_end = (int)(((long)(z + 1) * nkb) / p.splits);
   };
 
+// ---- epilogue of one tile, run by the 8 producer warps: warp w reads TMEM lane quarter (w & 3) and the column half (w >> 2)
+  auto epilogue_tile = [&](int lt, int z, int m0, int n0) {
+    const int q = warp & 3, ehalf = warp >> 2;
+    const int r = q * 32 + lane;
+    const int HoWo = p.Ho * p.Wo;
+    const int buf = lt & 1;
+    const int m = m0 + r;
+    const bool row_ok = m < p.M;
+    const int nchunks = BN / 16, h0 = (nchunks + 1) / 2;
+    const int cb_lo = (ehalf == 0 ? 0 : h0) * 16, cb_hi = (ehalf == 0 ? h0 : nchunks) * 16;
+    mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + (uint32_t)buf * acc_stride + ((uint32_t)(q * 32) << 16);
+    if (p.stat_max) {
+      // vocabulary head: online (max, first argmax, sum exp) over this thread's columns of its row; the logits never leave
+      // TMEM (model_48px_ctc.py:460-461).  Two partials per N tile (one per column half).
+      float bm = -INFINITY, bs = 0.f; int bi = 0x7fffffff;
+#pragma unroll 1
+      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr_row + (uint32_t)cb, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int c = n0 + cb + e;
+          if (c < p.Cout) {
+            const float x = __uint_as_float(raw[e]) + (p.shift ? __ldg(p.shift + c) : 0.f);
+            if (x > bm) { bs = bs * expf(bm - x) + 1.f; bm = x; bi = c; }
+            else bs += expf(x - bm);
+          }
+        }
+      }
+      if (row_ok) {
+        const size_t o = (size_t)m * p.stat_ld + (n0 / BN) * 2 + ehalf;
+        p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
+      }
+    } else if (p.splits > 1) {
+      // split-K partial: raw accumulators to partial[z][m][npad]
+      float* dst = p.partial + ((size_t)z * p.M + m) * p.npad + n0;
+#pragma unroll 1
+      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr_row + (uint32_t)cb, raw);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            *reinterpret_cast<uint4*>(dst + cb + qq * 4) = make_uint4(raw[qq * 4], raw[qq * 4 + 1], raw[qq * 4 + 2], raw[qq * 4 + 3]);
+        }
+      }
+    } else if (!p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0 &&
+               (!p.add0 || (!p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0)) &&
+               (!p.add1 || (!p.add1_planar && ((p.add1_cs | p.add1_coff) & 3) == 0))) {
+      // ---- NHWC output: transpose 32x16 accumulator chunks through shared memory so that one warp instruction touches
+      // 8 rows x 64 contiguous bytes (residual reads and stores coalesced) instead of 32 scattered 16-byte pieces
+      float* st = estage + (size_t)warp * 32 * 20;
+      const int sub = lane & 3, rsel = lane >> 2;              // this thread: columns 4*sub..+3 of rows rsel + 8j
+      size_t orow[4]; uint32_t rmask = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int mm = m0 + q * 32 + rsel + 8 * j;
+        orow[j] = 0;
+        if (mm < p.M) {
+          const int ni = mm / HoWo, pp = mm - ni * HoWo;
+          orow[j] = ((size_t)ni * p.oH + (pp / p.Wo) * p.oy_mul + p.oy_add) * p.oW + (pp % p.Wo) * p.ox_mul + p.ox_add;
+          rmask |= 1u << j;
+        }
+      }
+#pragma unroll 1
+      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr_row + (uint32_t)cb, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(st + lane * 20 + 4 * i) = make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
+        __syncwarp();
+        const int cq = n0 + cb + 4 * sub;
+        if (cq < p.Cout) {
+          const bool full = cq + 3 < p.Cout;
+          float sc4[4] = {1.f, 1.f, 1.f, 1.f}, sh4[4] = {0.f, 0.f, 0.f, 0.f}, mu4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (cq + e < p.Cout) {
+              if (p.scale) sc4[e] = __ldg(p.scale + cq + e);
+              if (p.shift) sh4[e] = __ldg(p.shift + cq + e);
+              if (p.mul1) mu4[e] = __ldg(p.mul1 + cq + e);
+            }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!((rmask >> j) & 1u)) continue;
+            const float4 a = *reinterpret_cast<const float4*>(st + (rsel + 8 * j) * 20 + 4 * sub);
+            float v4[4] = {a.x, a.y, a.z, a.w};
+            if (p.add0) {
+              if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add0 + orow[j] * p.add0_cs + p.add0_coff + cq);
+                          v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
+              else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add0[orow[j] * p.add0_cs + p.add0_coff + cq + e]; }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = v4[e];
+              if (p.scale) x *= sc4[e];
+              x += sh4[e];
+              x = act_t<ACT>(x, p.act);
+              if (p.mul1) x *= mu4[e];
+              v4[e] = x;
+            }
+            if (p.add1) {
+              if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add1 + orow[j] * p.add1_cs + p.add1_coff + cq);
+                          v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
+              else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add1[orow[j] * p.add1_cs + p.add1_coff + cq + e]; }
+            }
+            if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+            else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
+          }
+        }
+        __syncwarp();
+      }
+    } else {
+      // ---- planar (NCHW) or unaligned output: lane = pixel, so each channel's stores are already contiguous across lanes
+      int nimg = 0, pix = 0;
+      if (row_ok) { nimg = m / HoWo; pix = m - nimg * HoWo; }
+      const int py = (pix / p.Wo) * p.oy_mul + p.oy_add, px = (pix % p.Wo) * p.ox_mul + p.ox_add;
+      const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
+      const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
+#pragma unroll 1
+      for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr_row + (uint32_t)cb, raw);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int c = n0 + cb + e;
+          if (c >= p.Cout) break;
+          float x = __uint_as_float(raw[e]);
+          if (p.add0) x += p.add0_planar ? p.add0[((size_t)nimg * p.add0_cs + p.add0_coff + c) * oplane + opl_pix] : p.add0[opix * p.add0_cs + p.add0_coff + c];
+          if (p.scale) x *= __ldg(p.scale + c);
+          if (p.shift) x += __ldg(p.shift + c);
+          x = act_t<ACT>(x, p.act);
+          if (p.mul1) x *= __ldg(p.mul1 + c);
+          if (p.add1) x += p.add1_planar ? p.add1[((size_t)nimg * p.add1_cs + p.add1_coff + c) * oplane + opl_pix] : p.add1[opix * p.add1_cs + p.add1_coff + c];
+          if (p.out_planar) p.out[((size_t)nimg * p.out_cs + p.out_coff + c) * oplane + opl_pix] = x;
+          else p.out[opix * p.out_cs + p.out_coff + c] = x;
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(tempty_bar(buf));                       // accumulator drained -> the MMA warp may overwrite it
+  };
   if (warp < TC_AWARPS && !p.in_planar) {
     // =========================== A producers, NHWC input (coalesced) ===========================
     // A K block is 64 channels = 16 float4 per GEMM row.  Thread t owns float4 column f4 = t&15 of the 8 rows rb+16i
@@ -229,8 +379,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int HoWo = p.Ho * p.Wo;
     struct Blk { float4 v[8]; int ci; uint32_t valid; };
     Blk R0, R1;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int it = 0, lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       int z, m0, n0, kb_begin, kb_end;
       decode(t, z, m0, n0, kb_begin, kb_end);
       int rbase[8], ryx[8]; uint32_t okmask = 0;     // per row: image row base (nimg*H), (iy0<<16 | ix0)
@@ -306,6 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         produce(kb, R0);
         if (kb + 1 < kb_end) produce(kb + 1, R1);
       }
+      epilogue_tile(lt, z, m0, n0);
     }
   } else if (warp < TC_AWARPS) {
     // =========================== A producers, planar input: two threads per GEMM row (coalesced along pixels) ===========
@@ -315,8 +466,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t sw = (uint32_t)(r & 7);
     struct Blk { float v[4][8]; int cix[4]; };        // raw loaded values + channel index of each chunk (-1: all zero)
     Blk R0, R1;
-    int it = 0;                                        // global K-block counter of this CTA (smem stage ring)
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int it = 0, lt = 0;                                // global K-block / tile counters of this CTA
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       int z, m0, n0, kb_begin, kb_end;
       decode(t, z, m0, n0, kb_begin, kb_end);
       const int m = m0 + r;
@@ -400,8 +551,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         produce(kb, R0);
         if (kb + 1 < kb_end) produce(kb + 1, R1);
       }
+      epilogue_tile(lt, z, m0, n0);
     }
-  } else if (warp == TC_AWARPS) {
+  } else if (warp == TC_MMAWARP) {
     // =========================== MMA issuer (one elected thread) ===========================
     if (lane == 0) {
       // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9 / 10-12 = 1), K-major A and B,
@@ -435,7 +587,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp == TC_AWARPS + 1) {
+  } else if (warp == TC_TMAWARP) {
     // =========================== B producer: TMA of the pre-split K-major bf16 weight tiles ===========================
     if (lane == 0) {
       int it = 0;
@@ -453,211 +605,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
     __syncwarp();
-  } else {
-    // =========================== epilogue warps: TMEM -> registers -> global, one GEMM row per thread ===========================
-    const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
-    const int HoWo = p.Ho * p.Wo;
-    int lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      int z, m0, n0, kb_begin, kb_end;
-      decode(t, z, m0, n0, kb_begin, kb_end);
-      const int buf = lt & 1;
-      const int m = m0 + r;
-      const bool row_ok = m < p.M;
-      int nimg = 0, pix = 0;
-      if (row_ok) { nimg = m / HoWo; pix = m - nimg * HoWo; }
-      const int py = (pix / p.Wo) * p.oy_mul + p.oy_add, px = (pix % p.Wo) * p.ox_mul + p.ox_add;
-      const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
-      const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
-      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr_row = tmem_base + (uint32_t)buf * acc_stride + ((uint32_t)(q * 32) << 16);
-      if (p.stat_max) {
-        // vocabulary head: online (max, first argmax, sum exp) over the tile's columns of this thread's row; the logits
-        // never leave TMEM (model_48px_ctc.py:460-461).  One partial per N tile.
-        float bm = -INFINITY, bs = 0.f; int bi = 0x7fffffff;
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 16) {
-          uint32_t raw[16];
-          tmem_ld16(taddr_row + (uint32_t)cb, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = n0 + cb + e;
-            if (c < p.Cout) {
-              const float x = __uint_as_float(raw[e]) + (p.shift ? __ldg(p.shift + c) : 0.f);
-              if (x > bm) { bs = bs * expf(bm - x) + 1.f; bm = x; bi = c; }
-              else bs += expf(x - bm);
-            }
-          }
-        }
-        if (row_ok) {
-          const size_t o = (size_t)m * p.stat_ld + (n0 / BN);
-          p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
-        }
-      } else if (p.splits > 1) {
-        // split-K partial: raw accumulators to partial[z][m][npad]
-        float* dst = p.partial + ((size_t)z * p.M + m) * p.npad + n0;
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 16) {
-          uint32_t raw[16];
-          tmem_ld16(taddr_row + (uint32_t)cb, raw);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq)
-              *reinterpret_cast<uint4*>(dst + cb + qq * 4) = make_uint4(raw[qq * 4], raw[qq * 4 + 1], raw[qq * 4 + 2], raw[qq * 4 + 3]);
-          }
-        }
-      } else if (!p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0 &&
-                 (!p.add0 || (!p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0)) &&
-                 (!p.add1 || (!p.add1_planar && ((p.add1_cs | p.add1_coff) & 3) == 0))) {
-        // ---- NHWC output: transpose 32x32 accumulator chunks through shared memory so that a warp instruction touches
-        // 4 rows x 128 contiguous bytes (residual reads and stores fully coalesced) instead of 32 scattered 16-byte pieces
-        float* st = estage + (size_t)(warp - (TC_AWARPS + 2)) * 32 * 36;
-        const int sub = lane & 7, rsel = lane >> 3;            // this thread: columns 4*sub..+3 of rows rsel + 4j
-        size_t orow[8]; uint32_t rmask = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int mm = m0 + q * 32 + rsel + 4 * j;
-          orow[j] = 0;
-          if (mm < p.M) {
-            const int ni = mm / HoWo, pp = mm - ni * HoWo;
-            orow[j] = ((size_t)ni * p.oH + (pp / p.Wo) * p.oy_mul + p.oy_add) * p.oW + (pp % p.Wo) * p.ox_mul + p.ox_add;
-            rmask |= 1u << j;
-          }
-        }
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 32) {
-          uint32_t raw[32];
-          tmem_ld16(taddr_row + (uint32_t)cb, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
-          if (cb + 16 < BN) tmem_ld16(taddr_row + (uint32_t)cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
-          else {
-#pragma unroll
-            for (int e = 16; e < 32; ++e) raw[e] = 0;
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<uint4*>(st + lane * 36 + 4 * i) = make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
-          __syncwarp();
-          const int cq = n0 + cb + 4 * sub;
-          if (cq < p.Cout) {
-            const bool full = cq + 3 < p.Cout;
-            float sc4[4] = {1.f, 1.f, 1.f, 1.f}, sh4[4] = {0.f, 0.f, 0.f, 0.f}, mu4[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (cq + e < p.Cout) {
-                if (p.scale) sc4[e] = __ldg(p.scale + cq + e);
-                if (p.shift) sh4[e] = __ldg(p.shift + cq + e);
-                if (p.mul1) mu4[e] = __ldg(p.mul1 + cq + e);
-              }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (!((rmask >> j) & 1u)) continue;
-              const float4 a = *reinterpret_cast<const float4*>(st + (rsel + 4 * j) * 36 + 4 * sub);
-              float v4[4] = {a.x, a.y, a.z, a.w};
-              if (p.add0) {
-                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add0 + orow[j] * p.add0_cs + p.add0_coff + cq);
-                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
-                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add0[orow[j] * p.add0_cs + p.add0_coff + cq + e]; }
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x = v4[e];
-                if (p.scale) x *= sc4[e];
-                x += sh4[e];
-                x = act_t<ACT>(x, p.act);
-                if (p.mul1) x *= mu4[e];
-                v4[e] = x;
-              }
-              if (p.add1) {
-                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add1 + orow[j] * p.add1_cs + p.add1_coff + cq);
-                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
-                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add1[orow[j] * p.add1_cs + p.add1_coff + cq + e]; }
-              }
-              if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-              else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
-            }
-          }
-          __syncwarp();
-        }
-      } else {
-        const bool vec_out = !p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0;
-        const bool vec0 = p.add0 && !p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0;
-        const bool vec1 = p.add1 && !p.add1_planar && ((p.add1_cs | p.add1_coff) & 3) == 0;
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 16) {
-          uint32_t raw[16];
-          tmem_ld16(taddr_row + (uint32_t)cb, raw);
-          tmem_ld_wait();
-          const int c0 = n0 + cb;
-          if (!row_ok || c0 >= p.Cout) continue;
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const int cq = c0 + qq * 4;
-            if (cq >= p.Cout) break;
-            float v4[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v4[e] = __uint_as_float(raw[qq * 4 + e]);
-            const bool full = cq + 3 < p.Cout;
-            if (p.add0) {
-              if (vec0 && full) {
-                const float4 tt = *reinterpret_cast<const float4*>(p.add0 + opix * p.add0_cs + p.add0_coff + cq);
-                v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (cq + e < p.Cout)
-                    v4[e] += p.add0_planar ? p.add0[((size_t)nimg * p.add0_cs + p.add0_coff + cq + e) * oplane + opl_pix]
-                                           : p.add0[opix * p.add0_cs + p.add0_coff + cq + e];
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cq + e;
-              if (c < p.Cout) {
-                float x = v4[e];
-                if (p.scale) x *= __ldg(p.scale + c);
-                if (p.shift) x += __ldg(p.shift + c);
-                x = act_t<ACT>(x, p.act);
-                if (p.mul1) x *= __ldg(p.mul1 + c);
-                v4[e] = x;
-              }
-            }
-            if (p.add1) {
-              if (vec1 && full) {
-                const float4 tt = *reinterpret_cast<const float4*>(p.add1 + opix * p.add1_cs + p.add1_coff + cq);
-                v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (cq + e < p.Cout)
-                    v4[e] += p.add1_planar ? p.add1[((size_t)nimg * p.add1_cs + p.add1_coff + cq + e) * oplane + opl_pix]
-                                           : p.add1[opix * p.add1_cs + p.add1_coff + cq + e];
-              }
-            }
-            if (vec_out && full) {
-              *reinterpret_cast<float4*>(p.out + opix * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (cq + e < p.Cout) {
-                  if (p.out_planar) p.out[((size_t)nimg * p.out_cs + p.out_coff + cq + e) * oplane + opl_pix] = v4[e];
-                  else p.out[opix * p.out_cs + p.out_coff + cq + e] = v4[e];
-                }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(buf));                     // accumulator drained -> the MMA warp may overwrite it
-    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_AWARPS) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+  if (warp == TC_MMAWARP) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
 // split-K second pass: sum the partials and run the regular epilogue (one thread per 4 output channels of a pixel)
@@ -763,7 +714,7 @@ void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
   make_weight_tmap(&cw.tmm, wm, cw.tc_kpad, cw.tc_npad, bn);
 }
 
-int conv_tc_stat_blocks(const ConvOp& op) { return op.tc_npad / op.tc_bn; }   // one partial per N tile
+int conv_tc_stat_blocks(const ConvOp& op) { return 2 * (op.tc_npad / op.tc_bn); }   // two column halves per N tile
 
 bool conv_tc_supported(const ConvOp& op) {
   if (!g_tc_enabled || !op.wh || !op.wm) return false;
@@ -790,14 +741,14 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
   p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
-  MITB_CHECK(!op.stat_max || op.stat_ld == op.tc_npad / op.tc_bn, "tc conv: stat_ld must equal conv_stat_blocks(op)");
+  MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tc conv: stat_ld must equal conv_stat_blocks(op)");
   p.M = op.in.N * op.Ho * op.Wo; p.K = op.ntaps * op.in.C; p.BN = op.tc_bn;
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tc conv: bad BN %d", p.BN);
   MITB_CHECK(p.in_planar || p.Cin % 4 == 0, "tc conv: Cin must be a multiple of 4");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;                                  // double-buffered accumulator
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)p.BN * 128;
-  const size_t epi_bytes = (size_t)TC_EWARPS * 32 * 36 * sizeof(float);
+  const size_t epi_bytes = (size_t)TC_AWARPS * 32 * 20 * sizeof(float);
   int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes); if (stages > 4) stages = 4;
   MITB_CHECK(stages >= 2, "tc conv: tile does not fit shared memory");
   p.stages = stages;

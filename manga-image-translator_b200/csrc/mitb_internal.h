@@ -184,12 +184,12 @@ void lama_run(Ctx&, LamaModel&, const float* img, const float* mask, const int* 
               int tw, int n, int h, int w, float* out, cudaStream_t st, const LamaU8Io* u8 = nullptr);
 
 struct Profiler {
-  struct Rec { const char* kind; double flops, bytes; cudaEvent_t a, b; };
+  struct Rec { const char* kind; double flops, bytes; cudaEvent_t a, b; int m, k, n; };
   bool on = false; std::vector<Rec> recs; std::vector<cudaEvent_t> pool;
 };
 extern thread_local Profiler* g_prof;
 struct ProfScope {          // records an event pair around the launches issued in its scope (no-op unless profiling)
-  ProfScope(const char* kind, double flops, double bytes, cudaStream_t st);
+  ProfScope(const char* kind, double flops, double bytes, cudaStream_t st, int m = 0, int k = 0, int n = 0);
   ~ProfScope();
   Profiler* p_; cudaStream_t st_;
 };
