@@ -46,6 +46,7 @@ struct TcParams {
   float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;     // fused log-softmax/argmax partials (vocabulary head)
   int M, K, BN, stages, tmem_cols;
   int splits; float* partial;                                       // split-K: partial sums [splits][M][npad]
+  int tmin_dy, tmax_dy, tmin_dx, tmax_dx;                           // extent of the tap offsets (fast interior addressing)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -179,7 +180,7 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __maxnreg__(200) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A_hi 16K | A_mid 16K | B_hi BN*128 | B_mid BN*128], then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -383,18 +384,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       int z, m0, n0, kb_begin, kb_end;
       decode(t, z, m0, n0, kb_begin, kb_end);
-      int rbase[8], ryx[8]; uint32_t okmask = 0;     // per row: image row base (nimg*H), (iy0<<16 | ix0)
+      // per row: pointer to the pixel under tap (0,0); rows whose whole tap window lies inside the image take the fast
+      // address path (pointer + per-K-block tap offset), border rows redo the padded index arithmetic
+      const float* rptr[8]; int rbase[8], ryx[8]; uint32_t okmask = 0, imask = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = m0 + rb + 16 * i;
-        rbase[i] = 0; ryx[i] = 0;
+        rbase[i] = 0; ryx[i] = 0; rptr[i] = p.in;
         if (m < p.M) {
           const int nimg = m / HoWo, rr = m - nimg * HoWo;
           const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
-          rbase[i] = nimg * p.H; ryx[i] = ((oy * p.sy) << 16) | (ox * p.sx);
+          const int iy0 = oy * p.sy, ix0 = ox * p.sx;
+          rbase[i] = nimg * p.H; ryx[i] = (iy0 << 16) | ix0;
+          rptr[i] = p.in + ((size_t)(nimg * p.H + iy0) * p.W + ix0) * p.in_cs + p.in_coff;
           okmask |= 1u << i;
+          if (iy0 + p.tmin_dy >= 0 && iy0 + p.tmax_dy < p.H && ix0 + p.tmin_dx >= 0 && ix0 + p.tmax_dx < p.W) imask |= 1u << i;
         }
       }
+      const uint32_t soff0 = (uint32_t)rb * 128u + ((((uint32_t)f4 >> 1) ^ ((uint32_t)rb & 7u)) << 4) + ((uint32_t)f4 & 1u) * 8u;
       int tap, ci;
       { const int k0 = kb_begin * TC_BK + f4 * 4; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
 
@@ -403,10 +410,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         B.ci = ci; B.valid = 0;
         const bool kval = k < p.K;
         const int dy = kval ? p.tdy[tap] : 0, dx = kval ? p.tdx[tap] : 0;
+        const long toff = (long)(dy * p.W + dx) * p.in_cs + ci;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           B.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kval && ((okmask >> i) & 1u)) {
+          if (kval && ((imask >> i) & 1u)) {
+            B.v[i] = __ldg(reinterpret_cast<const float4*>(rptr[i] + toff));
+            B.valid |= 1u << i;
+          } else if (kval && ((okmask >> i) & 1u)) {
             int iy = (ryx[i] >> 16) + dy, ix = (ryx[i] & 0xffff) + dx;
             bool inb = true;
             if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
@@ -441,8 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         uint8_t* a_mid = a_hi + a_bytes;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t r = (uint32_t)(rb + 16 * i);
-          const uint32_t off = r * 128u + ((((uint32_t)f4 >> 1) ^ (r & 7u)) << 4) + ((uint32_t)f4 & 1u) * 8u;
+          const uint32_t off = soff0 + (uint32_t)i * 2048u;          // row rb+16i: same swizzle phase, 16 rows further
           *reinterpret_cast<uint2*>(a_hi + off) = hi[i];
           *reinterpret_cast<uint2*>(a_mid + off) = mid[i];
         }
@@ -732,7 +742,14 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   memcpy(&p.tmh, &op.tmh, sizeof(CUtensorMap)); memcpy(&p.tmm, &op.tmm, sizeof(CUtensorMap));
   p.kpad = op.tc_kpad; p.npad = op.tc_npad;
   p.ntaps = op.ntaps;
-  for (int t = 0; t < op.ntaps; ++t) { p.tdy[t] = op.tdy[t]; p.tdx[t] = op.tdx[t]; }
+  p.tmin_dy = p.tmin_dx = 127; p.tmax_dy = p.tmax_dx = -127;
+  for (int t = 0; t < op.ntaps; ++t) {
+    p.tdy[t] = op.tdy[t]; p.tdx[t] = op.tdx[t];
+    if (op.tdy[t] < p.tmin_dy) p.tmin_dy = op.tdy[t];
+    if (op.tdy[t] > p.tmax_dy) p.tmax_dy = op.tdy[t];
+    if (op.tdx[t] < p.tmin_dx) p.tmin_dx = op.tdx[t];
+    if (op.tdx[t] > p.tmax_dx) p.tmax_dx = op.tdx[t];
+  }
   p.sy = op.sy; p.sx = op.sx; p.pad = op.pad; p.Ho = op.Ho; p.Wo = op.Wo;
   p.out = op.out.p; p.oH = op.out.H; p.oW = op.out.W; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C;
   p.out_planar = op.out.planar; p.oy_mul = op.oy_mul; p.oy_add = op.oy_add; p.ox_mul = op.ox_mul; p.ox_add = op.ox_add;
