@@ -180,7 +180,7 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 }
 
 template <int ACT>
-__global__ void __maxnreg__(200) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __maxnreg__(192) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A_hi 16K | A_mid 16K | B_hi BN*128 | B_mid BN*128], then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -204,7 +204,7 @@ __global__ void __maxnreg__(200) conv_tc_kernel(const __grid_constant__ TcParams
   const uint32_t acc_stride = (uint32_t)(p.tmem_cols >> 1);          // columns per accumulator buffer
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_AWARPS * 32 + 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), (p.in_planar ? TC_AWARPS * 32 : TC_AWARPS * 16) + 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_AWARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -372,100 +372,100 @@ __global__ void __maxnreg__(200) conv_tc_kernel(const __grid_constant__ TcParams
     mbar_arrive(tempty_bar(buf));                       // accumulator drained -> the MMA warp may overwrite it
   };
   if (warp < TC_AWARPS && !p.in_planar) {
-    // =========================== A producers, NHWC input (coalesced) ===========================
-    // A K block is 64 channels = 16 float4 per GEMM row.  Thread t owns float4 column f4 = t&15 of the 8 rows rb+16i
-    // (rb = t>>4): one warp instruction reads two complete 256-byte row segments (instead of 32 scattered 16-byte
-    // pieces), and all 8 loads of a thread share one (tap, channel) cursor.
-    const int f4 = tid & 15, rb = tid >> 4;
+    // =========================== A producers, NHWC input (coalesced, ping-pong groups) ===========================
+    // A K block is 64 channels = 16 float4 per GEMM row.  The 8 producer warps form two groups of 128 threads that take
+    // alternate K blocks: while one group splits/stores its block (and executes the proxy fence, which drains that
+    // thread's outstanding loads), the other group's global loads for the next block are in flight.  Inside a group thread
+    // tg owns float4 column f4 = tg&15 of the 16 rows rb+8i (rb = tg>>4): a warp instruction reads two complete 256-byte
+    // row segments, and all 16 loads of a thread share one (tap, channel) cursor.
+    const int grp = warp >> 2, tg = tid & 127;
+    const int f4 = tg & 15, rb = tg >> 4;
     const int HoWo = p.Ho * p.Wo;
-    struct Blk { float4 v[8]; int ci; uint32_t valid; };
-    Blk R0, R1;
-    int it = 0, lt = 0;
+    const uint32_t soff0 = (uint32_t)rb * 128u + ((((uint32_t)f4 >> 1) ^ ((uint32_t)rb & 7u)) << 4) + ((uint32_t)f4 & 1u) * 8u;
+    float4 v[16];
+    int git = 0, lt = 0;                               // global K-block / tile counters of this CTA
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       int z, m0, n0, kb_begin, kb_end;
       decode(t, z, m0, n0, kb_begin, kb_end);
-      // per row: pointer to the pixel under tap (0,0); rows whose whole tap window lies inside the image take the fast
-      // address path (pointer + per-K-block tap offset), border rows redo the padded index arithmetic
-      const float* rptr[8]; int rbase[8], ryx[8]; uint32_t okmask = 0, imask = 0;
+      // per row: pointer to the pixel under tap (0,0) and its (iy0, ix0); rows whose whole tap window lies inside the
+      // image take the fast address path (pointer + per-K-block tap offset), border rows redo the padded index arithmetic
+      const float* rptr[16]; int ryx[16]; uint32_t okmask = 0, imask = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + rb + 16 * i;
-        rbase[i] = 0; ryx[i] = 0; rptr[i] = p.in;
+      for (int i = 0; i < 16; ++i) {
+        const int m = m0 + rb + 8 * i;
+        ryx[i] = 0; rptr[i] = p.in;
         if (m < p.M) {
           const int nimg = m / HoWo, rr = m - nimg * HoWo;
           const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
           const int iy0 = oy * p.sy, ix0 = ox * p.sx;
-          rbase[i] = nimg * p.H; ryx[i] = (iy0 << 16) | ix0;
+          ryx[i] = (iy0 << 16) | ix0;
           rptr[i] = p.in + ((size_t)(nimg * p.H + iy0) * p.W + ix0) * p.in_cs + p.in_coff;
           okmask |= 1u << i;
           if (iy0 + p.tmin_dy >= 0 && iy0 + p.tmax_dy < p.H && ix0 + p.tmin_dx >= 0 && ix0 + p.tmax_dx < p.W) imask |= 1u << i;
         }
       }
-      const uint32_t soff0 = (uint32_t)rb * 128u + ((((uint32_t)f4 >> 1) ^ ((uint32_t)rb & 7u)) << 4) + ((uint32_t)f4 & 1u) * 8u;
+      // this group's first K block of the tile: the one whose global index has parity grp
+      int kb = kb_begin + ((grp - (git & 1)) & 1);
       int tap, ci;
-      { const int k0 = kb_begin * TC_BK + f4 * 4; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
+      { const int k0 = kb * TC_BK + f4 * 4; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
+      uint32_t valid = 0; int cur_ci = 0;
 
-      auto load_block = [&](int kb, Blk& B) {
-        const int k = kb * TC_BK + f4 * 4;
-        B.ci = ci; B.valid = 0;
+      auto load_block = [&](int kbl) {
+        const int k = kbl * TC_BK + f4 * 4;
+        cur_ci = ci; valid = 0;
         const bool kval = k < p.K;
         const int dy = kval ? p.tdy[tap] : 0, dx = kval ? p.tdx[tap] : 0;
         const long toff = (long)(dy * p.W + dx) * p.in_cs + ci;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          B.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 16; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kval && ((imask >> i) & 1u)) {
-            B.v[i] = __ldg(reinterpret_cast<const float4*>(rptr[i] + toff));
-            B.valid |= 1u << i;
+            v[i] = __ldg(reinterpret_cast<const float4*>(rptr[i] + toff));
+            valid |= 1u << i;
           } else if (kval && ((okmask >> i) & 1u)) {
-            int iy = (ryx[i] >> 16) + dy, ix = (ryx[i] & 0xffff) + dx;
+            const int iy0 = ryx[i] >> 16, ix0 = ryx[i] & 0xffff;
+            int iy = iy0 + dy, ix = ix0 + dx;
             bool inb = true;
             if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
             else inb = (iy >= 0) & (iy < p.H) & (ix >= 0) & (ix < p.W);
             if (inb) {
-              B.v[i] = __ldg(reinterpret_cast<const float4*>(p.in + ((size_t)(rbase[i] + iy) * p.W + ix) * p.in_cs + p.in_coff + ci));
-              B.valid |= 1u << i;
+              v[i] = __ldg(reinterpret_cast<const float4*>(rptr[i] + (long)((iy - iy0) * p.W + (ix - ix0)) * p.in_cs + ci));
+              valid |= 1u << i;
             }
           }
         }
-        ci += TC_BK; while (ci >= p.Cin) { ci -= p.Cin; ++tap; }
+        ci += 2 * TC_BK; while (ci >= p.Cin) { ci -= p.Cin; ++tap; }      // this group's next block is two K blocks ahead
       };
-      auto produce = [&](int kb, Blk& B) {
-        const int s = it % S;
-        uint2 hi[8], mid[8];
+
+      if (kb < kb_end) load_block(kb);
+      for (; kb < kb_end; kb += 2) {
+        const int itg = git + (kb - kb_begin);               // global index of this K block
+        const int s = itg % S;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.in_scale && B.valid) {
-          sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + B.ci)); sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + B.ci));
+        if (p.in_scale && valid) {
+          sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + cur_ci)); sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + cur_ci));
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 v = B.v[i];
-          if (p.in_scale && ((B.valid >> i) & 1u)) {
-            v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
-            if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          }
-          split4(v, hi[i], mid[i]);
-        }
-        if (kb + 2 < kb_end) load_block(kb + 2, B);
-        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+        mbar_wait(empty_bar(s), ((itg / S) & 1) ^ 1);
         uint8_t* a_hi = smem + (size_t)s * stage_bytes;
         uint8_t* a_mid = a_hi + a_bytes;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t off = soff0 + (uint32_t)i * 2048u;          // row rb+16i: same swizzle phase, 16 rows further
-          *reinterpret_cast<uint2*>(a_hi + off) = hi[i];
-          *reinterpret_cast<uint2*>(a_mid + off) = mid[i];
+        for (int i = 0; i < 16; ++i) {
+          float4 x = v[i];
+          if (p.in_scale && ((valid >> i) & 1u)) {
+            x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
+            if (p.in_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+          }
+          uint2 hi, mid;
+          split4(x, hi, mid);
+          const uint32_t off = soff0 + (uint32_t)i * 1024u;          // row rb+8i: same swizzle phase, 8 rows further
+          *reinterpret_cast<uint2*>(a_hi + off) = hi;
+          *reinterpret_cast<uint2*>(a_mid + off) = mid;
         }
-        fence_async_smem();
+        fence_async_smem();                                  // also drains this thread's loads: none are outstanding here
         mbar_arrive(full_bar(s));
-        ++it;
-      };
-      load_block(kb_begin, R0);
-      if (kb_begin + 1 < kb_end) load_block(kb_begin + 1, R1);
-      for (int kb = kb_begin; kb < kb_end; kb += 2) {
-        produce(kb, R0);
-        if (kb + 1 < kb_end) produce(kb + 1, R1);
+        if (kb + 2 < kb_end) load_block(kb + 2);             // in flight while the other group produces the next K block
       }
+      git += kb_end - kb_begin;
       epilogue_tile(lt, z, m0, n0);
     }
   } else if (warp < TC_AWARPS) {

@@ -135,3 +135,79 @@ void launch_conv_thin(const ConvOp& op, cudaStream_t st) {
 }
 
 }  // namespace mitb
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ConvTranspose2d(Cin -> 1, k4, s2, p1) + activation, the last layer of both DBHead branches (dbnet_convnext.py:393,445)
+// at full page resolution.  As four sub-pixel implicit GEMMs the 32-channel input is gathered 4 x 4 times; here a CTA
+// stages a 16x16 block of input positions with a 1-pixel halo in shared memory once and every thread emits the 2x2
+// output block of its position: y = 2i - 1 + ky  ->  output (2i+py) takes ky in {1,3} (py=0: rows i, i-1) or {0,2}
+// (py=1: rows i+1, i).
+namespace mitb {
+namespace {
+constexpr int CT_T = 16, CT_PITCH = 36;          // tile edge (input positions), padded channel pitch (floats) for Cin = 32
+
+__global__ void __launch_bounds__(256) convT4_c1_kernel(const float* in, int H, int W, int in_cs, int in_coff, const float* w,
+                                                        const float* bias, int act, float* out, int out_cs, int out_coff) {
+  __shared__ __align__(16) float tile[(CT_T + 2) * (CT_T + 2) * CT_PITCH];     // 18*18*36*4 = 46656 B
+  __shared__ __align__(16) float wsm[16 * 32];                                  // [ky*4+kx][cin]
+  const int n = blockIdx.z, i0 = blockIdx.y * CT_T, j0 = blockIdx.x * CT_T;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < 16 * 32; t += 256) { const int c = t & 31, k = t >> 5; wsm[k * 32 + c] = w[c * 16 + k]; }
+  for (int t = tid; t < (CT_T + 2) * (CT_T + 2) * 8; t += 256) {
+    const int c4 = t & 7, pp = t >> 3;
+    const int ty = pp / (CT_T + 2), tx = pp - ty * (CT_T + 2);
+    const int gy = i0 + ty - 1, gx = j0 + tx - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)(n * H + gy) * W + gx) * in_cs + in_coff + c4 * 4));
+    *reinterpret_cast<float4*>(&tile[pp * CT_PITCH + c4 * 4]) = v;
+  }
+  __syncthreads();
+  const int ly = tid >> 4, lx = tid & 15;
+  const int i = i0 + ly, j = j0 + lx;
+  if (i >= H || j >= W) return;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int ky = py == 0 ? 1 + 2 * a : 2 * a, dy = (py + 1 - ky) / 2;      // exact: (py+1-ky) is even
+          const int kx = px == 0 ? 1 + 2 * b : 2 * b, dx = (px + 1 - kx) / 2;
+          const float* src = &tile[((ly + 1 + dy) * (CT_T + 2) + (lx + 1 + dx)) * CT_PITCH];
+          const float* wk = &wsm[(ky * 4 + kx) * 32];
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(src + c), ww = *reinterpret_cast<const float4*>(wk + c);
+            s = fmaf(x.x, ww.x, s); s = fmaf(x.y, ww.y, s); s = fmaf(x.z, ww.z, s); s = fmaf(x.w, ww.w, s);
+          }
+          acc[py][px] += s;
+        }
+  const float bv = bias ? bias[0] : 0.f;
+  const size_t plane = (size_t)(2 * H) * (2 * W);
+  float* o = out + ((size_t)n * out_cs + out_coff) * plane;
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+    float v0 = acc[py][0] + bv, v1 = acc[py][1] + bv;
+    if (act == ACT_SIGMOID || act == ACT_SIGMOID2) { v0 = 1.f / (1.f + expf(-v0)); v1 = 1.f / (1.f + expf(-v1)); }
+    if (act == ACT_SIGMOID2) { v0 = 1.f / (1.f + expf(-v0)); v1 = 1.f / (1.f + expf(-v1)); }
+    *reinterpret_cast<float2*>(o + (size_t)(2 * i + py) * (2 * W) + 2 * j) = make_float2(v0, v1);
+  }
+}
+}  // namespace
+
+// in: NHWC view with 32 channels; w: ConvTranspose2d weight [32,1,4,4] (PyTorch layout, fp32 device); out: planar view, C == 1
+void launch_convT4_c1(const View& in, const float* w, const float* bias, int act, const View& out, cudaStream_t st) {
+  MITB_CHECK(!in.planar && in.C == 32 && in.cs % 4 == 0 && in.coff % 4 == 0, "convT4_c1 expects a 32-channel NHWC input");
+  MITB_CHECK(out.planar && out.C == 1 && out.H == 2 * in.H && out.W == 2 * in.W && out.N == in.N, "convT4_c1 output shape");
+  dim3 grid((in.W + CT_T - 1) / CT_T, (in.H + CT_T - 1) / CT_T, in.N);
+  ProfScope ps("convT4_c1", 2.0 * in.pixels() * 4 * 4 * 32, 4.0 * (in.pixels() * 32 + in.pixels() * 4), st);
+  convT4_c1_kernel<<<grid, 256, 0, st>>>(in.p, in.H, in.W, in.cs, in.coff, w, bias, act, out.p, out.cs, out.coff);
+  count_launch();
+  CUDA_OK(cudaGetLastError());
+}
+}  // namespace mitb

@@ -19,7 +19,7 @@ struct CnStage {
   std::vector<CnBlock> blocks;
 };
 struct Upconv { CnBlock blk; ConvW up[4]; };
-struct HeadBranch { ConvW c0; ConvW t1[4]; ConvW t2[4]; };
+struct HeadBranch { ConvW c0; ConvW t1[4]; ConvW t2[4]; const float* t2_w = nullptr; const float* t2_b = nullptr; };
 
 struct DbnetModel {
   DevBlob blob;
@@ -97,6 +97,7 @@ DbnetModel* dbnet_build(Ctx& ctx, const Weights& W) {
       if (W.has(p + "0.bias")) h.c0.shift = L.vec(p + "0.bias");
       load_convT4(L, p + "2.weight", 4, 1, h.t1, L.vec(p + "2.bias"));
       load_convT4(L, p + "4.weight", 4, 1, h.t2, L.vec(p + "4.bias"));
+      h.t2_w = L.vec(p + "4.weight"); h.t2_b = L.vec(p + "4.bias");      // raw [32,1,4,4] for the fused full-resolution kernel
     }
     m->m0 = L.conv("conv_mask.0.weight", 1, 1); m->m0.shift = L.vec("conv_mask.0.bias");
     m->m2 = L.conv("conv_mask.2.weight", 1, 1); m->m2.shift = L.vec("conv_mask.2.bias");
@@ -206,7 +207,7 @@ void dbnet_run(Ctx& ctx, DbnetModel& m, const float* x_nchw, const uint8_t* x_u8
       { ConvOp op = Exec::op_from(hb.c0, up8, a); op.act = ACT_SILU; e.conv(op); }
       e.convT2(hb.t1, a, b, [](ConvOp& op) { op.act = ACT_SILU; });
       View o = dbv; o.coff = br;
-      e.convT2(hb.t2, b, o, [&](ConvOp& op) { op.act = br == 0 ? ACT_SIGMOID : ACT_SIGMOID2; });
+      if (!e.dry) launch_convT4_c1(b, hb.t2_w, hb.t2_b, br == 0 ? ACT_SIGMOID : ACT_SIGMOID2, o, st);
       ws.release(mk);
     }
     {  // conv_mask (dbnet_convnext.py:455-460)

@@ -96,6 +96,7 @@ void launch_layernorm(const View& in, const View& out, const float* w, const flo
 void launch_dwconv7_ln(const View& in, const View& out, const float* wdw /*[49][C]*/, const float* bdw,
                        const float* lnw, const float* lnb, float eps, cudaStream_t st);
 void launch_avgpool(const View& in, const View& out, int mode /*0: 2x2s2, 1: k2 s(2,1) p(0,1)*/, cudaStream_t st);
+void launch_convT4_c1(const View& in, const float* w, const float* bias, int act, const View& out, cudaStream_t st);
 void launch_nchw_to_nhwc(const float* src, int N, int C, int H, int W, const View& dst, cudaStream_t st);
 void launch_nhwc_to_nchw(const View& src, float* dst, cudaStream_t st);
 void launch_u8_to_nhwc(const uint8_t* src, int N, int H, int W, int C, const View& dst, float mul, float add,
