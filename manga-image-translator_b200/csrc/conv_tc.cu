@@ -180,7 +180,7 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 }
 
 template <int ACT>
-__global__ void __maxnreg__(192) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A_hi 16K | A_mid 16K | B_hi BN*128 | B_mid BN*128], then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -389,17 +389,17 @@ __global__ void __maxnreg__(192) conv_tc_kernel(const __grid_constant__ TcParams
       decode(t, z, m0, n0, kb_begin, kb_end);
       // per row: pointer to the pixel under tap (0,0) and its (iy0, ix0); rows whose whole tap window lies inside the
       // image take the fast address path (pointer + per-K-block tap offset), border rows redo the padded index arithmetic
-      const float* rptr[16]; int ryx[16]; uint32_t okmask = 0, imask = 0;
+      uint32_t roff[16]; int ryx[16]; uint32_t okmask = 0, imask = 0;     // element offsets fit 32 bits (checked on the host)
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int m = m0 + rb + 8 * i;
-        ryx[i] = 0; rptr[i] = p.in;
+        ryx[i] = 0; roff[i] = 0;
         if (m < p.M) {
           const int nimg = m / HoWo, rr = m - nimg * HoWo;
           const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
           const int iy0 = oy * p.sy, ix0 = ox * p.sx;
           ryx[i] = (iy0 << 16) | ix0;
-          rptr[i] = p.in + ((size_t)(nimg * p.H + iy0) * p.W + ix0) * p.in_cs + p.in_coff;
+          roff[i] = (uint32_t)(((size_t)(nimg * p.H + iy0) * p.W + ix0) * p.in_cs + p.in_coff);
           okmask |= 1u << i;
           if (iy0 + p.tmin_dy >= 0 && iy0 + p.tmax_dy < p.H && ix0 + p.tmin_dx >= 0 && ix0 + p.tmax_dx < p.W) imask |= 1u << i;
         }
@@ -415,12 +415,12 @@ __global__ void __maxnreg__(192) conv_tc_kernel(const __grid_constant__ TcParams
         cur_ci = ci; valid = 0;
         const bool kval = k < p.K;
         const int dy = kval ? p.tdy[tap] : 0, dx = kval ? p.tdx[tap] : 0;
-        const long toff = (long)(dy * p.W + dx) * p.in_cs + ci;
+        const int toff = (dy * p.W + dx) * p.in_cs + ci;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kval && ((imask >> i) & 1u)) {
-            v[i] = __ldg(reinterpret_cast<const float4*>(rptr[i] + toff));
+            v[i] = __ldg(reinterpret_cast<const float4*>(p.in + (roff[i] + (uint32_t)toff)));
             valid |= 1u << i;
           } else if (kval && ((okmask >> i) & 1u)) {
             const int iy0 = ryx[i] >> 16, ix0 = ryx[i] & 0xffff;
@@ -429,7 +429,7 @@ __global__ void __maxnreg__(192) conv_tc_kernel(const __grid_constant__ TcParams
             if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
             else inb = (iy >= 0) & (iy < p.H) & (ix >= 0) & (ix < p.W);
             if (inb) {
-              v[i] = __ldg(reinterpret_cast<const float4*>(rptr[i] + (long)((iy - iy0) * p.W + (ix - ix0)) * p.in_cs + ci));
+              v[i] = __ldg(reinterpret_cast<const float4*>(p.in + (roff[i] + (uint32_t)(((iy - iy0) * p.W + (ix - ix0)) * p.in_cs + ci))));
               valid |= 1u << i;
             }
           }
@@ -762,6 +762,7 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   p.M = op.in.N * op.Ho * op.Wo; p.K = op.ntaps * op.in.C; p.BN = op.tc_bn;
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tc conv: bad BN %d", p.BN);
   MITB_CHECK(p.in_planar || p.Cin % 4 == 0, "tc conv: Cin must be a multiple of 4");
+  MITB_CHECK((size_t)op.in.pixels() * op.in.cs < (size_t)1 << 31, "tc conv: input tensor too large for 32-bit element offsets");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;                                  // double-buffered accumulator
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)p.BN * 128;
