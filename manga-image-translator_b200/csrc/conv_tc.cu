@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t acc_stride = (uint32_t)(p.tmem_cols >> 1);          // columns per accumulator buffer
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_AWARPS * 16 + 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), (p.in_planar ? TC_AWARPS * 32 : TC_AWARPS * 16) + 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_AWARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -469,84 +469,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       epilogue_tile(lt, z, m0, n0);
     }
   } else if (warp < TC_AWARPS) {
-    // =========================== A producers, planar (NCHW) input, 1x1 convs of the spectral branch ===========================
-    // Same ping-pong scheme.  A thread owns 4 consecutive pixels (one float4 along the plane) x two 8-channel chunks:
-    // 16 fully coalesced LDG.128 per K block (a warp reads 512 contiguous bytes of one channel plane), an in-register
-    // 8x4 transpose, then one hi + one mid 16-byte swizzled store per (row, chunk).
-    const int grp = warp >> 2, tg = tid & 127;
-    const int m4 = tg & 31, c0 = tg >> 5;                  // rows 4*m4..+3 ; chunks c0 and c0+4
-    const int HW = p.H * p.W;
-    const bool vec_ok = (HW & 3) == 0;
-    float4 v[2][8];
-    int git = 0, lt = 0;
+    // =========================== A producers, planar input: two threads per GEMM row (coalesced along pixels) ===========
+    const int r = tid & 127, half = tid >> 7;
+    const int HoWo = p.Ho * p.Wo, HW = p.H * p.W;
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    struct Blk { float v[4][8]; int cix[4]; };        // raw loaded values + channel index of each chunk (-1: all zero)
+    Blk R0, R1;
+    int it = 0, lt = 0;                                // global K-block / tile counters of this CTA
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       int z, m0, n0, kb_begin, kb_end;
       decode(t, z, m0, n0, kb_begin, kb_end);
-      const int mrow = m0 + 4 * m4;
-      int kb = kb_begin + ((grp - (git & 1)) & 1);
+      const int m = m0 + r;
+      const bool row_ok = m < p.M;
+      int nimg = 0, iy0 = 0, ix0 = 0, pix = 0;
+      if (row_ok) {
+        nimg = m / HoWo; const int rr = m - nimg * HoWo;
+        const int oy = rr / p.Wo, ox = rr - oy * p.Wo;
+        iy0 = oy * p.sy; ix0 = ox * p.sx; pix = rr;
+      }
+      int tap = 0, ci = 0;                             // cursor of this thread's next 8-channel chunk
+      if (!p.in_planar) { const int k0 = kb_begin * TC_BK + half * 32; tap = k0 / p.Cin; ci = k0 - tap * p.Cin; }
 
-      auto load_block = [&](int kbl) {
+      auto load_block = [&](int kb, Blk& B) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int j = 0; j < 4; ++j) {
+          const int k = kb * TC_BK + half * 32 + j * 8;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int k = kbl * TC_BK + (c0 + 4 * h) * 8 + e;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < p.K && mrow < p.M) {
-              if (vec_ok && mrow + 3 < p.M) {
-                const int nimg = mrow / HW, pix = mrow - nimg * HW;
-                x = __ldg(reinterpret_cast<const float4*>(p.in + ((size_t)nimg * p.in_cs + p.in_coff + k) * HW + pix));
-              } else {
-                float tt[4];
+          for (int e = 0; e < 8; ++e) B.v[j][e] = 0.f;
+          B.cix[j] = -1;
+          if (row_ok && k < p.K) {
+            if (!p.in_planar) {
+              int iy = iy0 + p.tdy[tap], ix = ix0 + p.tdx[tap];
+              bool inb = true;
+              if (p.pad == PAD_REFLECT) { iy = reflect_tc(iy, p.H); ix = reflect_tc(ix, p.W); }
+              else inb = (iy >= 0) & (iy < p.H) & (ix >= 0) & (ix < p.W);
+              if (inb) {
+                const float* src = p.in + ((size_t)(nimg * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                B.v[j][0] = a.x; B.v[j][1] = a.y; B.v[j][2] = a.z; B.v[j][3] = a.w;
+                B.v[j][4] = b.x; B.v[j][5] = b.y; B.v[j][6] = b.z; B.v[j][7] = b.w;
+                B.cix[j] = ci;
+              }
+            } else {
+              B.cix[j] = k;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int mm = mrow + q; tt[q] = 0.f;
-                  if (mm < p.M) { const int nimg = mm / HW, pix = mm - nimg * HW; tt[q] = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + k) * HW + pix); }
-                }
-                x = make_float4(tt[0], tt[1], tt[2], tt[3]);
+              for (int e = 0; e < 8; ++e)
+                if (k + e < p.K) B.v[j][e] = __ldg(p.in + ((size_t)nimg * p.in_cs + p.in_coff + k + e) * HW + pix);
+            }
+          }
+          if (!p.in_planar) { ci += 8; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }
+        }
+        if (!p.in_planar) { ci += 32; while (ci >= p.Cin) { ci -= p.Cin; ++tap; } }     // skip the other half-row
+      };
+      // BN+ReLU prologue (applied at consume time so the loads stay in flight) + hi/mid split + swizzled stores
+      auto produce = [&](int kb, Blk& B) {
+        const int s = it % S;
+        uint4 hi[4], mid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p.in_scale && B.cix[j] >= 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = B.cix[j] + e;
+              if (!p.in_planar || ch < p.K) {
+                const float tt = B.v[j][e] * __ldg(p.in_scale + ch) + __ldg(p.in_shift + ch);
+                B.v[j][e] = p.in_relu ? fmaxf(tt, 0.f) : tt;
               }
             }
-            v[h][e] = x;
           }
-      };
-
-      if (kb < kb_end) load_block(kb);
-      for (; kb < kb_end; kb += 2) {
-        const int itg = git + (kb - kb_begin);
-        const int s = itg % S;
-        mbar_wait(empty_bar(s), ((itg / S) & 1) ^ 1);
+          split8(B.v[j], hi[j], mid[j]);
+        }
+        if (kb + 2 < kb_end) load_block(kb + 2, B);     // refill this ring slot: loads stay in flight for two K blocks
+        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
         uint8_t* a_hi = smem + (size_t)s * stage_bytes;
         uint8_t* a_mid = a_hi + a_bytes;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int ch0 = kb * TC_BK + (c0 + 4 * h) * 8;
-          float sc[8], sh[8];
-          if (p.in_scale) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { sc[e] = ch0 + e < p.K ? __ldg(p.in_scale + ch0 + e) : 0.f; sh[e] = ch0 + e < p.K ? __ldg(p.in_shift + ch0 + e) : 0.f; }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 w4 = v[h][e];
-              x[e] = q == 0 ? w4.x : q == 1 ? w4.y : q == 2 ? w4.z : w4.w;
-              if (p.in_scale) { x[e] = x[e] * sc[e] + sh[e]; if (p.in_relu) x[e] = fmaxf(x[e], 0.f); if (ch0 + e >= p.K || mrow + q >= p.M) x[e] = 0.f; }
-            }
-            uint4 hi, mid;
-            split8(x, hi, mid);
-            const uint32_t r = (uint32_t)(4 * m4 + q);
-            const uint32_t off = r * 128u + ((((uint32_t)(c0 + 4 * h)) ^ (r & 7u)) << 4);
-            *reinterpret_cast<uint4*>(a_hi + off) = hi;
-            *reinterpret_cast<uint4*>(a_mid + off) = mid;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c = (uint32_t)(half * 4 + j);
+          const uint32_t off = row_off + ((c ^ sw) << 4);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi[j];
+          *reinterpret_cast<uint4*>(a_mid + off) = mid[j];
         }
         fence_async_smem();
         mbar_arrive(full_bar(s));
-        if (kb + 2 < kb_end) load_block(kb + 2);
+        ++it;
+      };
+      load_block(kb_begin, R0);
+      if (kb_begin + 1 < kb_end) load_block(kb_begin + 1, R1);
+      for (int kb = kb_begin; kb < kb_end; kb += 2) {
+        produce(kb, R0);
+        if (kb + 1 < kb_end) produce(kb + 1, R1);
       }
-      git += kb_end - kb_begin;
       epilogue_tile(lt, z, m0, n0);
     }
   } else if (warp == TC_MMAWARP) {
