@@ -1,0 +1,506 @@
+// TMA-fed tcgen05 implicit-GEMM convolution for sm_100a (stride-1 convs whose Cin is a multiple of 64).
+//
+// conv_tc.cu gathers the fp32 activation tile with producer warps and splits it into bf16 hi/mid inside the main loop.
+// Measured on B200 that loop is bound by the producers' own instruction stream (~650 dependent instructions per K block per
+// warp, 2 producer warps per scheduler): with loads, conversion, weight TMA and even the MMAs removed the kernel skeleton
+// still needs ~2600 cycles per K block against a tensor floor of 768 (profiles/r01_tc_skeleton_experiments.txt), and a 3x3
+// conv repeats the conversion of every input element 9 times (once per tap) per N tile.
+//
+// Here the conversion happens ONCE per input element in a separate memory-bound pass (split_pad_kernel: fp32 view ->
+// dense bf16 hi / mid NHWC tensors, optional BN+ReLU prologue, reflect halo materialised, planar inputs transposed), and the
+// GEMM main loop has no producer warps at all:
+//   warp 9   one thread: per K block (= 64 channels of one tap) four TMA loads - the activation box {64 ch, bw, bh} of the
+//            hi and mid tensors at the tap-shifted pixel coordinates (zero padding = TMA out-of-bounds fill) and the
+//            weight boxes {64 k, BN} - all landing in the UMMA K-major SWIZZLE_128B layout, completing on the stage's
+//            "full" mbarrier (expect_tx);
+//   warp 8   one thread: 12 tcgen05.mma per K block (bf16x3: Ah*Bh + Ah*Bm + Am*Bh), tcgen05.commit -> "empty" barrier;
+//   warps 0-7 epilogue: TMEM -> registers -> (+add0)*scale+shift -> act -> *mul1 -> +add1 -> coalesced fp32 stores through a
+//            shared-memory transpose; double-buffered accumulator, so tile i drains while tile i+1 is multiplied.
+// An output tile is a bh x bw pixel patch of one image (bw*bh = 128, bw a power of two) so that a tap is a rectangular TMA
+// box; 1x1 convs use the flattened [pixels][C] matrix (bw = 128, bh = 1).  Persistent CTAs, one per SM.
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+#include <cuda_bf16.h>
+#include "mitb_internal.h"
+
+namespace mitb {
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TM_EWARPS = 8;
+constexpr int TM_MMAWARP = TM_EWARPS, TM_TMAWARP = TM_EWARPS + 1;
+constexpr int TM_THREADS = (TM_EWARPS + 2) * 32;
+
+struct TmaParams {
+  CUtensorMap ta_hi, ta_mid;                                  // activations: 4-D (C, Wp, Hp, N) bf16, box {64, bw, bh, 1}
+  CUtensorMap tb_hi, tb_mid;                                  // weights: 2-D (K, Npad) bf16, box {64, BN}
+  int ntaps, cblks; int8_t tdy[kMaxTaps], tdx[kMaxTaps];      // tap offsets in (padded) input coordinates
+  int N, Ho, Wo, M, lin;                                      // lin: tile = 128 consecutive rows of the flattened [M][C] matrix
+  int bw_log2, tiles_x, tiles_y;
+  int npad, BN, stages, tmem_cols;
+  float* out; int oH, oW, out_cs, out_coff, Cout, out_planar, oy_mul, oy_add, ox_mul, ox_add;
+  const float* add0; int add0_cs, add0_coff, add0_planar;
+  const float* add1; int add1_cs, add1_coff, add1_planar;
+  const float* scale; const float* shift; const float* mul1; int act;
+  float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;
+};
+
+#include "tc_common.cuh"
+
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c, int x, int y, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n) : "memory");
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN, S = p.stages;
+  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)BN * 128;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  float* estage = reinterpret_cast<float*>(bars + 2 * S + 6);          // [TM_EWARPS][32 rows][20 floats] epilogue transpose buffer
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = p.ntaps * p.cblks;
+  const int bw = 1 << p.bw_log2, bh = TC_BM >> p.bw_log2;
+  const int mt = p.N * p.tiles_y * p.tiles_x, nt = p.npad / BN;
+  const int total_tiles = mt * nt;
+  const uint32_t acc_stride = (uint32_t)(p.tmem_cols >> 1);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TM_EWARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TM_MMAWARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile t -> (image, patch origin, N tile); N fastest so CTAs running together share the activation boxes in L2
+  auto decode = [&](int t, int& nimg, int& oy0, int& ox0, int& n0) {
+    const int mtile = t / nt; n0 = (t - mtile * nt) * BN;
+    const int per_img = p.tiles_y * p.tiles_x;
+    nimg = mtile / per_img; const int r = mtile - nimg * per_img;
+    const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+    oy0 = ty * bh; ox0 = tx * bw;
+  };
+
+  if (warp < TM_EWARPS) {
+    // =========================== epilogue: warp w drains TMEM lane quarter (w & 3), column half (w >> 2) ===========================
+    const int q = warp & 3, ehalf = warp >> 2;
+    const int HoWo = p.Ho * p.Wo;
+    const int nchunks = BN / 16, h0 = (nchunks + 1) / 2;
+    const int cb_lo = (ehalf == 0 ? 0 : h0) * 16, cb_hi = (ehalf == 0 ? h0 : nchunks) * 16;
+    // row r of the tile -> output pixel (linear index into the Ho x Wo grid of image nimg), -1 when outside
+    auto row_pixel = [&](int r, int nimg_t, int oy0, int ox0, int& nimg, int& oy, int& ox) -> bool {
+      if (p.lin) {
+        const int m = ox0 + r;
+        if (m >= p.M) return false;
+        nimg = m / HoWo; const int pp = m - nimg * HoWo;
+        oy = pp / p.Wo; ox = pp - oy * p.Wo;
+        return true;
+      }
+      nimg = nimg_t; oy = oy0 + (r >> p.bw_log2); ox = ox0 + (r & (bw - 1));
+      return oy < p.Ho && ox < p.Wo;
+    };
+    int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      int nimg_t, oy0, ox0, n0;
+      decode(t, nimg_t, oy0, ox0, n0);
+      const int buf = lt & 1;
+      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + (uint32_t)buf * acc_stride + ((uint32_t)(q * 32) << 16);
+      if (p.stat_max) {
+        // vocabulary head: online (max, first argmax, sum exp) over this thread's columns of its row (model_48px_ctc.py:460-461)
+        int nimg, oy, ox;
+        const bool row_ok = row_pixel(q * 32 + lane, nimg_t, oy0, ox0, nimg, oy, ox);
+        float bm = -INFINITY, bs = 0.f; int bi = 0x7fffffff;
+#pragma unroll 1
+        for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+          uint32_t raw[16];
+          tmem_ld16(taddr_row + (uint32_t)cb, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int c = n0 + cb + e;
+            if (c < p.Cout) {
+              const float x = __uint_as_float(raw[e]) + (p.shift ? __ldg(p.shift + c) : 0.f);
+              if (x > bm) { bs = bs * expf(bm - x) + 1.f; bm = x; bi = c; }
+              else bs += expf(x - bm);
+            }
+          }
+        }
+        if (row_ok) {
+          const size_t m = ((size_t)nimg * p.Ho + oy) * p.Wo + ox;
+          const size_t o = m * p.stat_ld + (n0 / BN) * 2 + ehalf;
+          p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
+        }
+      } else if (!p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0 &&
+                 (!p.add0 || (!p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0)) &&
+                 (!p.add1 || (!p.add1_planar && ((p.add1_cs | p.add1_coff) & 3) == 0))) {
+        // ---- NHWC output: transpose 32x16 accumulator chunks through shared memory so that one warp instruction touches
+        // 8 rows x 64 contiguous bytes (residual reads and stores coalesced)
+        float* st = estage + (size_t)warp * 32 * 20;
+        const int sub = lane & 3, rsel = lane >> 2;              // this thread: columns 4*sub..+3 of rows rsel + 8j
+        size_t orow[4]; uint32_t rmask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int nimg, oy, ox;
+          orow[j] = 0;
+          if (row_pixel(q * 32 + rsel + 8 * j, nimg_t, oy0, ox0, nimg, oy, ox)) {
+            orow[j] = ((size_t)nimg * p.oH + oy * p.oy_mul + p.oy_add) * p.oW + ox * p.ox_mul + p.ox_add;
+            rmask |= 1u << j;
+          }
+        }
+#pragma unroll 1
+        for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+          uint32_t raw[16];
+          tmem_ld16(taddr_row + (uint32_t)cb, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(st + lane * 20 + 4 * i) = make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
+          __syncwarp();
+          const int cq = n0 + cb + 4 * sub;
+          if (cq < p.Cout) {
+            const bool full = cq + 3 < p.Cout;
+            float sc4[4] = {1.f, 1.f, 1.f, 1.f}, sh4[4] = {0.f, 0.f, 0.f, 0.f}, mu4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (cq + e < p.Cout) {
+                if (p.scale) sc4[e] = __ldg(p.scale + cq + e);
+                if (p.shift) sh4[e] = __ldg(p.shift + cq + e);
+                if (p.mul1) mu4[e] = __ldg(p.mul1 + cq + e);
+              }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (!((rmask >> j) & 1u)) continue;
+              const float4 a = *reinterpret_cast<const float4*>(st + (rsel + 8 * j) * 20 + 4 * sub);
+              float v4[4] = {a.x, a.y, a.z, a.w};
+              if (p.add0) {
+                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add0 + orow[j] * p.add0_cs + p.add0_coff + cq);
+                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
+                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add0[orow[j] * p.add0_cs + p.add0_coff + cq + e]; }
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = v4[e];
+                if (p.scale) x *= sc4[e];
+                x += sh4[e];
+                x = act_t<ACT>(x, p.act);
+                if (p.mul1) x *= mu4[e];
+                v4[e] = x;
+              }
+              if (p.add1) {
+                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add1 + orow[j] * p.add1_cs + p.add1_coff + cq);
+                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
+                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add1[orow[j] * p.add1_cs + p.add1_coff + cq + e]; }
+              }
+              if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+              else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // ---- planar (NCHW) or unaligned output: lane = pixel, so each channel's stores are contiguous across lanes
+        int nimg = 0, oy = 0, ox = 0;
+        const bool row_ok = row_pixel(q * 32 + lane, nimg_t, oy0, ox0, nimg, oy, ox);
+        const int py = oy * p.oy_mul + p.oy_add, px = ox * p.ox_mul + p.ox_add;
+        const size_t opix = ((size_t)nimg * p.oH + py) * p.oW + px;
+        const size_t oplane = (size_t)p.oH * p.oW, opl_pix = (size_t)py * p.oW + px;
+#pragma unroll 1
+        for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+          uint32_t raw[16];
+          tmem_ld16(taddr_row + (uint32_t)cb, raw);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int c = n0 + cb + e;
+            if (c >= p.Cout) break;
+            float x = __uint_as_float(raw[e]);
+            if (p.add0) x += p.add0_planar ? p.add0[((size_t)nimg * p.add0_cs + p.add0_coff + c) * oplane + opl_pix] : p.add0[opix * p.add0_cs + p.add0_coff + c];
+            if (p.scale) x *= __ldg(p.scale + c);
+            if (p.shift) x += __ldg(p.shift + c);
+            x = act_t<ACT>(x, p.act);
+            if (p.mul1) x *= __ldg(p.mul1 + c);
+            if (p.add1) x += p.add1_planar ? p.add1[((size_t)nimg * p.add1_cs + p.add1_coff + c) * oplane + opl_pix] : p.add1[opix * p.add1_cs + p.add1_coff + c];
+            if (p.out_planar) p.out[((size_t)nimg * p.out_cs + p.out_coff + c) * oplane + opl_pix] = x;
+            else p.out[opix * p.out_cs + p.out_coff + c] = x;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));        // accumulator drained -> the MMA warp may overwrite it
+    }
+  } else if (warp == TM_MMAWARP) {
+    // =========================== MMA issuer (one elected thread) ===========================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_stride;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(full_bar(s), (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+          const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+          const uint64_t dah = make_desc_sw128(a_hi), dam = make_desc_sw128(a_mid), dbh = make_desc_sw128(b_hi), dbm = make_desc_sw128(b_mid);
+#pragma unroll
+          for (int j = 0; j < TC_BK / 16; ++j) {
+            const uint64_t adv = (uint64_t)(j * 2);                  // 16 bf16 = 32 bytes = 2 x 16-byte units inside the swizzle row
+            umma_bf16(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, dah + adv, dbm + adv, idesc, 1u);
+            umma_bf16(tmem_d, dam + adv, dbh + adv, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));          // frees the stage when the MMAs retire
+        }
+        umma_commit(tfull_bar(buf));          // accumulator of this tile complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp == TM_TMAWARP) {
+    // =========================== operand loader: four TMA boxes per K block ===========================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int nimg, oy0, ox0, n0;
+        decode(t, nimg, oy0, ox0, n0);
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+          const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+          const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+          mbar_arrive_expect_tx(full_bar(s), 2 * a_bytes + 2 * b_bytes);
+          const int x = ox0 + p.tdx[tap], y = oy0 + p.tdy[tap];
+          tma_load_4d(a_hi, &p.ta_hi, full_bar(s), cb * TC_BK, x, y, nimg);
+          tma_load_4d(a_mid, &p.ta_mid, full_bar(s), cb * TC_BK, x, y, nimg);
+          tma_load_2d(b_hi, &p.tb_hi, full_bar(s), kb * TC_BK, n0);
+          tma_load_2d(b_mid, &p.tb_mid, full_bar(s), kb * TC_BK, n0);
+          if (++cb == p.cblks) { cb = 0; ++tap; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TM_MMAWARP) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fp32 view -> dense bf16 hi / mid NHWC tensors [N][Hp][Wp][C] (one thread = 8 channels of one padded pixel).
+// Halo rows/cols (pt/pl) are filled by reflection (PAD_REFLECT); zero padding needs no halo (TMA out-of-bounds fill).
+// The BN+ReLU prologue of the pre-activation ResNet is applied here, once per element.
+struct SplitParams {
+  const float* in; int N, H, W, C, cs, coff, planar;
+  int Hp, Wp, pt, pl;
+  const float* in_scale; const float* in_shift; int in_relu;
+  uint16_t* hi; uint16_t* mid;
+};
+
+__global__ void __launch_bounds__(256) split_pad_kernel(const SplitParams q) {
+  const int c8n = q.C >> 3;
+  const long npix = (long)q.N * q.Hp * q.Wp;
+  const long total = npix * c8n;
+  const size_t HW = (size_t)q.H * q.W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long pix; int c8;
+    if (q.planar) { c8 = (int)(i / npix); pix = i - (long)c8 * npix; }      // pixel fastest: plane reads coalesced
+    else { pix = i / c8n; c8 = (int)(i - pix * c8n); }                        // channel fastest: NHWC reads coalesced
+    const int x = (int)(pix % q.Wp); const long r = pix / q.Wp;
+    const int y = (int)(r % q.Hp), n = (int)(r / q.Hp);
+    const int sy = reflect_tc(y - q.pt, q.H), sx = reflect_tc(x - q.pl, q.W);
+    const int c0 = c8 * 8;
+    float v[8];
+    if (q.planar) {
+      const float* src = q.in + ((size_t)n * q.cs + q.coff + c0) * HW + (size_t)sy * q.W + sx;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(src + (size_t)e * HW);
+    } else {
+      const float* src = q.in + ((size_t)(n * q.H + sy) * q.W + sx) * q.cs + q.coff + c0;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    if (q.in_scale) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float t = v[e] * __ldg(q.in_scale + c0 + e) + __ldg(q.in_shift + c0 + e);
+        v[e] = q.in_relu ? fmaxf(t, 0.f) : t;
+      }
+    }
+    uint4 hi, mid;
+    split8(v, hi, mid);
+    const size_t o = (size_t)pix * q.C + c0;
+    *reinterpret_cast<uint4*>(q.hi + o) = hi;
+    *reinterpret_cast<uint4*>(q.mid + o) = mid;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    MITB_CHECK(p && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 4-D activation map over a dense bf16 tensor [N][Hp][Wp][C], box {64, bw, bh, 1}, 128-byte swizzle, zero OOB fill
+void make_act_tmap(CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int bw, int bh) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+  const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MITB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for activations [%d,%d,%d,%d] box %dx%d", (int)r, N, Hp, Wp, C, bw, bh);
+}
+
+bool g_tma_enabled = true;
+
+}  // namespace
+
+void conv_tma_set_enabled(bool on) { g_tma_enabled = on; }
+
+bool conv_tma_supported(const ConvOp& op) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("MITB_NO_TMA_CONV"); env = (e && atoi(e)) ? 0 : 1; }
+  if (!g_tma_enabled || !env || !op.wh || !op.wm) return false;
+  if (op.sy != 1 || op.sx != 1) return false;
+  if (op.in.C % 64 != 0 || op.in.C < 64) return false;
+  if (op.tc_kpad != op.ntaps * op.in.C) return false;          // weight K layout must be (tap, channel) without padding
+  if (!op.in.planar && (op.in.cs % 4 != 0 || op.in.coff % 4 != 0)) return false;
+  if (op.in.planar && op.ntaps != 1) return false;
+  const long M = (long)op.in.N * op.Ho * op.Wo;
+  if (M < 128) return false;
+  return true;
+}
+
+void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
+  const int C = op.in.C, N = op.in.N, H = op.in.H, W = op.in.W;
+  // ---- geometry of the split tensor: reflect padding is materialised as a halo, zero padding is TMA out-of-bounds fill
+  int tmin_dy = 127, tmax_dy = -127, tmin_dx = 127, tmax_dx = -127;
+  for (int t = 0; t < op.ntaps; ++t) {
+    tmin_dy = op.tdy[t] < tmin_dy ? op.tdy[t] : tmin_dy; tmax_dy = op.tdy[t] > tmax_dy ? op.tdy[t] : tmax_dy;
+    tmin_dx = op.tdx[t] < tmin_dx ? op.tdx[t] : tmin_dx; tmax_dx = op.tdx[t] > tmax_dx ? op.tdx[t] : tmax_dx;
+  }
+  int pt = 0, pb = 0, pl = 0, pr = 0;
+  if (op.pad == PAD_REFLECT) {
+    pt = tmin_dy < 0 ? -tmin_dy : 0; pl = tmin_dx < 0 ? -tmin_dx : 0;
+    pb = (op.Ho - 1) + tmax_dy - (H - 1); if (pb < 0) pb = 0;
+    pr = (op.Wo - 1) + tmax_dx - (W - 1); if (pr < 0) pr = 0;
+  }
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  const size_t elems = (size_t)N * Hp * Wp * C;
+  static uint16_t* g_split = nullptr; static size_t g_split_cap = 0;      // grow-only scratch (hi | mid), one per process
+  if (2 * elems > g_split_cap) {
+    if (g_split) { CUDA_OK(cudaDeviceSynchronize()); CUDA_OK(cudaFree(g_split)); }
+    g_split_cap = 2 * elems + (2 * elems) / 8;
+    CUDA_OK(cudaMalloc(&g_split, g_split_cap * sizeof(uint16_t)));
+  }
+  uint16_t* hi = g_split; uint16_t* mid = g_split + elems;
+  {
+    SplitParams q;
+    q.in = op.in.p; q.N = N; q.H = H; q.W = W; q.C = C; q.cs = op.in.cs; q.coff = op.in.coff; q.planar = op.in.planar;
+    q.Hp = Hp; q.Wp = Wp; q.pt = pt; q.pl = pl;
+    q.in_scale = op.in_scale; q.in_shift = op.in_shift; q.in_relu = op.in_relu;
+    q.hi = hi; q.mid = mid;
+    const long total = (long)(elems / 8);
+    long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+    split_pad_kernel<<<(int)blocks, 256, 0, st>>>(q);
+    count_launch();
+  }
+
+  TmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.ntaps = op.ntaps; p.cblks = C / TC_BK;
+  for (int t = 0; t < op.ntaps; ++t) { p.tdy[t] = (int8_t)(op.tdy[t] + pt); p.tdx[t] = (int8_t)(op.tdx[t] + pl); }
+  p.N = N; p.Ho = op.Ho; p.Wo = op.Wo; p.M = N * op.Ho * op.Wo;
+  const bool lin = op.ntaps == 1 && op.Ho == H && op.Wo == W;       // 1x1: flattened [pixels][C] matrix
+  p.lin = lin ? 1 : 0;
+  int bw, bh;
+  if (lin) { bw = 128; bh = 1; p.tiles_x = (p.M + 127) / 128; p.tiles_y = 1; p.N = 1; }
+  else {
+    long best = -1; bw = 128;
+    for (int cand = 128; cand >= 8; cand >>= 1) {
+      const int ch = 128 / cand;
+      const long cost = (long)((op.Wo + cand - 1) / cand) * cand * (long)((op.Ho + ch - 1) / ch) * ch;
+      if (best < 0 || cost < best) { best = cost; bw = cand; }
+    }
+    bh = 128 / bw;
+    p.tiles_x = (op.Wo + bw - 1) / bw; p.tiles_y = (op.Ho + bh - 1) / bh;
+  }
+  p.bw_log2 = 0; while ((1 << p.bw_log2) < bw) ++p.bw_log2;
+  if (lin) { make_act_tmap(&p.ta_hi, hi, 1, 1, N * Hp * Wp, C, bw, bh); make_act_tmap(&p.ta_mid, mid, 1, 1, N * Hp * Wp, C, bw, bh); }
+  else { make_act_tmap(&p.ta_hi, hi, N, Hp, Wp, C, bw, bh); make_act_tmap(&p.ta_mid, mid, N, Hp, Wp, C, bw, bh); }
+  static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "TmaDesc must mirror CUtensorMap");
+  memcpy(&p.tb_hi, &op.tmh, sizeof(CUtensorMap)); memcpy(&p.tb_mid, &op.tmm, sizeof(CUtensorMap));
+  p.npad = op.tc_npad; p.BN = op.tc_bn;
+  MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tma conv: bad BN %d", p.BN);
+  p.out = op.out.p; p.oH = op.out.H; p.oW = op.out.W; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C;
+  p.out_planar = op.out.planar; p.oy_mul = op.oy_mul; p.oy_add = op.oy_add; p.ox_mul = op.ox_mul; p.ox_add = op.ox_add;
+  p.add0 = op.add0.p; p.add0_cs = op.add0.cs; p.add0_coff = op.add0.coff; p.add0_planar = op.add0.planar;
+  p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
+  p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
+  p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
+  MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
+  int cols = 32; while (cols < p.BN) cols <<= 1;
+  p.tmem_cols = 2 * cols;
+  const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)p.BN * 128;
+  const size_t epi_bytes = (size_t)TM_EWARPS * 32 * 20 * sizeof(float);
+  int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes); if (stages > 6) stages = 6;
+  MITB_CHECK(stages >= 2, "tma conv: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + (2 * stages + 6) * 8 + epi_bytes + 1024;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int total_tiles = p.N * p.tiles_y * p.tiles_x * (p.npad / p.BN);
+  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  switch (op.stat_max ? ACT_NONE : p.act) {
+    case ACT_NONE: conv_tma_kernel<ACT_NONE><<<grid, TM_THREADS, smem, st>>>(p); break;
+    case ACT_RELU: conv_tma_kernel<ACT_RELU><<<grid, TM_THREADS, smem, st>>>(p); break;
+    case ACT_GELU: conv_tma_kernel<ACT_GELU><<<grid, TM_THREADS, smem, st>>>(p); break;
+    case ACT_SILU: conv_tma_kernel<ACT_SILU><<<grid, TM_THREADS, smem, st>>>(p); break;
+    default: conv_tma_kernel<-1><<<grid, TM_THREADS, smem, st>>>(p); break;
+  }
+  count_launch();
+  CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace mitb
