@@ -539,6 +539,20 @@ __global__ void split_weights_kernel(const float* w, int K, int Cout, int ldw, u
   }
 }
 
+// same, with every tap's channel range padded to cp (multiple of 64): k' = tap*cp + c
+__global__ void split_weights_padded_kernel(const float* w, int ntaps, int Cin, int cp, int Cout, int ldw, uint16_t* wh, uint16_t* wm, int npad) {
+  const int kp = ntaps * cp;
+  const long total = (long)npad * kp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kp), n = (int)(i / kp);
+    const int tap = k / cp, c = k - tap * cp;
+    float x = (c < Cin && n < Cout) ? w[(size_t)(tap * Cin + c) * ldw + n] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 m = __float2bfloat16_rn(x - __bfloat162float(h));
+    wh[i] = __bfloat16_as_ushort(h); wm[i] = __bfloat16_as_ushort(m);
+  }
+}
+
 int pick_bn(int Cout) {
   const int tiles = (Cout + 255) / 256;
   int bn = (Cout + tiles - 1) / tiles;
@@ -594,6 +608,17 @@ void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
   cw.wh = wh; cw.wm = wm;
   make_weight_tmap(&cw.tmh, wh, cw.tc_kpad, cw.tc_npad, bn);
   make_weight_tmap(&cw.tmm, wm, cw.tc_kpad, cw.tc_npad, bn);
+  if (cw.Cin % 64 != 0 && cw.Cin % 8 == 0 && cw.Cin >= 16) {
+    // the TMA-fed kernel consumes K blocks of 64 channels of one tap: give it a copy with each tap padded to a multiple of 64
+    const int cp = (cw.Cin + 63) / 64 * 64;
+    const size_t np = (size_t)cw.tc_npad * cw.ntaps * cp;
+    uint16_t* whp = (uint16_t*)blob.alloc_f((np + 1) / 2 + 4);
+    uint16_t* wmp = (uint16_t*)blob.alloc_f((np + 1) / 2 + 4);
+    int b2 = (int)((np + 255) / 256); if (b2 > 148 * 16) b2 = 148 * 16;
+    split_weights_padded_kernel<<<b2, 256, 0, st>>>(cw.w, cw.ntaps, cw.Cin, cp, cw.Cout, cw.ldw, whp, wmp, cw.tc_npad);
+    CUDA_OK(cudaGetLastError());
+    cw.whp = whp; cw.wmp = wmp; cw.tc_cp = cp;
+  }
 }
 
 int conv_tc_stat_blocks(const ConvOp& op) { return 2 * (op.tc_npad / op.tc_bn); }   // two column halves per N tile

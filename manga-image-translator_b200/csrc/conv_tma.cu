@@ -38,6 +38,7 @@ struct TmaParams {
   CUtensorMap tb_hi, tb_mid;                                  // weights: 2-D (K, Npad) bf16, box {64, BN}
   int ntaps, cblks; int8_t tdy[kMaxTaps], tdx[kMaxTaps];      // tap offsets in (padded) input coordinates
   int N, Ho, Wo, M, lin;                                      // lin: tile = 128 consecutive rows of the flattened [M][C] matrix
+  int sy, sx;                                                 // conv stride (TMA element strides of the activation box)
   int bw_log2, tiles_x, tiles_y;
   int npad, BN, stages, tmem_cols;
   float* out; int oH, oW, out_cs, out_coff, Cout, out_planar, oy_mul, oy_add, ox_mul, ox_add;
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
           const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
           const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
           mbar_arrive_expect_tx(full_bar(s), 2 * a_bytes + 2 * b_bytes);
-          const int x = ox0 + p.tdx[tap], y = oy0 + p.tdy[tap];
+          const int x = ox0 * p.sx + p.tdx[tap], y = oy0 * p.sy + p.tdy[tap];
           tma_load_4d(a_hi, &p.ta_hi, full_bar(s), cb * TC_BK, x, y, nimg);
           tma_load_4d(a_mid, &p.ta_mid, full_bar(s), cb * TC_BK, x, y, nimg);
           tma_load_2d(b_hi, &p.tb_hi, full_bar(s), kb * TC_BK, n0);
@@ -314,14 +315,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
 // Halo rows/cols (pt/pl) are filled by reflection (PAD_REFLECT); zero padding needs no halo (TMA out-of-bounds fill).
 // The BN+ReLU prologue of the pre-activation ResNet is applied here, once per element.
 struct SplitParams {
-  const float* in; int N, H, W, C, cs, coff, planar;
+  const float* in; int N, H, W, C, Cp, cs, coff, planar;          // C source channels, Cp >= C stored channels (zero padded)
   int Hp, Wp, pt, pl;
   const float* in_scale; const float* in_shift; int in_relu;
   uint16_t* hi; uint16_t* mid;
 };
 
 __global__ void __launch_bounds__(256) split_pad_kernel(const SplitParams q) {
-  const int c8n = q.C >> 3;
+  const int c8n = q.Cp >> 3;
   const long npix = (long)q.N * q.Hp * q.Wp;
   const long total = npix * c8n;
   const size_t HW = (size_t)q.H * q.W;
@@ -334,25 +335,30 @@ __global__ void __launch_bounds__(256) split_pad_kernel(const SplitParams q) {
     const int sy = reflect_tc(y - q.pt, q.H), sx = reflect_tc(x - q.pl, q.W);
     const int c0 = c8 * 8;
     float v[8];
-    if (q.planar) {
-      const float* src = q.in + ((size_t)n * q.cs + q.coff + c0) * HW + (size_t)sy * q.W + sx;
+    if (c0 >= q.C) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = __ldg(src + (size_t)e * HW);
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
     } else {
-      const float* src = q.in + ((size_t)(n * q.H + sy) * q.W + sx) * q.cs + q.coff + c0;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    }
-    if (q.in_scale) {
+      if (q.planar) {
+        const float* src = q.in + ((size_t)n * q.cs + q.coff + c0) * HW + (size_t)sy * q.W + sx;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float t = v[e] * __ldg(q.in_scale + c0 + e) + __ldg(q.in_shift + c0 + e);
-        v[e] = q.in_relu ? fmaxf(t, 0.f) : t;
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(src + (size_t)e * HW);
+      } else {
+        const float* src = q.in + ((size_t)(n * q.H + sy) * q.W + sx) * q.cs + q.coff + c0;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+      if (q.in_scale) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = v[e] * __ldg(q.in_scale + c0 + e) + __ldg(q.in_shift + c0 + e);
+          v[e] = q.in_relu ? fmaxf(t, 0.f) : t;
+        }
       }
     }
     uint4 hi, mid;
     split8(v, hi, mid);
-    const size_t o = (size_t)pix * q.C + c0;
+    const size_t o = (size_t)pix * q.Cp + c0;
     *reinterpret_cast<uint4*>(q.hi + o) = hi;
     *reinterpret_cast<uint4*>(q.mid + o) = mid;
   }
@@ -372,16 +378,48 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 4-D activation map over a dense bf16 tensor [N][Hp][Wp][C], box {64, bw, bh, 1}, 128-byte swizzle, zero OOB fill
-void make_act_tmap(CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int bw, int bh) {
+// 4-D activation map over a dense bf16 tensor [N][Hp][Wp][C]: box = {64 ch, bw, bh, 1} pixels taken every (sx, sy)-th element,
+// 128-byte swizzle, zero out-of-bounds fill (= zero padding of the convolution)
+void make_act_tmap(CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int bw, int bh, int sx, int sy) {
   const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
   const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(bw * sx), (cuuint32_t)(bh * sy), 1};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
   const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, gdim, gstride, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MITB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for activations [%d,%d,%d,%d] box %dx%d", (int)r, N, Hp, Wp, C, bw, bh);
+  MITB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for activations [%d,%d,%d,%d] box %dx%d stride %dx%d", (int)r, N, Hp, Wp, C,
+             bw, bh, sx, sy);
+}
+
+// weight map over bf16 [rows][kdim] K-major: box {64 k, bn}; rows beyond `rows` are zero filled
+void make_w_tmap(CUtensorMap* m, const uint16_t* base, int kdim, int rows, int bn) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)kdim * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MITB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for weights [%d x %d] box %d", (int)r, rows, kdim, bn);
+}
+
+// N tile width: minimise waves x tile time.  Tile time per K block = max(tensor floor 6*bn cycles, operand bytes over the
+// SM's share of L2 bandwidth ~42 B/clk); candidates split Cout into j equal tiles rounded up to 16.
+int choose_bn(int Cout, long mtiles, int nkb, int sms) {
+  double best = 1e30; int best_bn = 16;
+  for (int j = 1; j <= 16; ++j) {
+    int bn = ((Cout + j - 1) / j + 15) & ~15;
+    if (bn > 256) continue;
+    if (bn < 16) bn = 16;
+    const long nt = (Cout + bn - 1) / bn;
+    const long waves = (mtiles * nt + sms - 1) / sms;
+    const double mma = 6.0 * bn, l2 = (32768.0 + 256.0 * bn) / 42.0;
+    const double tile = nkb * (mma > l2 ? mma : l2) + 40.0 * bn + 600.0;
+    const double cost = waves * tile;
+    if (cost < best * 0.999) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
 }
 
 bool g_tma_enabled = true;
@@ -394,9 +432,10 @@ bool conv_tma_supported(const ConvOp& op) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("MITB_NO_TMA_CONV"); env = (e && atoi(e)) ? 0 : 1; }
   if (!g_tma_enabled || !env || !op.wh || !op.wm) return false;
-  if (op.sy != 1 || op.sx != 1) return false;
-  if (op.in.C % 64 != 0 || op.in.C < 64) return false;
-  if (op.tc_kpad != op.ntaps * op.in.C) return false;          // weight K layout must be (tap, channel) without padding
+  if (op.sy < 1 || op.sy > 2 || op.sx < 1 || op.sx > 2) return false;
+  const int C = op.in.C;
+  if (C % 64 == 0) { if (op.tc_kpad != op.ntaps * C) return false; }       // main copy is already in (tap, 64-channel block) order
+  else if (!(op.whp && op.wmp && op.tc_cp >= C)) return false;             // needs the per-tap padded copy (Cin % 8 == 0, >= 16)
   if (!op.in.planar && (op.in.cs % 4 != 0 || op.in.coff % 4 != 0)) return false;
   if (op.in.planar && op.ntaps != 1) return false;
   const long M = (long)op.in.N * op.Ho * op.Wo;
@@ -406,6 +445,8 @@ bool conv_tma_supported(const ConvOp& op) {
 
 void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   const int C = op.in.C, N = op.in.N, H = op.in.H, W = op.in.W;
+  const bool padded_w = C % 64 != 0;
+  const int Cp = padded_w ? op.tc_cp : C;                           // channels stored per pixel (multiple of 64)
   // ---- geometry of the split tensor: reflect padding is materialised as a halo, zero padding is TMA out-of-bounds fill
   int tmin_dy = 127, tmax_dy = -127, tmin_dx = 127, tmax_dx = -127;
   for (int t = 0; t < op.ntaps; ++t) {
@@ -415,11 +456,11 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   int pt = 0, pb = 0, pl = 0, pr = 0;
   if (op.pad == PAD_REFLECT) {
     pt = tmin_dy < 0 ? -tmin_dy : 0; pl = tmin_dx < 0 ? -tmin_dx : 0;
-    pb = (op.Ho - 1) + tmax_dy - (H - 1); if (pb < 0) pb = 0;
-    pr = (op.Wo - 1) + tmax_dx - (W - 1); if (pr < 0) pr = 0;
+    pb = (op.Ho - 1) * op.sy + tmax_dy - (H - 1); if (pb < 0) pb = 0;
+    pr = (op.Wo - 1) * op.sx + tmax_dx - (W - 1); if (pr < 0) pr = 0;
   }
   const int Hp = H + pt + pb, Wp = W + pl + pr;
-  const size_t elems = (size_t)N * Hp * Wp * C;
+  const size_t elems = (size_t)N * Hp * Wp * Cp;
   static uint16_t* g_split = nullptr; static size_t g_split_cap = 0;      // grow-only scratch (hi | mid), one per process
   if (2 * elems > g_split_cap) {
     if (g_split) { CUDA_OK(cudaDeviceSynchronize()); CUDA_OK(cudaFree(g_split)); }
@@ -429,7 +470,7 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   uint16_t* hi = g_split; uint16_t* mid = g_split + elems;
   {
     SplitParams q;
-    q.in = op.in.p; q.N = N; q.H = H; q.W = W; q.C = C; q.cs = op.in.cs; q.coff = op.in.coff; q.planar = op.in.planar;
+    q.in = op.in.p; q.N = N; q.H = H; q.W = W; q.C = C; q.Cp = Cp; q.cs = op.in.cs; q.coff = op.in.coff; q.planar = op.in.planar;
     q.Hp = Hp; q.Wp = Wp; q.pt = pt; q.pl = pl;
     q.in_scale = op.in_scale; q.in_shift = op.in_shift; q.in_relu = op.in_relu;
     q.hi = hi; q.mid = mid;
@@ -439,13 +480,24 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     count_launch();
   }
 
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+
   TmaParams p;
   memset(&p, 0, sizeof(p));
-  p.ntaps = op.ntaps; p.cblks = C / TC_BK;
+  p.ntaps = op.ntaps; p.cblks = Cp / TC_BK;
   for (int t = 0; t < op.ntaps; ++t) { p.tdy[t] = (int8_t)(op.tdy[t] + pt); p.tdx[t] = (int8_t)(op.tdx[t] + pl); }
-  p.N = N; p.Ho = op.Ho; p.Wo = op.Wo; p.M = N * op.Ho * op.Wo;
-  const bool lin = op.ntaps == 1 && op.Ho == H && op.Wo == W;       // 1x1: flattened [pixels][C] matrix
-  p.lin = lin ? 1 : 0;
+  p.N = N; p.Ho = op.Ho; p.Wo = op.Wo; p.M = N * op.Ho * op.Wo; p.sy = op.sy; p.sx = op.sx;
+  const bool lin = op.ntaps == 1 && op.Ho == H && op.Wo == W && op.sy == 1 && op.sx == 1 && op.tdy[0] == 0 && op.tdx[0] == 0;
+  p.lin = lin ? 1 : 0;                                              // 1x1: flattened [pixels][C] matrix
   int bw, bh;
   if (lin) { bw = 128; bh = 1; p.tiles_x = (p.M + 127) / 128; p.tiles_y = 1; p.N = 1; }
   else {
@@ -459,12 +511,17 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     p.tiles_x = (op.Wo + bw - 1) / bw; p.tiles_y = (op.Ho + bh - 1) / bh;
   }
   p.bw_log2 = 0; while ((1 << p.bw_log2) < bw) ++p.bw_log2;
-  if (lin) { make_act_tmap(&p.ta_hi, hi, 1, 1, N * Hp * Wp, C, bw, bh); make_act_tmap(&p.ta_mid, mid, 1, 1, N * Hp * Wp, C, bw, bh); }
-  else { make_act_tmap(&p.ta_hi, hi, N, Hp, Wp, C, bw, bh); make_act_tmap(&p.ta_mid, mid, N, Hp, Wp, C, bw, bh); }
-  static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "TmaDesc must mirror CUtensorMap");
-  memcpy(&p.tb_hi, &op.tmh, sizeof(CUtensorMap)); memcpy(&p.tb_mid, &op.tmm, sizeof(CUtensorMap));
-  p.npad = op.tc_npad; p.BN = op.tc_bn;
+  if (lin) { make_act_tmap(&p.ta_hi, hi, 1, 1, N * Hp * Wp, Cp, bw, bh, 1, 1); make_act_tmap(&p.ta_mid, mid, 1, 1, N * Hp * Wp, Cp, bw, bh, 1, 1); }
+  else { make_act_tmap(&p.ta_hi, hi, N, Hp, Wp, Cp, bw, bh, op.sx, op.sy); make_act_tmap(&p.ta_mid, mid, N, Hp, Wp, Cp, bw, bh, op.sx, op.sy); }
+  // ---- N tile: fixed by the row-stat layout for the vocabulary head, otherwise chosen per launch against wave quantisation
+  const long mtiles = (long)p.N * p.tiles_y * p.tiles_x;
+  const int nkb = p.ntaps * p.cblks;
+  p.BN = op.stat_max ? op.tc_bn : choose_bn(op.out.C, mtiles, nkb, num_sms);
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tma conv: bad BN %d", p.BN);
+  p.npad = (op.out.C + p.BN - 1) / p.BN * p.BN;
+  const int kdim = p.ntaps * Cp;
+  make_w_tmap(&p.tb_hi, padded_w ? op.whp : op.wh, kdim, op.tc_npad, p.BN);
+  make_w_tmap(&p.tb_mid, padded_w ? op.wmp : op.wm, kdim, op.tc_npad, p.BN);
   p.out = op.out.p; p.oH = op.out.H; p.oW = op.out.W; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C;
   p.out_planar = op.out.planar; p.oy_mul = op.oy_mul; p.oy_add = op.oy_add; p.ox_mul = op.ox_mul; p.ox_add = op.ox_add;
   p.add0 = op.add0.p; p.add0_cs = op.add0.cs; p.add0_coff = op.add0.coff; p.add0_planar = op.add0.planar;
@@ -480,18 +537,8 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   MITB_CHECK(stages >= 2, "tma conv: tile does not fit shared memory");
   p.stages = stages;
   const size_t smem = stages * stage_bytes + (2 * stages + 6) * 8 + epi_bytes + 1024;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
-    CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  }
-  const int total_tiles = p.N * p.tiles_y * p.tiles_x * (p.npad / p.BN);
-  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  const long total_tiles = mtiles * (p.npad / p.BN);
+  const int grid = total_tiles < num_sms ? (int)total_tiles : num_sms;
   switch (op.stat_max ? ACT_NONE : p.act) {
     case ACT_NONE: conv_tma_kernel<ACT_NONE><<<grid, TM_THREADS, smem, st>>>(p); break;
     case ACT_RELU: conv_tma_kernel<ACT_RELU><<<grid, TM_THREADS, smem, st>>>(p); break;

@@ -16,6 +16,7 @@ struct Exec {
     op.sy = op.sx = stride; op.pad = pad_mode; op.Ho = out.H; op.Wo = out.W;
     op.scale = w.scale; op.shift = w.shift;
     op.wh = w.wh; op.wm = w.wm; op.tc_bn = w.tc_bn; op.tc_kpad = w.tc_kpad; op.tc_npad = w.tc_npad; op.tmh = w.tmh; op.tmm = w.tmm;
+    op.whp = w.whp; op.wmp = w.wmp; op.tc_cp = w.tc_cp;
     return op;
   }
   void conv(const ConvOp& op) { if (!dry) launch_conv(op, st); }

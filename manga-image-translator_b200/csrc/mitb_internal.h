@@ -77,6 +77,8 @@ struct ConvOp {
   // tensor-core copies of the weights (conv_tc.cu): bf16 hi/mid [tc_npad][tc_kpad], K-major; null -> SIMT path only
   const uint16_t* wh = nullptr; const uint16_t* wm = nullptr; int tc_bn = 0, tc_kpad = 0, tc_npad = 0;
   TmaDesc tmh, tmm;                   // TMA descriptors of wh / wm
+  // per-tap channel-padded copies [tc_npad][ntaps*tc_cp] for the TMA-fed kernel when Cin % 64 != 0 (null otherwise)
+  const uint16_t* whp = nullptr; const uint16_t* wmp = nullptr; int tc_cp = 0;
   // optional fused row statistics (vocabulary head): no tensor output, per (row, column-block) partials
   float* stat_max = nullptr; float* stat_sum = nullptr; int* stat_idx = nullptr; int stat_ld = 0;
 };
@@ -143,6 +145,7 @@ struct ConvW {
   const float* scale = nullptr; const float* shift = nullptr;   // folded BN / bias (may be null)
   const uint16_t* wh = nullptr; const uint16_t* wm = nullptr; int tc_bn = 0, tc_kpad = 0, tc_npad = 0;
   TmaDesc tmh, tmm;
+  const uint16_t* whp = nullptr; const uint16_t* wmp = nullptr; int tc_cp = 0;   // per-tap channel-padded copies (conv_tma.cu)
 };
 struct DevBlob;
 void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st);   // build the bf16 hi/mid tensor-core weight copies

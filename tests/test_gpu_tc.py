@@ -35,6 +35,10 @@ TC_CASES = [
     (1, 1024, 12, 16, 128, 7, 1, 3, "zeros", 0),       # DBNet upconv1-like: M = 192, K = 50176 -> split-K over 74 CTAs
     (1, 64, 40, 36, 3, 3, 1, 1, "reflect", 4),         # thin output on the tensor cores (BN = 16)
     (1, 32, 30, 26, 1, 1, 1, 0, "zeros", 4),           # mask head 1x1 -> 1 channel
+    (1, 160, 13, 21, 160, 3, 1, 1, "zeros", 1),        # OCR layer3: Cin = 160 -> per-tap padding to 192 on the TMA path
+    (2, 80, 9, 70, 96, 3, 1, 1, "zeros", 0),           # Cin = 80 -> 128, Cout = 96 (BN chosen per launch), batch of 2 patches
+    (1, 256, 33, 47, 256, 3, 2, 1, "reflect", 0),      # LaMa downsample: stride 2 + reflect halo through TMA element strides
+    (1, 192, 40, 24, 384, 1, 1, 0, "zeros", 0),        # 1x1 on the flattened pixel matrix, M tail
 ]
 
 
