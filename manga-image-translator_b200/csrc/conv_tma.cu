@@ -167,10 +167,36 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             rmask |= 1u << j;
           }
         }
+        // The residual / branch-sum operands of chunk cb+16 are fetched while chunk cb is transposed and stored: the loads
+        // would otherwise sit on the critical path of every 16-column step (short-K layers are epilogue bound).
+        float4 pa0[4], pa1[4];
+        auto fetch_adds = [&](int cb, float4 (&A0)[4], float4 (&A1)[4]) {
+          const int cq = n0 + cb + 4 * sub;
+          const bool vec = cq + 3 < p.Cout;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            A0[j] = make_float4(0.f, 0.f, 0.f, 0.f); A1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!((rmask >> j) & 1u) || cq >= p.Cout) continue;
+            if (p.add0) {
+              const float* s0 = p.add0 + orow[j] * p.add0_cs + p.add0_coff + cq;
+              if (vec) A0[j] = *reinterpret_cast<const float4*>(s0);
+              else { A0[j].x = s0[0]; if (cq + 1 < p.Cout) A0[j].y = s0[1]; if (cq + 2 < p.Cout) A0[j].z = s0[2]; }
+            }
+            if (p.add1) {
+              const float* s1 = p.add1 + orow[j] * p.add1_cs + p.add1_coff + cq;
+              if (vec) A1[j] = *reinterpret_cast<const float4*>(s1);
+              else { A1[j].x = s1[0]; if (cq + 1 < p.Cout) A1[j].y = s1[1]; if (cq + 2 < p.Cout) A1[j].z = s1[2]; }
+            }
+          }
+        };
+        if (p.add0 || p.add1) fetch_adds(cb_lo, pa0, pa1);
 #pragma unroll 1
         for (int cb = cb_lo; cb < cb_hi; cb += 16) {
           uint32_t raw[16];
           tmem_ld16(taddr_row + (uint32_t)cb, raw);
+          float4 na0[4], na1[4];
+          const bool more = cb + 16 < cb_hi;
+          if ((p.add0 || p.add1) && more) fetch_adds(cb + 16, na0, na1);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -192,11 +218,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
               if (!((rmask >> j) & 1u)) continue;
               const float4 a = *reinterpret_cast<const float4*>(st + (rsel + 8 * j) * 20 + 4 * sub);
               float v4[4] = {a.x, a.y, a.z, a.w};
-              if (p.add0) {
-                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add0 + orow[j] * p.add0_cs + p.add0_coff + cq);
-                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
-                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add0[orow[j] * p.add0_cs + p.add0_coff + cq + e]; }
-              }
+              if (p.add0) { v4[0] += pa0[j].x; v4[1] += pa0[j].y; v4[2] += pa0[j].z; v4[3] += pa0[j].w; }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float x = v4[e];
@@ -206,16 +228,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                 if (p.mul1) x *= mu4[e];
                 v4[e] = x;
               }
-              if (p.add1) {
-                if (full) { const float4 tt = *reinterpret_cast<const float4*>(p.add1 + orow[j] * p.add1_cs + p.add1_coff + cq);
-                            v4[0] += tt.x; v4[1] += tt.y; v4[2] += tt.z; v4[3] += tt.w; }
-                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) v4[e] += p.add1[orow[j] * p.add1_cs + p.add1_coff + cq + e]; }
-              }
+              if (p.add1) { v4[0] += pa1[j].x; v4[1] += pa1[j].y; v4[2] += pa1[j].z; v4[3] += pa1[j].w; }
               if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
               else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
             }
           }
           __syncwarp();
+          if (more && (p.add0 || p.add1)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { pa0[j] = na0[j]; pa1[j] = na1[j]; }
+          }
         }
       } else {
         // ---- planar (NCHW) or unaligned output: lane = pixel, so each channel's stores are contiguous across lanes
