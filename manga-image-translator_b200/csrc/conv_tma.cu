@@ -46,6 +46,7 @@ struct TmaParams {
   const float* add1; int add1_cs, add1_coff, add1_planar;
   const float* scale; const float* shift; const float* mul1; int act;
   float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;
+  int dbg;                                                    // development switches (MITB_TMA_DBG): 1 no weight loads, 2 no activation loads
 };
 
 #include "tc_common.cuh"
@@ -315,12 +316,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
           mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
           const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
           const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
-          mbar_arrive_expect_tx(full_bar(s), 2 * a_bytes + 2 * b_bytes);
+          mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 2) ? 0u : 2 * a_bytes) + ((p.dbg & 1) ? 0u : 2 * b_bytes));
           const int x = ox0 * p.sx + p.tdx[tap], y = oy0 * p.sy + p.tdy[tap];
-          tma_load_4d(a_hi, &p.ta_hi, full_bar(s), cb * TC_BK, x, y, nimg);
-          tma_load_4d(a_mid, &p.ta_mid, full_bar(s), cb * TC_BK, x, y, nimg);
-          tma_load_2d(b_hi, &p.tb_hi, full_bar(s), kb * TC_BK, n0);
-          tma_load_2d(b_mid, &p.tb_mid, full_bar(s), kb * TC_BK, n0);
+          if (!(p.dbg & 2)) {
+            tma_load_4d(a_hi, &p.ta_hi, full_bar(s), cb * TC_BK, x, y, nimg);
+            tma_load_4d(a_mid, &p.ta_mid, full_bar(s), cb * TC_BK, x, y, nimg);
+          }
+          if (!(p.dbg & 1)) {
+            tma_load_2d(b_hi, &p.tb_hi, full_bar(s), kb * TC_BK, n0);
+            tma_load_2d(b_mid, &p.tb_mid, full_bar(s), kb * TC_BK, n0);
+          }
           if (++cb == p.cblks) { cb = 0; ++tap; }
         }
       }
@@ -550,6 +555,7 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
   p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MITB_TMA_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;
