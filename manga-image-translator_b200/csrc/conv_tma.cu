@@ -46,7 +46,6 @@ struct TmaParams {
   const float* add1; int add1_cs, add1_coff, add1_planar;
   const float* scale; const float* shift; const float* mul1; int act;
   float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;
-  int dbg;                                                    // development switches (MITB_TMA_DBG): 1 no weight loads, 2 no activation loads
 };
 
 #include "tc_common.cuh"
@@ -54,6 +53,60 @@ struct TmaParams {
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c, int x, int y, int n) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n) : "memory");
+}
+
+// One K block of the bf16x3 product: for each of the four 16-wide k steps Ah*Bh, Ah*Bm, Am*Bh, then tcgen05.commit on the
+// stage's "empty" barrier - issued by one elected lane of a converged warp (operands stay in uniform registers).
+__device__ __forceinline__ void umma_kblock_x3(uint32_t tmem_d, uint64_t dah, uint64_t dam, uint64_t dbh, uint64_t dbm, uint32_t idesc,
+                                               uint32_t acc_first, uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe, pa, pt;\n"
+      ".reg .b64 ah, am, bh, bm;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 pa, %6, 0;\n"
+      "setp.eq.u32 pt, %5, %5;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, pa;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, pt;\n"
+      "add.s64 ah, %1, 2;\n add.s64 am, %2, 2;\n add.s64 bh, %3, 2;\n add.s64 bm, %4, 2;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bm, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], am, bh, %5, pt;\n"
+      "add.s64 ah, %1, 4;\n add.s64 am, %2, 4;\n add.s64 bh, %3, 4;\n add.s64 bm, %4, 4;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bm, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], am, bh, %5, pt;\n"
+      "add.s64 ah, %1, 6;\n add.s64 am, %2, 6;\n add.s64 bh, %3, 6;\n add.s64 bm, %4, 6;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bm, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], am, bh, %5, pt;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+      "}\n" ::"r"(tmem_d), "l"(dah), "l"(dam), "l"(dbh), "l"(dbm), "r"(idesc), "r"(acc_first), "r"(empty_bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar) : "memory");
+}
+// expect_tx + the four operand boxes of one K block, issued by one elected lane of a converged warp
+__device__ __forceinline__ void tma_kblock(uint32_t bar, uint32_t bytes, uint32_t a_hi, uint32_t a_mid, uint32_t b_hi, uint32_t b_mid,
+                                           const CUtensorMap* ta_hi, const CUtensorMap* ta_mid, const CUtensorMap* tb_hi,
+                                           const CUtensorMap* tb_mid, int c, int x, int y, int n, int k, int n0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%6, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%7, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%8, {%14, %15}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%9, {%14, %15}], [%0];\n"
+      "}\n" ::"r"(bar), "r"(bytes), "r"(a_hi), "r"(a_mid), "r"(b_hi), "r"(b_mid), "l"(ta_hi), "l"(ta_mid), "l"(tb_hi), "l"(tb_mid),
+      "r"(c), "r"(x), "r"(y), "r"(n), "r"(k), "r"(n0) : "memory");
 }
 
 template <int ACT>
@@ -274,60 +327,46 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
       if (lane == 0) mbar_arrive(tempty_bar(buf));        // accumulator drained -> the MMA warp may overwrite it
     }
   } else if (warp == TM_MMAWARP) {
-    // =========================== MMA issuer (one elected thread) ===========================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
+    // =========================== MMA issuer ===========================
+    // The whole warp runs the (warp-uniform) loop and one elected lane issues: descriptors and barrier addresses then live in
+    // uniform registers and a K block costs ~40 SASS instructions.  With the loop inside `if (lane == 0)` the compiler
+    // moved every operand of every tcgen05.mma through R2UR/ELECT sequences: ~350 dependent instructions per K block on this
+    // single warp, i.e. ~1400 cycles against the 768-cycle tensor floor of a 128x128x64 bf16x3 block (ncu, r01).
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int s = 0; uint32_t ph = 0; int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_stride;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_stride;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(full_bar(s), (it / S) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
-          const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
-          const uint64_t dah = make_desc_sw128(a_hi), dam = make_desc_sw128(a_mid), dbh = make_desc_sw128(b_hi), dbm = make_desc_sw128(b_mid);
-#pragma unroll
-          for (int j = 0; j < TC_BK / 16; ++j) {
-            const uint64_t adv = (uint64_t)(j * 2);                  // 16 bf16 = 32 bytes = 2 x 16-byte units inside the swizzle row
-            umma_bf16(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-            umma_bf16(tmem_d, dah + adv, dbm + adv, idesc, 1u);
-            umma_bf16(tmem_d, dam + adv, dbh + adv, idesc, 1u);
-          }
-          umma_commit(empty_bar(s));          // frees the stage when the MMAs retire
-        }
-        umma_commit(tfull_bar(buf));          // accumulator of this tile complete -> epilogue
+        const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+        const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+        umma_kblock_x3(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
+                       kb > 0 ? 1u : 0u, empty_bar(s));            // 12 MMAs + commit -> frees the stage when they retire
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
+      umma_commit_elect(tfull_bar(buf));      // accumulator of this tile complete -> epilogue
     }
     __syncwarp();
   } else if (warp == TM_TMAWARP) {
-    // =========================== operand loader: four TMA boxes per K block ===========================
-    if (lane == 0) {
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int nimg, oy0, ox0, n0;
-        decode(t, nimg, oy0, ox0, n0);
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
-          const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
-          const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
-          mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 2) ? 0u : 2 * a_bytes) + ((p.dbg & 1) ? 0u : 2 * b_bytes));
-          const int x = ox0 * p.sx + p.tdx[tap], y = oy0 * p.sy + p.tdy[tap];
-          if (!(p.dbg & 2)) {
-            tma_load_4d(a_hi, &p.ta_hi, full_bar(s), cb * TC_BK, x, y, nimg);
-            tma_load_4d(a_mid, &p.ta_mid, full_bar(s), cb * TC_BK, x, y, nimg);
-          }
-          if (!(p.dbg & 1)) {
-            tma_load_2d(b_hi, &p.tb_hi, full_bar(s), kb * TC_BK, n0);
-            tma_load_2d(b_mid, &p.tb_mid, full_bar(s), kb * TC_BK, n0);
-          }
-          if (++cb == p.cblks) { cb = 0; ++tap; }
-        }
+    // =========================== operand loader: four TMA boxes per K block (whole warp loops, one elected lane issues) =====
+    int s = 0; uint32_t ph = 1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int nimg, oy0, ox0, n0;
+      decode(t, nimg, oy0, ox0, n0);
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(empty_bar(s), ph);
+        const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+        const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+        const int x = ox0 * p.sx + p.tdx[tap], y = oy0 * p.sy + p.tdy[tap];
+        tma_kblock(full_bar(s), 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &p.ta_hi, &p.ta_mid, &p.tb_hi, &p.tb_mid,
+                   cb * TC_BK, x, y, nimg, kb * TC_BK, n0);
+        if (++cb == p.cblks) { cb = 0; ++tap; }
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
     __syncwarp();
@@ -555,7 +594,6 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
   p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MITB_TMA_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;
