@@ -268,7 +268,7 @@ int mitb_op_layernorm(mitb_ctx* ctx, const float* x, int rows, int c, const floa
   API_BEGIN(ctx)
   View in; in.p = const_cast<float*>(x); in.N = 1; in.H = 1; in.W = rows; in.C = c; in.cs = c;
   View out = in; out.p = y;
-  g_launch_counter = &ctx->c.launches;
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;
   launch_layernorm(in, out, w, b, eps, nullptr, nullptr, 1, (cudaStream_t)stream);
   g_launch_counter = nullptr;
   API_END(ctx)
@@ -304,7 +304,7 @@ int mitb_op_irfft2(mitb_ctx* ctx, const float* spec, int c, int h, int w, float*
 
 int mitb_op_attention(mitb_ctx* ctx, const float* qk, const float* v, int n, int t, int heads, int head_dim, float* out, void* stream) {
   API_BEGIN(ctx)
-  g_launch_counter = &ctx->c.launches;
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;
   launch_attention(qk, v, out, n, t, heads, head_dim, (cudaStream_t)stream);
   g_launch_counter = nullptr;
   API_END(ctx)
@@ -312,7 +312,7 @@ int mitb_op_attention(mitb_ctx* ctx, const float* qk, const float* v, int n, int
 
 int mitb_op_bilateral17(mitb_ctx* ctx, const uint8_t* img, int h, int w, uint8_t* out, void* stream) {
   API_BEGIN(ctx)
-  g_launch_counter = &ctx->c.launches;
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;
   launch_bilateral17(img, h, w, out, (cudaStream_t)stream);
   g_launch_counter = nullptr;
   API_END(ctx)

@@ -18,6 +18,7 @@
 namespace mitb {
 
 thread_local long* g_launch_counter = nullptr;
+unsigned long g_launch_epoch = 0;
 
 struct ConvKParams {
   const float* in; int N, H, W, in_cs, in_coff, Cin, in_planar;

@@ -534,7 +534,21 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     CUDA_OK(cudaMalloc(&g_split, g_split_cap * sizeof(uint16_t)));
   }
   uint16_t* hi = g_split; uint16_t* mid = g_split + elems;
-  {
+  // ---- split pass, skipped when the previous kernel launched by this library was a TMA conv over exactly the same input
+  // (the four sub-pixel phases of a transposed conv, sibling convs of one tensor): the scratch still holds its split.
+  // Safe by construction: ANY other launch in between bumps g_launch_epoch, and a conv whose output overlaps the cached
+  // input invalidates the entry.
+  struct SplitKey {
+    const float* in; int N, H, W, C, Cp, cs, coff, planar, Hp, Wp, pt, pl, relu; const float* sc; const float* sh; cudaStream_t st;
+    bool same(const SplitKey& o) const {
+      return in == o.in && N == o.N && H == o.H && W == o.W && C == o.C && Cp == o.Cp && cs == o.cs && coff == o.coff && planar == o.planar &&
+             Hp == o.Hp && Wp == o.Wp && pt == o.pt && pl == o.pl && relu == o.relu && sc == o.sc && sh == o.sh && st == o.st;
+    }
+  };
+  static SplitKey g_key; static bool g_key_valid = false; static unsigned long g_key_epoch = 0; static const uint16_t* g_key_hi = nullptr;
+  const SplitKey key{op.in.p, N, H, W, C, Cp, op.in.cs, op.in.coff, op.in.planar, Hp, Wp, pt, pl, op.in_relu, op.in_scale, op.in_shift, st};
+  const bool reuse = g_key_valid && g_key_epoch == g_launch_epoch && g_key_hi == hi && key.same(g_key);
+  if (!reuse) {
     SplitParams q;
     q.in = op.in.p; q.N = N; q.H = H; q.W = W; q.C = C; q.Cp = Cp; q.cs = op.in.cs; q.coff = op.in.coff; q.planar = op.in.planar;
     q.Hp = Hp; q.Wp = Wp; q.pt = pt; q.pl = pl;
@@ -544,6 +558,14 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
     split_pad_kernel<<<(int)blocks, 256, 0, st>>>(q);
     count_launch();
+  }
+  {
+    // remember this split unless the conv writes into the tensor it was made from
+    const float* ib = op.in.p; const float* ie = ib + (size_t)op.in.N * op.in.H * op.in.W * op.in.cs;
+    const float* ob = op.out.p; const float* oe = ob ? ob + (size_t)op.out.N * op.out.H * op.out.W * op.out.cs : ob;
+    const bool overlap = ob && ob < ie && ib < oe;
+    g_key = key; g_key_hi = hi;
+    g_key_valid = !overlap;            // g_key_epoch is stamped after this conv's own launch, below
   }
 
   static int num_sms = 0;
@@ -613,6 +635,7 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     default: conv_tma_kernel<-1><<<grid, TM_THREADS, smem, st>>>(p); break;
   }
   count_launch();
+  g_key_epoch = g_launch_epoch;
   CUDA_OK(cudaGetLastError());
 }
 

@@ -48,7 +48,7 @@ void run_with_workspace(Ctx& ctx, cudaStream_t st, F body) {
   ws.dry = false; ws.off = 0;
   ctx.ensure_ws(need);
   ws.peak = 0;
-  g_launch_counter = &ctx.launches; g_prof = &ctx.prof;
+  g_launch_counter = &ctx.launches; g_prof = &ctx.prof; ++g_launch_epoch;   /* new API call: inputs may have been rewritten by the host */
   { Exec e{ctx, st, false}; body(e); }
   g_launch_counter = nullptr; g_prof = nullptr;
 }

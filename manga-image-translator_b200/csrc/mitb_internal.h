@@ -210,6 +210,7 @@ struct Ctx {
   void ensure_ws(size_t bytes);
 };
 extern thread_local long* g_launch_counter;
-inline void count_launch() { if (g_launch_counter) ++*g_launch_counter; }
+extern unsigned long g_launch_epoch;     // bumped by EVERY kernel launch of the library (conv_tma.cu's split reuse keys on it)
+inline void count_launch() { ++g_launch_epoch; if (g_launch_counter) ++*g_launch_counter; }
 
 }  // namespace mitb
