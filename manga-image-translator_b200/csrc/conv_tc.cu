@@ -634,15 +634,21 @@ bool conv_tc_supported(const ConvOp& op) {
 bool conv_tma_supported(const ConvOp& op);     // conv_tma.cu
 void launch_conv_tma(const ConvOp& op, cudaStream_t st);
 
+static bool tma_dispatch(const ConvOp& op) {
+  if (!conv_tma_supported(op)) return false;
+  // TMA-fed kernel unless the layer is so small that it needs split-K
+  static int sms = 0;
+  if (!sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+  const long Mrows = (long)op.in.N * op.Ho * op.Wo;
+  const long tiles = ((Mrows + TC_BM - 1) / TC_BM) * (op.tc_npad / op.tc_bn);
+  const bool would_split = !op.stat_max && tiles * 2 <= sms && op.tc_kpad / TC_BK >= 16;
+  return !would_split;
+}
+bool conv_uses_tma(const ConvOp& op) { return op.out.C > 4 && conv_tc_supported(op) && tma_dispatch(op); }
+
 void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
-  if (conv_tma_supported(op)) {
-    // TMA-fed kernel for stride-1 convs with Cin % 64 == 0, unless the layer is so small that it needs split-K
-    int sms = 0, dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long Mrows = (long)op.in.N * op.Ho * op.Wo;
-    const long tiles = ((Mrows + TC_BM - 1) / TC_BM) * (op.tc_npad / op.tc_bn);
-    const bool would_split = !op.stat_max && tiles * 2 <= sms && op.tc_kpad / TC_BK >= 16;
-    if (!would_split) { launch_conv_tma(op, st); return; }
-  }
+  if (tma_dispatch(op)) { launch_conv_tma(op, st); return; }
+  MITB_CHECK(!op.in_split && !op.out_split, "conv: split-fused ops must run on the TMA path");
   TcParams p;
   p.in = op.in.p; p.N = op.in.N; p.H = op.in.H; p.W = op.in.W; p.in_cs = op.in.cs; p.in_coff = op.in.coff; p.Cin = op.in.C;
   p.in_planar = op.in.planar;

@@ -46,6 +46,7 @@ struct TmaParams {
   const float* add1; int add1_cs, add1_coff, add1_planar;
   const float* scale; const float* shift; const float* mul1; int act;
   float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;
+  uint16_t* os_hi; uint16_t* os_mid;                          // out_split: bf16 hi / mid destinations [pixels][Cout] (else null)
 };
 
 #include "tc_common.cuh"
@@ -283,7 +284,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                 v4[e] = x;
               }
               if (p.add1) { v4[0] += pa1[j].x; v4[1] += pa1[j].y; v4[2] += pa1[j].z; v4[3] += pa1[j].w; }
-              if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+              if (p.os_hi) {                         // conv -> conv fusion: store the consumer's bf16 hi / mid operands directly
+                uint2 hh, mm;
+                split4(make_float4(v4[0], v4[1], v4[2], v4[3]), hh, mm);
+                *reinterpret_cast<uint2*>(p.os_hi + orow[j] * p.Cout + cq) = hh;
+                *reinterpret_cast<uint2*>(p.os_mid + orow[j] * p.Cout + cq) = mm;
+              } else if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
               else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
             }
           }
@@ -534,6 +540,12 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     CUDA_OK(cudaMalloc(&g_split, g_split_cap * sizeof(uint16_t)));
   }
   uint16_t* hi = g_split; uint16_t* mid = g_split + elems;
+  if (op.in_split) {
+    // the producer conv already stored bf16 hi | mid into the bytes of this fp32 view (ConvOp::out_split)
+    MITB_CHECK(!padded_w && pt == 0 && pl == 0 && pb == 0 && pr == 0 && !op.in.planar && op.in.cs == C && op.in.coff == 0 && !op.in_scale,
+               "tma conv: in_split needs a dense NHWC input without halo or prologue");
+    hi = reinterpret_cast<uint16_t*>(const_cast<float*>(op.in.p)); mid = hi + elems;
+  }
   // ---- split pass, skipped when the previous kernel launched by this library was a TMA conv over exactly the same input
   // (the four sub-pixel phases of a transposed conv, sibling convs of one tensor): the scratch still holds its split.
   // Safe by construction: ANY other launch in between bumps g_launch_epoch, and a conv whose output overlaps the cached
@@ -548,7 +560,7 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   static SplitKey g_key; static bool g_key_valid = false; static unsigned long g_key_epoch = 0; static const uint16_t* g_key_hi = nullptr;
   const SplitKey key{op.in.p, N, H, W, C, Cp, op.in.cs, op.in.coff, op.in.planar, Hp, Wp, pt, pl, op.in_relu, op.in_scale, op.in_shift, st};
   const bool reuse = g_key_valid && g_key_epoch == g_launch_epoch && g_key_hi == hi && key.same(g_key);
-  if (!reuse) {
+  if (!reuse && !op.in_split) {
     SplitParams q;
     q.in = op.in.p; q.N = N; q.H = H; q.W = W; q.C = C; q.Cp = Cp; q.cs = op.in.cs; q.coff = op.in.coff; q.planar = op.in.planar;
     q.Hp = Hp; q.Wp = Wp; q.pt = pt; q.pl = pl;
@@ -565,7 +577,7 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     const float* ob = op.out.p; const float* oe = ob ? ob + (size_t)op.out.N * op.out.H * op.out.W * op.out.cs : ob;
     const bool overlap = ob && ob < ie && ib < oe;
     g_key = key; g_key_hi = hi;
-    g_key_valid = !overlap;            // g_key_epoch is stamped after this conv's own launch, below
+    g_key_valid = !overlap && !op.in_split;            // g_key_epoch is stamped after this conv's own launch, below
   }
 
   static int num_sms = 0;
@@ -616,6 +628,15 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
   p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
+  if (op.out_split) {
+    MITB_CHECK(!op.out.planar && op.out.cs == op.out.C && op.out.coff == 0 && op.out.C % 4 == 0 && !op.stat_max && op.oy_mul == 1 &&
+               op.ox_mul == 1 && op.oy_add == 0 && op.ox_add == 0 && op.out.H == op.Ho && op.out.W == op.Wo &&
+               (!op.add0.p || (!op.add0.planar && ((op.add0.cs | op.add0.coff) & 3) == 0)) &&
+               (!op.add1.p || (!op.add1.planar && ((op.add1.cs | op.add1.coff) & 3) == 0)),
+               "tma conv: out_split needs a dense NHWC output on the conv's own pixel grid");
+    p.os_hi = reinterpret_cast<uint16_t*>(op.out.p);
+    p.os_mid = p.os_hi + (size_t)op.out.N * op.out.H * op.out.W * op.out.C;
+  }
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;

@@ -122,13 +122,18 @@ static void run_block(Exec& e, const CnBlock& b, const View& x, const View& out)
     e.dwconv7_ln(x, t, b.dw_w, b.dw_b, b.ln_w, b.ln_b, kLnEps);
   }
   View hid = ws.view(x.N, x.H, x.W, 4 * b.cout);
-  { ConvOp op = Exec::op_from(b.fc1, t, hid); op.act = ACT_GELU; e.conv(op); }
   View sc = x;
   if (b.has_sc) {
     sc = ws.view(x.N, x.H, x.W, b.cout);
     ConvOp op = Exec::op_from(b.sc, x, sc); e.conv(op);
   }
-  { ConvOp op = Exec::op_from(b.fc2, hid, out); op.mul1 = b.gamma; op.add1 = sc; e.conv(op); }
+  ConvOp op1 = Exec::op_from(b.fc1, t, hid); op1.act = ACT_GELU;
+  ConvOp op2 = Exec::op_from(b.fc2, hid, out); op2.mul1 = b.gamma; op2.add1 = sc;
+  // fc1 -> GELU -> fc2: when both run on the TMA-fed kernel, fc1 stores fc2's bf16 hi/mid operands straight into `hid`
+  // (same bytes as the fp32 tensor it replaces) and fc2 skips its split pass
+  if (!e.dry && conv_uses_tma(op1) && conv_uses_tma(op2)) { op1.out_split = true; op2.in_split = true; }
+  e.conv(op1);
+  e.conv(op2);
   ws.release(mk);
 }
 

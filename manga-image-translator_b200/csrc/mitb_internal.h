@@ -79,11 +79,16 @@ struct ConvOp {
   TmaDesc tmh, tmm;                   // TMA descriptors of wh / wm
   // per-tap channel-padded copies [tc_npad][ntaps*tc_cp] for the TMA-fed kernel when Cin % 64 != 0 (null otherwise)
   const uint16_t* whp = nullptr; const uint16_t* wmp = nullptr; int tc_cp = 0;
+  // TMA-path fusion of a conv -> conv pair (ConvNeXt fc1 -> fc2): the producer's epilogue stores bf16 hi | mid halves INTO the
+  // bytes of its fp32 output buffer (same size), the consumer reads them as its pre-split input and skips the split pass.
+  // Only legal when conv_uses_tma() holds for the op; dense NHWC views (cs == C, coff == 0), 1x1 consumer.
+  bool out_split = false, in_split = false;
   // optional fused row statistics (vocabulary head): no tensor output, per (row, column-block) partials
   float* stat_max = nullptr; float* stat_sum = nullptr; int* stat_idx = nullptr; int stat_ld = 0;
 };
 
 void launch_conv(const ConvOp& op, cudaStream_t st);
+bool conv_uses_tma(const ConvOp& op);      // true when launch_conv() will run this op on the TMA-fed tensor-core kernel
 int conv_stat_blocks(const ConvOp& op);   // number of column blocks the row-stat epilogue writes per row
 void launch_rowstat_final(const float* pmax, const float* psum, const int* pidx, int rows, int nblk,
                           int* idx, float* logprob, cudaStream_t st);
