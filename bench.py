@@ -257,8 +257,20 @@ def run_ours(args, rank, world, local_rank):
             achieved, peak, unit = top["flops"] / sec / 1e12, peaks["tf_sust"], "TFLOP/s"
         else:
             achieved, peak, unit = top["bytes"] / sec / 1e9, peaks["hbm"], "GB/s"
+        # DRAM traffic of the dominant class from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum summed over the
+        # class's kernels of one page, cold caches), per launch like `achieved`; null if that summary is not in the tree
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_v13.json")
+        if tensor_bound and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            per_page = top["launches"] / max(1, args.steps * n_pages)
+            traffic = tj["conv_class_dram_bytes_per_page"] / max(1.0, per_page)
+            traffic_src = "profiles/r01_ncu_traffic_v13.json (ncu, one page, cold cache; includes the split pass of each conv)"
         roof = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": None, "peak_source": peaks["src"] + (" bf16 sustained" if tensor_bound else " copy"),
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
+                "algorithmic_flops_per_launch": top["flops"] / max(1, top["launches"]),
+                "scheme_ceiling_frac": 1.0 / 3.0 if tensor_bound else 1.0, "peak_source": peaks["src"] + (" bf16 sustained" if tensor_bound else " copy"),
                 "launches": top["launches"], "avg_launch_ms": top["ms"] / max(1, top["launches"]),
                 "share_of_kernel_time": top["ms"] / total_kernel_ms,
                 "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
