@@ -153,6 +153,42 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def roofline_from_profile(prof, peaks, pages_timed):
+    """`roofline` object of the JSON line from the per-class profile {class: {launches, ms, flops, bytes}} that the library
+    recorded with CUDA events around every launch of the timed region (`pages_timed` pages on this rank)."""
+    if not prof:
+        return None
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    sec = top["ms"] / 1e3
+    tensor_bound = name.startswith("conv")
+    if tensor_bound:
+        achieved, peak, unit = top["flops"] / sec / 1e12, peaks["tf_sust"], "TFLOP/s"
+    else:
+        achieved, peak, unit = top["bytes"] / sec / 1e9, peaks["hbm"], "GB/s"
+    # DRAM traffic of the dominant class from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum summed over the
+    # class's kernels of one page, cold caches), per launch like `achieved`; null if that summary is not in the tree
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_v13.json")
+    if tensor_bound and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        per_page = top["launches"] / max(1, pages_timed)
+        traffic = tj["conv_class_dram_bytes_per_page"] / max(1.0, per_page)
+        traffic_src = "profiles/r01_ncu_traffic_v13.json (ncu, one page, cold cache; includes the split pass of each conv)"
+    return {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
+            "algorithmic_flops_per_launch": top["flops"] / max(1, top["launches"]),
+            "scheme_ceiling_frac": 1.0 / 3.0 if tensor_bound else 1.0,
+            "peak_source": peaks["src"] + (" bf16 sustained" if tensor_bound else " copy"),
+            "launches": top["launches"], "avg_launch_ms": top["ms"] / max(1, top["launches"]),
+            "share_of_kernel_time": top["ms"] / total_kernel_ms,
+            "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                            "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                            "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from mit_b200 import synth
@@ -246,36 +282,7 @@ def run_ours(args, rank, world, local_rank):
     h2d, d2h = eng.h2d_bytes / args.steps, eng.d2h_bytes / args.steps
 
     # ---------------- roofline of the dominant kernel class (CUDA events recorded per launch during the timed region)
-    peaks = load_peaks()
-    roof = None
-    if prof:
-        total_kernel_ms = sum(v["ms"] for v in prof.values())
-        name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-        sec = top["ms"] / 1e3
-        tensor_bound = name.startswith("conv")
-        if tensor_bound:
-            achieved, peak, unit = top["flops"] / sec / 1e12, peaks["tf_sust"], "TFLOP/s"
-        else:
-            achieved, peak, unit = top["bytes"] / sec / 1e9, peaks["hbm"], "GB/s"
-        # DRAM traffic of the dominant class from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum summed over the
-        # class's kernels of one page, cold caches), per launch like `achieved`; null if that summary is not in the tree
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_v13.json")
-        if tensor_bound and os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            per_page = top["launches"] / max(1, args.steps * n_pages)
-            traffic = tj["conv_class_dram_bytes_per_page"] / max(1.0, per_page)
-            traffic_src = "profiles/r01_ncu_traffic_v13.json (ncu, one page, cold cache; includes the split pass of each conv)"
-        roof = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
-                "algorithmic_flops_per_launch": top["flops"] / max(1, top["launches"]),
-                "scheme_ceiling_frac": 1.0 / 3.0 if tensor_bound else 1.0, "peak_source": peaks["src"] + (" bf16 sustained" if tensor_bound else " copy"),
-                "launches": top["launches"], "avg_launch_ms": top["ms"] / max(1, top["launches"]),
-                "share_of_kernel_time": top["ms"] / total_kernel_ms,
-                "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
-                                "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
-                                "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+    roof = roofline_from_profile(prof, load_peaks(), args.steps * n_pages)
 
     # ---------------- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
     cpu = None

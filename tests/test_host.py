@@ -170,3 +170,20 @@ def test_detector_helpers_match_reference():
     for size in (512, 256, 300):
         a, b = det_post.resize_aspect_ratio(img, size, cv2.INTER_LINEAR), ip.resize_aspect_ratio(img, size, cv2.INTER_LINEAR, mag_ratio=1)
         assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+
+
+def test_bench_roofline_object_from_profile():
+    """bench.py's roofline block is pure host code: feed it the per-class profile of a recorded run."""
+    import json as _json
+    import os as _os
+    import bench
+    prof = _json.loads(open(_os.path.join(bench.ROOT, "profiles", "r01_layers_tma_v13.txt")).read().strip().splitlines()[-1])
+    peaks = bench.load_peaks()
+    roof = bench.roofline_from_profile(prof, peaks, 1)
+    assert roof["kernel"] == "conv_tc" and roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s"
+    assert 0.0 < roof["frac"] < 1.0 / 3.0 + 1e-6                       # bf16x3 cannot exceed a third of the bf16 peak
+    assert abs(roof["achieved"] * 1e12 * prof["conv_tc"]["ms"] / 1e3 - prof["conv_tc"]["flops"]) < 1e-3 * prof["conv_tc"]["flops"]
+    assert roof["traffic"] is None or roof["traffic"] > roof["algorithmic_bytes_per_launch"] * 0.5
+    assert set(roof["classes"]) == set(prof)
+    assert bench.roofline_from_profile({}, peaks, 1) is None
+    _json.dumps(roof)
