@@ -1,23 +1,28 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a.
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a, register-gather variant.
 //
 // Same contract as the SIMT kernel in conv_simt.cu (tap list, zero/reflect padding, strided output mapping for the
-// transposed-conv phases, BN+ReLU prologue, fused epilogue), but the contraction runs on the tensor cores:
+// transposed-conv phases, BN+ReLU prologue, fused epilogue), contraction on the tensor cores.  Since r01 the main path is
+// conv_tma.cu (activations split once, every operand by TMA); this kernel keeps the layers that one does not take: inputs
+// whose channel count is not a multiple of 8 (Cin = 4 stems) and tiny-M / huge-K decoder layers that need split-K.
 //
-//   * 128-pixel x BN-channel output tile per CTA, accumulator in TMEM (128 lanes x BN fp32 columns).
+//   * 128-pixel x BN-channel output tile per CTA, accumulator in TMEM (128 lanes x BN fp32 columns, double buffered).
 //   * fp32 accuracy from bf16 tensor cores by operand splitting ("bf16x3"): x = hi + mid with hi = bf16(x),
 //     mid = bf16(x - hi); D += A_hi*B_hi + A_hi*B_mid + A_mid*B_hi.  The dropped terms are <= ~3*2^-18 relative
 //     (about 1e-5), far inside the 1e-3 parity budget, at 1/3 of the bf16 tensor rate (2x a 3xTF32 scheme).
-//   * K is consumed in blocks of 64 (one 128-byte swizzle row of bf16).  Warp-specialised:
-//       warps 0-7  gather the activation tile from the NHWC (or planar) view (two threads per GEMM row, register
-//                  prefetch of the next K block), apply the optional BN+ReLU prologue, split hi/mid and store both
-//                  tiles into shared memory in the UMMA K-major SWIZZLE_128B layout;
+//   * K is consumed in blocks of 64 (one 128-byte swizzle row of bf16).  Warp-specialised, 320 threads (168 registers: the
+//     register file is partitioned per SM sub-partition, three warps of 168 x 32 fit in its 16 K registers):
+//       warps 0-7  two ping-pong groups of 128 threads gather alternate K blocks of the activation tile from the NHWC view
+//                  (thread = one float4 column of 16 rows: a warp load covers two complete 256-byte row segments), apply the
+//                  optional BN+ReLU prologue, split hi/mid and store both tiles in the UMMA K-major SWIZZLE_128B layout;
+//                  planar (NCHW) inputs use a row-per-thread gather that is coalesced along pixels.  After the last K
+//                  block the same warps run the epilogue (tcgen05.ld, shared-memory transpose, (+add0)*scale+shift -> act ->
+//                  *mul1 -> +add1, coalesced fp32 stores, or row-stat / split-K partials);
 //       warp  9    one thread streams the pre-split K-major bf16 weight tiles (hi/mid) with TMA (cp.async.bulk.tensor,
 //                  128B swizzle) straight into the stage, completing on the stage's "full" mbarrier (expect_tx);
-//       warp  8    one elected thread issues tcgen05.mma (12 per K block) and commits to the stage's "empty" mbarrier;
+//       warp  8    one thread issues tcgen05.mma (12 per K block) and commits to the stage's "empty" mbarrier;
 //     full/empty mbarrier ring, producers signal after fence.proxy.async (generic-proxy stores -> async-proxy reads).
-//   * Persistent: one CTA per SM loops over output tiles; the accumulator is double-buffered in TMEM (2 x BN columns) so
-//     the epilogue of tile i (4 dedicated warps: tcgen05.ld, (+add0)*scale+shift -> act -> *mul1 -> +add1, fp32 stores)
-//     overlaps the MMAs of tile i+1; TMEM alloc / barrier init / descriptor fetch are paid once per SM.
+//   * Persistent: one CTA per SM loops over output tiles; split-K (splitk_reduce_kernel) when tiles cannot fill the SMs.
+//   Measured limit (profiles/r01_tc_skeleton_experiments.txt): the producers' own instruction stream, ~160 TF/s.
 #include <cuda.h>
 #include <string.h>
 #include <cuda_bf16.h>

@@ -1,4 +1,4 @@
-// TMA-fed tcgen05 implicit-GEMM convolution for sm_100a (stride-1 convs whose Cin is a multiple of 64).
+// TMA-fed tcgen05 implicit-GEMM convolution for sm_100a (stride 1 or 2, Cin a multiple of 8; the main conv path).
 //
 // conv_tc.cu gathers the fp32 activation tile with producer warps and splits it into bf16 hi/mid inside the main loop.
 // Measured on B200 that loop is bound by the producers' own instruction stream (~650 dependent instructions per K block per
