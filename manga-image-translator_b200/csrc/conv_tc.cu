@@ -712,12 +712,8 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   p.splits = splits; p.partial = nullptr;
   if (splits > 1) {
     const size_t need = (size_t)splits * p.M * p.npad * sizeof(float);
-    static float* g_partial = nullptr; static size_t g_partial_cap = 0;      // grow-only scratch, one per process
-    if (need > g_partial_cap) {
-      if (g_partial) CUDA_OK(cudaFree(g_partial));
-      CUDA_OK(cudaMalloc(&g_partial, need)); g_partial_cap = need;
-    }
-    p.partial = g_partial;
+    static DeviceScratch g_partial;                                           // split-K partial sums
+    p.partial = static_cast<float*>(g_partial.get(need));
   }
   const int total_tiles = tiles * splits;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;      // persistent: one CTA per SM

@@ -533,13 +533,8 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   }
   const int Hp = H + pt + pb, Wp = W + pl + pr;
   const size_t elems = (size_t)N * Hp * Wp * Cp;
-  static uint16_t* g_split = nullptr; static size_t g_split_cap = 0;      // grow-only scratch (hi | mid), one per process
-  if (2 * elems > g_split_cap) {
-    if (g_split) { CUDA_OK(cudaDeviceSynchronize()); CUDA_OK(cudaFree(g_split)); }
-    g_split_cap = 2 * elems + (2 * elems) / 8;
-    CUDA_OK(cudaMalloc(&g_split, g_split_cap * sizeof(uint16_t)));
-  }
-  uint16_t* hi = g_split; uint16_t* mid = g_split + elems;
+  static DeviceScratch g_split;                                             // bf16 hi | mid of the current conv's input
+  uint16_t* hi = static_cast<uint16_t*>(g_split.get(2 * elems * sizeof(uint16_t))); uint16_t* mid = hi + elems;
   if (op.in_split) {
     // the producer conv already stored bf16 hi | mid into the bytes of this fp32 view (ConvOp::out_split)
     MITB_CHECK(!padded_w && pt == 0 && pl == 0 && pb == 0 && pr == 0 && !op.in.planar && op.in.cs == C && op.in.coff == 0 && !op.in_scale,

@@ -215,6 +215,24 @@ struct Ctx {
   void ensure_ws(size_t bytes);
 };
 extern thread_local long* g_launch_counter;
+// Grow-only device scratch, one buffer per (purpose, device).  The library runs one context per device (one process per GPU,
+// get_engine() is a per-device singleton) and every kernel that uses a scratch is ordered on that context's stream; growing
+// synchronises the device before the old buffer is released.
+struct DeviceScratch {
+  static constexpr int kMaxDev = 64;
+  void* ptr[kMaxDev] = {}; size_t cap[kMaxDev] = {};
+  void* get(size_t bytes) {
+    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+    MITB_CHECK(dev >= 0 && dev < kMaxDev, "device ordinal %d out of range", dev);
+    if (bytes > cap[dev]) {
+      if (ptr[dev]) { CUDA_OK(cudaDeviceSynchronize()); CUDA_OK(cudaFree(ptr[dev])); ptr[dev] = nullptr; cap[dev] = 0; }
+      const size_t want = bytes + bytes / 8;
+      CUDA_OK(cudaMalloc(&ptr[dev], want)); cap[dev] = want;
+    }
+    return ptr[dev];
+  }
+};
+
 extern unsigned long g_launch_epoch;     // bumped by EVERY kernel launch of the library (conv_tma.cu's split reuse keys on it)
 inline void count_launch() { ++g_launch_epoch; if (g_launch_counter) ++*g_launch_counter; }
 
