@@ -187,3 +187,29 @@ def test_bench_roofline_object_from_profile():
     assert set(roof["classes"]) == set(prof)
     assert bench.roofline_from_profile({}, peaks, 1) is None
     _json.dumps(roof)
+
+
+def test_host_logic_on_empty_and_degenerate_inputs():
+    """Edge cases of the host glue: empty detector map, no text lines, all-blank and all-repeat CTC rows, empty shards."""
+    import numpy as np
+    from mit_b200 import plugins, synth
+    from mit_b200.host import det_post, geometry
+    from mit_b200.pipeline import shard_indices
+    # nothing above threshold -> no boxes, no polygons
+    boxes, scores = det_post.boxes_from_prob(np.zeros((64, 48), np.float32), 0.5, 0.7, 2.3, 48, 64)
+    assert len(boxes) == 0 and len(scores) == 0
+    assert len(det_post.polys_from_boxes(boxes, scores, 1.0, 1.0)) == 0
+    # a single saturated blob still yields exactly one box
+    prob = np.zeros((64, 96), np.float32); prob[20:40, 10:80] = 0.99
+    boxes, scores = det_post.boxes_from_prob(prob, 0.5, 0.7, 2.3, 96, 64)
+    assert len(boxes) == 1 and scores[0] > 0.9
+    # direction graph / quads of nothing
+    assert geometry.generate_text_direction([]) == [] or list(geometry.generate_text_direction([])) == []
+    assert len(synth.make_quads([])) == 0
+    # CTC collapse: all blank, all the same symbol, alternating with blanks
+    idx = np.array([[0, 0, 0, 0], [5, 5, 5, 5], [5, 0, 5, 0], [1, 2, 2, 3]], np.int64)
+    kept = plugins.ctc_collapse(idx)
+    assert [k.tolist() for k in kept] == [[], [0], [0, 2], [0, 1, 3]]
+    # sharding more ranks than pages leaves some ranks empty, never duplicates or drops a page
+    parts = [list(shard_indices(3, r, 8)) for r in range(8)]
+    assert sorted(sum(parts, [])) == [0, 1, 2] and sum(1 for p in parts if not p) == 5
