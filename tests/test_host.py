@@ -213,3 +213,24 @@ def test_host_logic_on_empty_and_degenerate_inputs():
     # sharding more ranks than pages leaves some ranks empty, never duplicates or drops a page
     parts = [list(shard_indices(3, r, 8)) for r in range(8)]
     assert sorted(sum(parts, [])) == [0, 1, 2] and sum(1 for p in parts if not p) == 5
+
+
+def test_bench_lama_ffc_figure_from_recorded_launches():
+    """The LaMa FFC block figure of the bench line, computed from a recorded per-layer table (profiles/r01_layers_tma_v13.txt)."""
+    import json as _json
+    import os as _os
+    import bench
+    lines = open(_os.path.join(bench.ROOT, "profiles", "r01_layers_tma_v13.txt")).read().strip().splitlines()
+    prof = _json.loads(lines[-1])
+    launches = []
+    for ln in lines[2:-1]:
+        f = ln.split()
+        if len(f) == 7 and f[0].startswith("conv"):
+            kind, m, k, n, cnt, ms = f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), float(f[5])
+            launches += [[kind, m, k, n, ms / cnt]] * cnt
+    fig = bench.ffc_block_from_launches(launches, prof, 1, bench.load_peaks())
+    assert fig is not None and abs(fig["layers_timed"] - 18) < 1e-9          # 9 blocks x 2 FFC layers per LaMa-MPE page
+    assert 300 < fig["us_per_layer"] < 3000 and 0 < fig["hbm_frac"] < 1 and 0 < fig["tensor_frac"] < 1.0 / 3.0
+    assert fig["binding_term"] == "tensor"                                    # SURVEY 8d: the fused block is tensor bound
+    assert bench.ffc_block_from_launches([], prof, 1, bench.load_peaks()) is None
+    _json.dumps(fig)
