@@ -173,6 +173,38 @@ class Quadrilateral:
     def poly_distance(self, other) -> float:
         return polygon_distance(_hull(self.pts), _hull(other.pts))
 
+    @functools.cached_property
+    def centroid(self) -> np.ndarray:
+        return np.average(self.pts, axis=0)
+
+    def distance(self, other: "Quadrilateral", rho: float = 0.5) -> float:
+        """Reading-order distance between two lines (generic.py:543-596): distance of the line starts (or ends / middles) when
+        the quadrilateral spanned by the corresponding edges is thin relative to the font size, chosen per assigned direction."""
+        fs = max(self.font_size, other.font_size)
+
+        def d(p, q):
+            return float(np.hypot(float(p[0]) - float(q[0]), float(p[1]) - float(q[1])))
+
+        if self.assigned_direction == "h":
+            d1 = hull_area([self.pts[0], self.pts[3], other.pts[0], other.pts[3]]) / fs
+            d2 = hull_area([self.pts[2], self.pts[1], other.pts[2], other.pts[1]]) / fs
+            d3 = hull_area([self.structure[0], self.structure[1], other.structure[0], other.structure[1]]) / fs
+            pattern = "left"
+            if d2 < fs * rho and d2 < d1:
+                pattern = "right"
+            if d3 < fs * rho and d3 < d1 and d3 < d2:
+                pattern = "middle"
+            if pattern == "left":
+                return d(self.pts[0], other.pts[0])
+            if pattern == "right":
+                return d(self.pts[1], other.pts[1])
+            return d(self.structure[0], other.structure[0])
+        d1 = hull_area([self.pts[0], self.pts[1], other.pts[0], other.pts[1]]) / fs
+        d2 = hull_area([self.pts[2], self.pts[3], other.pts[2], other.pts[3]]) / fs
+        if d2 < fs * rho and d2 < d1:
+            return d(self.pts[2], other.pts[2])
+        return d(self.pts[0], other.pts[0])
+
     def clip(self, width, height):
         self.pts[:, 0] = np.clip(np.round(self.pts[:, 0]), 0, width)
         self.pts[:, 1] = np.clip(np.round(self.pts[:, 1]), 0, height)
