@@ -72,7 +72,9 @@ def boxes_from_prob(prob: np.ndarray, thresh: float, box_thresh: float, unclip_r
     """SegDetectorRepresenter.boxes_from_bitmap (dbnet_utils.py:96-144): rows of rejected contours stay all-zero."""
     bitmap = prob > thresh
     h, w = bitmap.shape
-    contours, _ = cv2.findContours((bitmap * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    # findContours treats every non-zero pixel as 1: the bool map viewed as u8 gives the contours of (bitmap*255) without
+    # materialising an int64 page (10 ms on 2048x1536)
+    contours, _ = cv2.findContours(np.ascontiguousarray(bitmap).view(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
     n = min(len(contours), max_candidates)
     boxes = np.zeros((n, 4, 2), dtype=np.int64)
     scores = np.zeros((n,), dtype=np.float32)

@@ -22,8 +22,15 @@ def _grow(known: np.ndarray, kernel: np.ndarray) -> np.ndarray:
 def mpe_tables_256(mask01: np.ndarray):
     """The tables at the 256x256 working resolution (before the reference's INTER_NEAREST upsampling, which libmitb does on
     the device): (rel_pos int32 [256,256] in [0,127], direct int32 [256,256,4])."""
-    m = (np.asarray(mask01, dtype=np.float32) * 255).astype(np.uint8)
-    return _tables_256(m)
+    return _tables_256(_mask_u8(mask01))
+
+
+def _mask_u8(mask01) -> np.ndarray:
+    """(mask*255).astype(u8) of the reference; integer/bool masks take a u8-only path (no float page)."""
+    a = np.asarray(mask01)
+    if a.dtype == np.bool_ or (a.dtype.kind in "iu" and a.size and int(a.max()) <= 1 and int(a.min()) >= 0):
+        return a.astype(np.uint8) * np.uint8(255)
+    return (a.astype(np.float32) * 255).astype(np.uint8)
 
 
 def _tables_256(m: np.ndarray):
@@ -47,7 +54,7 @@ def _tables_256(m: np.ndarray):
 
 def mpe_tables(mask01: np.ndarray):
     """mask01 [H,W] with 1 inside the hole -> (rel_pos int32 [H,W] in [0,127], direct int32 [H,W,4] in {0,1})."""
-    m = (np.asarray(mask01, dtype=np.float32) * 255).astype(np.uint8)
+    m = _mask_u8(mask01)
     H, W = m.shape
     rel, direct = _tables_256(m)
     if (H, W) != (256, 256):

@@ -239,12 +239,8 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
 
     async def _infer(self, image: np.ndarray, mask: np.ndarray, config: InpainterConfig, inpainting_size: int = 1024,
                      verbose: bool = False) -> np.ndarray:
-        img_original = np.copy(image)
-        mask_original = np.copy(mask)
-        mask_original[mask_original < 127] = 0
-        mask_original[mask_original >= 127] = 1
-        mask_original = mask_original[:, :, None]
-        height, width, _ = image.shape
+        img_original, mask_full = image, mask          # inputs are borrowed: never written; the host composite below (only taken
+        height, width, _ = image.shape                 # when the page had to be resized) derives its own {0,1} mask from them
         if max(image.shape[0:2]) > inpainting_size:
             r = float(inpainting_size) / max(image.shape[0], image.shape[1])
             size = (round(image.shape[1] * r), round(image.shape[0] * r))
@@ -262,7 +258,10 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
         rel_pos = direct = None
         if self._USE_MPE:
             # 256x256 tables on the host (binary morphology on a tiny image); upsampled inside the kernel
-            mask01 = ((mask.astype(np.float32) / 255.0) >= 0.5).astype(np.float32)
+            if mask.dtype == np.uint8:
+                mask01 = mask >= 128                   # == (mask / 255 >= 0.5) for uint8: 127/255 < 0.5 <= 128/255
+            else:
+                mask01 = ((mask.astype(np.float32) / 255.0) >= 0.5).astype(np.float32)
             rel_pos, direct = mpe.mpe_tables_256(mask01)
             rel_pos, direct = eng.h2d(rel_pos[None]), eng.h2d(direct[None])
         # /255, mask binarisation, pre-masking, network, blend, (x*255) truncation and (when no resize happened) the final
@@ -274,6 +273,7 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
             return img_inpainted
         if new_h != height or new_w != width:
             img_inpainted = cv2.resize(img_inpainted, (width, height), interpolation=cv2.INTER_LINEAR)
+        mask_original = (mask_full >= 127).astype(mask_full.dtype)[:, :, None]        # inpainting_lama_mpe.py:59-60
         return img_inpainted * mask_original + img_original * (1 - mask_original)
 
 
