@@ -194,14 +194,14 @@ class Model48pxCTCOCR(_InjectableWeights, OfflineOCR):
                     continue
                 chars = [self.dictionary[c] for c in pred[i, steps]]
                 chars = [" " if ch == "<SP>" else ch for ch in chars]
-                prob = np.exp(np.mean([float(v) for v in logprob[i, steps]]))
+                prob = np.exp(np.mean(logprob[i, steps].astype(np.float64)))          # mean of python floats == float64 mean
                 if prob < threshold:
                     continue
                 txt = "".join(chars)
                 sel = [s for s, ch in zip(steps, chars) if ch != " "]
                 cols = [0] * 6
                 if sel:
-                    ints = np.array([[int(float(v) * 255) for v in colors[i, s]] for s in sel])
+                    ints = (colors[i, sel].astype(np.float64) * 255).astype(np.int64)   # int(float(v) * 255) per element
                     cols = [int(ints[:, k].sum() / len(sel)) for k in range(6)]
                 fr, fg, fb, br, bg, bb = cols
                 self.logger.info(f"prob: {prob} {txt} fg: ({fr}, {fg}, {fb}) bg: ({br}, {bg}, {bb})")
