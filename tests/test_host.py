@@ -234,3 +234,67 @@ def test_bench_lama_ffc_figure_from_recorded_launches():
     assert fig["binding_term"] == "tensor"                                    # the fused block is tensor bound
     assert bench.ffc_block_from_launches([], prof, 1, bench.load_peaks()) is None
     _json.dumps(fig)
+
+
+class _FakeEngine:
+    """Stands in for mit_b200.engine.Engine so the plugins' HOST logic can run without a GPU (never part of the product path)."""
+
+    def __init__(self, T=20, V=12):
+        self.T, self.V = T, V
+        self.calls = []
+
+    def h2d(self, t, dtype=None):
+        return t
+
+    def d2h(self, t):
+        return t
+
+    def ocr_forward(self, region):
+        import numpy as np
+        n = region.shape[0]
+        rng = np.random.default_rng(5)
+        pred = rng.integers(0, self.V, (n, self.T)).astype(np.int32)
+        pred[:, ::3] = 0
+        logprob = (-rng.random((n, self.T)) * 0.2).astype(np.float32)
+        colors = rng.random((n, self.T, 6)).astype(np.float32)
+        self.calls.append(("ocr", region.shape))
+        return pred, logprob, colors
+
+    def lama_infer_u8(self, img, mask, rel, direct, composite=True):
+        self.calls.append(("lama", img.shape, mask.shape, None if rel is None else rel.shape, composite))
+        return (255 - img).copy()
+
+
+def test_plugin_host_logic_with_a_fake_engine():
+    """OCR post-processing (probability / colour statistics, in-place quad mutation) and the inpainter's resize + composite path."""
+    import asyncio
+    import numpy as np
+    from mit_b200 import plugins, synth
+    from mit_b200.compat import InpainterConfig, OcrConfig
+    page, boxes, mask = synth.make_page(3, 512, 384, 6)
+    quads = synth.make_quads(boxes)
+    ocr = plugins.Model48pxCTCOCR.__new__(plugins.Model48pxCTCOCR)
+    plugins.Model48pxCTCOCR.__init__(ocr)
+    ocr.engine = _FakeEngine()
+    ocr.dictionary = ["<S>", "</S>", "<SP>"] + [chr(0x3042 + i) for i in range(9)]
+    out = asyncio.run(ocr._infer(page, quads, OcrConfig(), False))
+    assert len(out) >= 1 and all(q.text and 0 < q.prob <= 1 for q in out)
+    assert all(0 <= c <= 255 for q in out for c in (q.fg_r, q.fg_g, q.fg_b, q.bg_r, q.bg_g, q.bg_b))
+    # reference arithmetic of the statistics, recomputed per element for the first kept line
+    eng = _FakeEngine()
+    pred, logprob, colors = eng.ocr_forward(np.zeros((6, 48, 8, 3), np.uint8))
+    steps = plugins.ctc_collapse(pred)[0]
+    want_prob = np.exp(np.mean([float(v) for v in logprob[0, steps]]))
+    assert any(abs(q.prob - want_prob) < 1e-12 for q in out)
+
+    inp = plugins.LamaMPEInpainter.__new__(plugins.LamaMPEInpainter)
+    plugins.LamaMPEInpainter.__init__(inp)
+    inp.engine = _FakeEngine()
+    page0, mask0 = page.copy(), mask.copy()
+    res = asyncio.run(inp._infer(page, mask, InpainterConfig(), 1024, False))           # no resize: device composite
+    assert res.shape == page.shape and inp.engine.calls[-1][-1] is True
+    res = asyncio.run(inp._infer(page, mask, InpainterConfig(), 256, False))            # resize: host composite with the {0,1} mask
+    m01 = (mask0 >= 127)[:, :, None]
+    assert res.shape == page.shape and inp.engine.calls[-1][-1] is False
+    assert (res[~np.broadcast_to(m01, res.shape)] == page0[~np.broadcast_to(m01, page0.shape)]).all()   # untouched outside the mask
+    assert (page == page0).all() and (mask == mask0).all()                               # borrowed inputs were not written
