@@ -35,6 +35,7 @@ class Engine:
         self._h = h
         self._keep = {}
         self._lock = threading.RLock()   # the context is not re-entrant: page-pipeline threads serialise their ENQUEUES here
+        self._pinned = {}       # (thread, shape, dtype) -> pinned staging tensor of d2h(scratch=True)
         self.h2d_bytes = 0      # bytes moved host->device / device->host through h2d()/d2h() (bench.py e2e accounting)
         self.d2h_bytes = 0
 
@@ -46,8 +47,26 @@ class Engine:
         t = t.to(self.device, non_blocking=True)
         return t if dtype is None else t.to(dtype)
 
-    def d2h(self, t: torch.Tensor) -> np.ndarray:
+    def d2h(self, t: torch.Tensor, scratch: bool = False) -> np.ndarray:
+        """Device tensor -> numpy.  `scratch=True` (large tensors the caller consumes before ITS next d2h of the same shape,
+        e.g. the detector's probability map) lands in a per-thread pinned buffer: the copy runs at full PCIe rate instead of
+        staging through pageable memory while the page threads' kernels queue behind it on the shared stream.  The returned
+        array is a view of that buffer - never hand it to the caller of the plugin."""
         self.d2h_bytes += t.numel() * t.element_size()
+        if scratch and self._pinned is not None and t.is_cuda and t.numel() * t.element_size() >= (1 << 20):
+            try:
+                key = (threading.get_ident(), tuple(t.shape), t.dtype)
+                buf = self._pinned.get(key)
+                if buf is None:
+                    if len(self._pinned) >= 64:          # page sizes changed often: stop growing the pinned pool
+                        raise RuntimeError("pinned pool full")
+                    buf = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+                    self._pinned[key] = buf
+                buf.copy_(t, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return buf.numpy()
+            except Exception:                             # any trouble with pinned memory: permanent fallback to the plain path
+                self._pinned = None
         return t.cpu().numpy()
 
     # ------------------------------------------------------------------ plumbing

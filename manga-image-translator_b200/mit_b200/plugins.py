@@ -89,7 +89,7 @@ class DBConvNextDetector(_InjectableWeights, OfflineDetector):
                 batch = eng.h2d(resized[None])
             ratio_h = ratio_w = 1 / target_ratio
             db_t, mask_t = eng.dbnet_forward(batch)
-            db, mask = eng.d2h(db_t[:, :1].contiguous()), eng.d2h(mask_t)
+            db, mask = eng.d2h(db_t[:, :1].contiguous(), scratch=True), eng.d2h(mask_t, scratch=True)   # consumed below, never returned
             img_resized_h, img_resized_w = rh, rw
         else:
             img_resized_h, img_resized_w = image.shape[:2]

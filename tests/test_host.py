@@ -246,7 +246,7 @@ class _FakeEngine:
     def h2d(self, t, dtype=None):
         return t
 
-    def d2h(self, t):
+    def d2h(self, t, scratch=False):
         return t
 
     def ocr_forward(self, region):
