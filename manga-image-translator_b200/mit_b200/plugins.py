@@ -268,7 +268,7 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
         # composite with the original page all run on the device; only uint8 crosses the bus.
         out_dev = eng.lama_infer_u8(eng.h2d(np.ascontiguousarray(image)), eng.h2d(np.ascontiguousarray(mask)), rel_pos, direct,
                                     composite=not resized)
-        img_inpainted = eng.d2h(out_dev)
+        img_inpainted = eng.d2h(out_dev, scratch=True).copy()      # pinned staging for the bus, then an owned array for the caller
         if not resized:
             return img_inpainted
         if new_h != height or new_w != width:
