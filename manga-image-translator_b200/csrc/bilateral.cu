@@ -15,9 +15,10 @@ __constant__ float c_space_w[BMAXN];
 __constant__ int8_t c_off_y[BMAXN], c_off_x[BMAXN];
 __constant__ float c_color_w[768];
 static int g_bilateral_n = 0;
+static PerDeviceOnce g_bilateral_once;     // the __constant__ tables live per device
 
 static void bilateral_init() {
-  if (g_bilateral_n) return;
+  if (!g_bilateral_once.first()) return;
   float sw[BMAXN]; int8_t oy[BMAXN], ox[BMAXN]; float cw[768];
   const double gs = -0.5 / (80.0 * 80.0), gc = -0.5 / (80.0 * 80.0);
   int n = 0;

@@ -642,8 +642,7 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st);
 static bool tma_dispatch(const ConvOp& op) {
   if (!conv_tma_supported(op)) return false;
   // TMA-fed kernel unless the layer is so small that it needs split-K
-  static int sms = 0;
-  if (!sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+  const int sms = device_sm_count();
   const long Mrows = (long)op.in.N * op.Ho * op.Wo;
   const long tiles = ((Mrows + TC_BM - 1) / TC_BM) * (op.tc_npad / op.tc_bn);
   const bool would_split = !op.stat_max && tiles * 2 <= sms && op.tc_kpad / TC_BK >= 16;
@@ -653,7 +652,7 @@ bool conv_uses_tma(const ConvOp& op) { return op.out.C > 4 && conv_tc_supported(
 
 void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   if (tma_dispatch(op)) { launch_conv_tma(op, st); return; }
-  MITB_CHECK(!op.in_split && !op.out_split, "conv: split-fused ops must run on the TMA path");
+  MITB_CHECK(!op.in_sv.valid() && !op.out_sv.valid() && !op.seg2.sv.valid(), "conv: operand-fused ops must run on the TMA path");
   TcParams p;
   p.in = op.in.p; p.N = op.in.N; p.H = op.in.H; p.W = op.in.W; p.in_cs = op.in.cs; p.in_coff = op.in.coff; p.Cin = op.in.C;
   p.in_planar = op.in.planar;
@@ -690,10 +689,9 @@ void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
   MITB_CHECK(stages >= 2, "tc conv: tile does not fit shared memory");
   p.stages = stages;
   const size_t smem = stages * stage_bytes + (2 * stages + 6) * 8 + epi_bytes + 1024;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
-    CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int num_sms = device_sm_count();
+  static PerDeviceOnce tc_attr;
+  if (tc_attr.first()) {
     CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

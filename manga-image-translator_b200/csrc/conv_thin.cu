@@ -126,8 +126,8 @@ void launch_conv_thin(const ConvOp& op, cudaStream_t st) {
   p.w = op.w; p.out = op.out.p; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C; p.out_planar = op.out.planar;
   p.shift = op.shift; p.act = op.act; p.pad = op.pad;
   const size_t smem = (size_t)(CCH * SH * SW + CCH * KS * KS * 4) * sizeof(float);
-  static bool attr = false;
-  if (!attr) { CUDA_OK(cudaFuncSetAttribute(conv7_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static PerDeviceOnce attr;
+  if (attr.first()) CUDA_OK(cudaFuncSetAttribute(conv7_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p.W + TW - 1) / TW, (p.H + TH - 1) / TH, p.N);
   conv7_thin_kernel<<<grid, 256, smem, st>>>(p);
   count_launch();

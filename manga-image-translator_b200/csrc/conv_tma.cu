@@ -16,6 +16,10 @@
 //   warp 8   one thread: 12 tcgen05.mma per K block (bf16x3: Ah*Bh + Ah*Bm + Am*Bh), tcgen05.commit -> "empty" barrier;
 //   warps 0-7 epilogue: TMEM -> registers -> (+add0)*scale+shift -> act -> *mul1 -> +add1 -> coalesced fp32 stores through a
 //            shared-memory transpose; double-buffered accumulator, so tile i drains while tile i+1 is multiplied.
+// Operand fusion (ConvOp::in_sv / out_sv / seg2): a producer's epilogue can store its result directly as the consumer's bf16
+// hi/mid operand tensor (SplitView, optionally with a reflect halo and the consumer's BN+ReLU prologue applied), so the split
+// pass disappears; and a second K segment with its own tensor maps lets two convolutions of different inputs accumulate into one
+// TMEM accumulator (FFC: conv1x1(U) + conv3x3_{l->g}(x_l) -> BN_g -> ReLU -> +residual in ONE launch).
 // An output tile is a bh x bw pixel patch of one image (bw*bh = 128, bw a power of two) so that a tap is a rectangular TMA
 // box; 1x1 convs use the flattened [pixels][C] matrix (bw = 128, bh = 1).  Persistent CTAs, one per SM.
 #include <cuda.h>
@@ -33,10 +37,13 @@ constexpr int TM_EWARPS = 8;
 constexpr int TM_MMAWARP = TM_EWARPS, TM_TMAWARP = TM_EWARPS + 1;
 constexpr int TM_THREADS = (TM_EWARPS + 2) * 32;
 
-struct TmaParams {
+struct SegParams {                                             // one K segment = one input tensor
   CUtensorMap ta_hi, ta_mid;                                  // activations: 4-D (C, Wp, Hp, N) bf16, box {64, bw, bh, 1}
+  int ntaps, cblks, c0; int8_t tdy[kMaxTaps], tdx[kMaxTaps];  // channel offset of the slice; tap offsets in (padded) input coordinates
+};
+struct TmaParams {
+  SegParams seg[2]; int nseg, nkb;
   CUtensorMap tb_hi, tb_mid;                                  // weights: 2-D (K, Npad) bf16, box {64, BN}
-  int ntaps, cblks; int8_t tdy[kMaxTaps], tdx[kMaxTaps];      // tap offsets in (padded) input coordinates
   int N, Ho, Wo, M, lin;                                      // lin: tile = 128 consecutive rows of the flattened [M][C] matrix
   int sy, sx;                                                 // conv stride (TMA element strides of the activation box)
   int bw_log2, tiles_x, tiles_y;
@@ -46,7 +53,9 @@ struct TmaParams {
   const float* add1; int add1_cs, add1_coff, add1_planar;
   const float* scale; const float* shift; const float* mul1; int act;
   float* stat_max; float* stat_sum; int* stat_idx; int stat_ld;
-  uint16_t* os_hi; uint16_t* os_mid;                          // out_split: bf16 hi / mid destinations [pixels][Cout] (else null)
+  // split output (ConvOp::out_sv): bf16 hi / mid at [((n*os_Hp + y + os_pt)*os_Wp + x + os_pl)*os_pitch + os_coff + c] (null: none)
+  uint16_t* os_hi; uint16_t* os_mid; int os_pitch, os_coff, os_Hp, os_Wp, os_pt, os_pl;
+  const float* os_scale; const float* os_shift; int os_relu;  // consumer prologue applied before splitting
 };
 
 #include "tc_common.cuh"
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkb = p.ntaps * p.cblks;
+  const int nkb = p.nkb;
   const int bw = 1 << p.bw_log2, bh = TC_BM >> p.bw_log2;
   const int mt = p.N * p.tiles_y * p.tiles_x, nt = p.npad / BN;
   const int total_tiles = mt * nt;
@@ -212,13 +221,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         // 8 rows x 64 contiguous bytes (residual reads and stores coalesced)
         float* st = estage + (size_t)warp * 32 * 20;
         const int sub = lane & 3, rsel = lane >> 2;              // this thread: columns 4*sub..+3 of rows rsel + 8j
-        size_t orow[4]; uint32_t rmask = 0;
+        size_t orow[4]; uint32_t srow[4]; uint32_t rmask = 0;    // srow: pixel index inside the (halo'd) split output tensor
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           int nimg, oy, ox;
-          orow[j] = 0;
+          orow[j] = 0; srow[j] = 0;
           if (row_pixel(q * 32 + rsel + 8 * j, nimg_t, oy0, ox0, nimg, oy, ox)) {
             orow[j] = ((size_t)nimg * p.oH + oy * p.oy_mul + p.oy_add) * p.oW + ox * p.ox_mul + p.ox_add;
+            srow[j] = (uint32_t)((nimg * p.os_Hp + oy + p.os_pt) * p.os_Wp + ox + p.os_pl);
             rmask |= 1u << j;
           }
         }
@@ -261,12 +271,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
           if (cq < p.Cout) {
             const bool full = cq + 3 < p.Cout;
             float sc4[4] = {1.f, 1.f, 1.f, 1.f}, sh4[4] = {0.f, 0.f, 0.f, 0.f}, mu4[4] = {1.f, 1.f, 1.f, 1.f};
+            float os_sc4[4] = {1.f, 1.f, 1.f, 1.f}, os_sh4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (cq + e < p.Cout) {
                 if (p.scale) sc4[e] = __ldg(p.scale + cq + e);
                 if (p.shift) sh4[e] = __ldg(p.shift + cq + e);
                 if (p.mul1) mu4[e] = __ldg(p.mul1 + cq + e);
+                if (p.os_scale) { os_sc4[e] = __ldg(p.os_scale + cq + e); os_sh4[e] = __ldg(p.os_shift + cq + e); }
               }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -284,13 +296,24 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
                 v4[e] = x;
               }
               if (p.add1) { v4[0] += pa1[j].x; v4[1] += pa1[j].y; v4[2] += pa1[j].z; v4[3] += pa1[j].w; }
-              if (p.os_hi) {                         // conv -> conv fusion: store the consumer's bf16 hi / mid operands directly
+              if (p.out) {
+                if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
+              }
+              if (p.os_hi) {                         // producer -> consumer fusion: store the consumer's bf16 hi / mid operands directly
+                if (p.os_scale) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    v4[e] = fmaf(v4[e], os_sc4[e], os_sh4[e]);
+                    if (p.os_relu) v4[e] = fmaxf(v4[e], 0.f);
+                  }
+                }
                 uint2 hh, mm;
                 split4(make_float4(v4[0], v4[1], v4[2], v4[3]), hh, mm);
-                *reinterpret_cast<uint2*>(p.os_hi + orow[j] * p.Cout + cq) = hh;
-                *reinterpret_cast<uint2*>(p.os_mid + orow[j] * p.Cout + cq) = mm;
-              } else if (full) *reinterpret_cast<float4*>(p.out + orow[j] * p.out_cs + p.out_coff + cq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-              else { for (int e = 0; e < 4; ++e) if (cq + e < p.Cout) p.out[orow[j] * p.out_cs + p.out_coff + cq + e] = v4[e]; }
+                const size_t so = (size_t)srow[j] * p.os_pitch + p.os_coff + cq;
+                *reinterpret_cast<uint2*>(p.os_hi + so) = hh;
+                *reinterpret_cast<uint2*>(p.os_mid + so) = mm;
+              }
             }
           }
           __syncwarp();
@@ -363,16 +386,21 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int nimg, oy0, ox0, n0;
       decode(t, nimg, oy0, ox0, n0);
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(empty_bar(s), ph);
-        const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
-        const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
-        const int x = ox0 * p.sx + p.tdx[tap], y = oy0 * p.sy + p.tdy[tap];
-        tma_kblock(full_bar(s), 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &p.ta_hi, &p.ta_mid, &p.tb_hi, &p.tb_mid,
-                   cb * TC_BK, x, y, nimg, kb * TC_BK, n0);
-        if (++cb == p.cblks) { cb = 0; ++tap; }
-        if (++s == S) { s = 0; ph ^= 1u; }
+      int kb = 0;
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        const SegParams& sp = p.seg[sg];
+        int tap = 0, cb = 0;
+        const int nk = sp.ntaps * sp.cblks;
+        for (int i = 0; i < nk; ++i, ++kb) {
+          mbar_wait(empty_bar(s), ph);
+          const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+          const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+          const int x = ox0 * p.sx + sp.tdx[tap], y = oy0 * p.sy + sp.tdy[tap];
+          tma_kblock(full_bar(s), 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &sp.ta_hi, &sp.ta_mid, &p.tb_hi, &p.tb_mid,
+                     sp.c0 + cb * TC_BK, x, y, nimg, kb * TC_BK, n0);
+          if (++cb == sp.cblks) { cb = 0; ++tap; }
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
       }
     }
     __syncwarp();
@@ -383,18 +411,18 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// fp32 view -> dense bf16 hi / mid NHWC tensors [N][Hp][Wp][C] (one thread = 8 channels of one padded pixel).
+// fp32 view -> bf16 hi / mid split tensor (one thread = 8 channels of one padded pixel), channels [coff, coff + C) of `sv`.
 // Halo rows/cols (pt/pl) are filled by reflection (PAD_REFLECT); zero padding needs no halo (TMA out-of-bounds fill).
 // The BN+ReLU prologue of the pre-activation ResNet is applied here, once per element.
 struct SplitParams {
-  const float* in; int N, H, W, C, Cp, cs, coff, planar;          // C source channels, Cp >= C stored channels (zero padded)
+  const float* in; int N, H, W, C, cs, coff, planar;
   int Hp, Wp, pt, pl;
   const float* in_scale; const float* in_shift; int in_relu;
-  uint16_t* hi; uint16_t* mid;
+  uint16_t* hi; uint16_t* mid; int o_pitch, o_coff;
 };
 
 __global__ void __launch_bounds__(256) split_pad_kernel(const SplitParams q) {
-  const int c8n = q.Cp >> 3;
+  const int c8n = q.C >> 3;
   const long npix = (long)q.N * q.Hp * q.Wp;
   const long total = npix * c8n;
   const size_t HW = (size_t)q.H * q.W;
@@ -407,32 +435,48 @@ __global__ void __launch_bounds__(256) split_pad_kernel(const SplitParams q) {
     const int sy = reflect_tc(y - q.pt, q.H), sx = reflect_tc(x - q.pl, q.W);
     const int c0 = c8 * 8;
     float v[8];
-    if (c0 >= q.C) {
+    if (q.planar) {
+      const float* src = q.in + ((size_t)n * q.cs + q.coff + c0) * HW + (size_t)sy * q.W + sx;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(src + (size_t)e * HW);
     } else {
-      if (q.planar) {
-        const float* src = q.in + ((size_t)n * q.cs + q.coff + c0) * HW + (size_t)sy * q.W + sx;
+      const float* src = q.in + ((size_t)(n * q.H + sy) * q.W + sx) * q.cs + q.coff + c0;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    if (q.in_scale) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(src + (size_t)e * HW);
-      } else {
-        const float* src = q.in + ((size_t)(n * q.H + sy) * q.W + sx) * q.cs + q.coff + c0;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      }
-      if (q.in_scale) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float t = v[e] * __ldg(q.in_scale + c0 + e) + __ldg(q.in_shift + c0 + e);
-          v[e] = q.in_relu ? fmaxf(t, 0.f) : t;
-        }
+      for (int e = 0; e < 8; ++e) {
+        const float t = v[e] * __ldg(q.in_scale + c0 + e) + __ldg(q.in_shift + c0 + e);
+        v[e] = q.in_relu ? fmaxf(t, 0.f) : t;
       }
     }
     uint4 hi, mid;
     split8(v, hi, mid);
-    const size_t o = (size_t)pix * q.Cp + c0;
+    const size_t o = (size_t)pix * q.o_pitch + q.o_coff + c0;
     *reinterpret_cast<uint4*>(q.hi + o) = hi;
     *reinterpret_cast<uint4*>(q.mid + o) = mid;
+  }
+}
+
+// Reflect halo of channels [coff, coff + C) of a split tensor, copied from its interior (one thread = 8 channels of one halo pixel).
+__global__ void __launch_bounds__(256) split_halo_kernel(uint16_t* hi, uint16_t* mid, int N, int H, int W, int Hp, int Wp, int pt, int pl,
+                                                         int pitch, int coff, int C) {
+  const int c8n = C >> 3;
+  const long rows_h = (long)(Hp - H) * Wp;                 // full-width halo rows (top + bottom)
+  const long per_img = rows_h + (long)H * (Wp - W);        // + left/right columns of the interior rows
+  const long total = (long)N * per_img * c8n;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n); const long hp = i / c8n;
+    const int n = (int)(hp / per_img); const long j = hp - (long)n * per_img;
+    int y, x;
+    if (j < rows_h) { const int r = (int)(j / Wp); x = (int)(j - (long)r * Wp); y = r < pt ? r : r + H; }
+    else { const long k = j - rows_h; const int r = (int)(k / (Wp - W)); const int xx = (int)(k - (long)r * (Wp - W)); y = pt + r; x = xx < pl ? xx : xx + W; }
+    const int sy = reflect_tc(y - pt, H) + pt, sx = reflect_tc(x - pl, W) + pl;
+    const size_t so = ((size_t)(n * Hp + sy) * Wp + sx) * pitch + coff + c8 * 8;
+    const size_t dst_o = ((size_t)(n * Hp + y) * Wp + x) * pitch + coff + c8 * 8;
+    *reinterpret_cast<uint4*>(hi + dst_o) = *reinterpret_cast<const uint4*>(hi + so);
+    *reinterpret_cast<uint4*>(mid + dst_o) = *reinterpret_cast<const uint4*>(mid + so);
   }
 }
 
@@ -451,7 +495,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // 4-D activation map over a dense bf16 tensor [N][Hp][Wp][C]: box = {64 ch, bw, bh, 1} pixels taken every (sx, sy)-th element,
-// 128-byte swizzle, zero out-of-bounds fill (= zero padding of the convolution)
+// 128-byte swizzle, zero out-of-bounds fill (= zero padding of the convolution, and zero for channels >= C)
 void make_act_tmap(CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int bw, int bh, int sx, int sy) {
   const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
   const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
@@ -496,9 +540,53 @@ int choose_bn(int Cout, long mtiles, int nkb, int sms) {
 
 bool g_tma_enabled = true;
 
+// halo a conv needs around its input for reflect padding (zero padding: none)
+void conv_halo(const int8_t* tdy, const int8_t* tdx, int ntaps, int pad, int H, int W, int Ho, int Wo, int sy, int sx, int& pt, int& pb,
+               int& pl, int& pr) {
+  pt = pb = pl = pr = 0;
+  if (pad != PAD_REFLECT) return;
+  int tmin_dy = 127, tmax_dy = -127, tmin_dx = 127, tmax_dx = -127;
+  for (int t = 0; t < ntaps; ++t) {
+    tmin_dy = tdy[t] < tmin_dy ? tdy[t] : tmin_dy; tmax_dy = tdy[t] > tmax_dy ? tdy[t] : tmax_dy;
+    tmin_dx = tdx[t] < tmin_dx ? tdx[t] : tmin_dx; tmax_dx = tdx[t] > tmax_dx ? tdx[t] : tmax_dx;
+  }
+  pt = tmin_dy < 0 ? -tmin_dy : 0; pl = tmin_dx < 0 ? -tmin_dx : 0;
+  pb = (Ho - 1) * sy + tmax_dy - (H - 1); if (pb < 0) pb = 0;
+  pr = (Wo - 1) * sx + tmax_dx - (W - 1); if (pr < 0) pr = 0;
+}
+
 }  // namespace
 
 void conv_tma_set_enabled(bool on) { g_tma_enabled = on; }
+
+void launch_split(const View& in, const SplitView& sv, int coff, const float* in_scale, const float* in_shift, int in_relu, cudaStream_t st) {
+  MITB_CHECK(sv.valid() && sv.N == in.N && sv.H == in.H && sv.W == in.W && coff + in.C <= sv.C, "split: shape mismatch");
+  MITB_CHECK(in.C % 8 == 0 && sv.C % 8 == 0 && coff % 8 == 0, "split: channel counts/offsets must be multiples of 8");
+  MITB_CHECK(in.planar || (in.cs % 4 == 0 && in.coff % 4 == 0), "split: unaligned NHWC view");
+  SplitParams q;
+  q.in = in.p; q.N = in.N; q.H = in.H; q.W = in.W; q.C = in.C; q.cs = in.cs; q.coff = in.coff; q.planar = in.planar;
+  q.Hp = sv.Hp; q.Wp = sv.Wp; q.pt = sv.pt; q.pl = sv.pl;
+  q.in_scale = in_scale; q.in_shift = in_shift; q.in_relu = in_relu;
+  q.hi = sv.hi; q.mid = sv.mid; q.o_pitch = sv.C; q.o_coff = coff;
+  const long total = (long)sv.N * sv.Hp * sv.Wp * (in.C / 8);
+  long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+  if (blocks < 1) return;
+  split_pad_kernel<<<(int)blocks, 256, 0, st>>>(q);
+  count_launch();
+  CUDA_OK(cudaGetLastError());
+}
+
+void launch_split_halo(const SplitView& sv, int coff, int C, cudaStream_t st) {
+  if (sv.Hp == sv.H && sv.Wp == sv.W) return;
+  MITB_CHECK(sv.valid() && C % 8 == 0 && coff % 8 == 0 && sv.C % 8 == 0 && coff + C <= sv.C, "split halo: bad channel slice");
+  MITB_CHECK(sv.pt < sv.H && sv.pl < sv.W && sv.Hp - sv.H - sv.pt < sv.H && sv.Wp - sv.W - sv.pl < sv.W, "split halo wider than the image");
+  const long total = (long)sv.N * ((long)(sv.Hp - sv.H) * sv.Wp + (long)sv.H * (sv.Wp - sv.W)) * (C / 8);
+  long blocks = (total + 255) / 256; if (blocks > 148L * 8) blocks = 148L * 8;
+  ProfScope ps("split_halo", 0.0, 4.0 * total * 8, st);
+  split_halo_kernel<<<(int)blocks, 256, 0, st>>>(sv.hi, sv.mid, sv.N, sv.H, sv.W, sv.Hp, sv.Wp, sv.pt, sv.pl, sv.C, coff, C);
+  count_launch();
+  CUDA_OK(cudaGetLastError());
+}
 
 bool conv_tma_supported(const ConvOp& op) {
   static int env = -1;
@@ -506,10 +594,12 @@ bool conv_tma_supported(const ConvOp& op) {
   if (!g_tma_enabled || !env || !op.wh || !op.wm) return false;
   if (op.sy < 1 || op.sy > 2 || op.sx < 1 || op.sx > 2) return false;
   const int C = op.in.C;
-  if (C % 64 == 0) { if (op.tc_kpad != op.ntaps * C) return false; }       // main copy is already in (tap, 64-channel block) order
+  if (C % 64 == 0) { if (!op.seg2.sv.valid() && op.tc_kpad != op.ntaps * C) return false; }   // main copy is already in (tap, 64-channel block) order
   else if (!(op.whp && op.wmp && op.tc_cp >= C)) return false;             // needs the per-tap padded copy (Cin % 8 == 0, >= 16)
-  if (!op.in.planar && (op.in.cs % 4 != 0 || op.in.coff % 4 != 0)) return false;
-  if (op.in.planar && op.ntaps != 1) return false;
+  if (!op.in_sv.valid()) {
+    if (!op.in.planar && (op.in.cs % 4 != 0 || op.in.coff % 4 != 0)) return false;
+    if (op.in.planar && op.ntaps != 1) return false;
+  }
   const long M = (long)op.in.N * op.Ho * op.Wo;
   if (M < 128) return false;
   return true;
@@ -518,67 +608,52 @@ bool conv_tma_supported(const ConvOp& op) {
 void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   const int C = op.in.C, N = op.in.N, H = op.in.H, W = op.in.W;
   const bool padded_w = C % 64 != 0;
-  const int Cp = padded_w ? op.tc_cp : C;                           // channels stored per pixel (multiple of 64)
-  // ---- geometry of the split tensor: reflect padding is materialised as a halo, zero padding is TMA out-of-bounds fill
-  int tmin_dy = 127, tmax_dy = -127, tmin_dx = 127, tmax_dx = -127;
-  for (int t = 0; t < op.ntaps; ++t) {
-    tmin_dy = op.tdy[t] < tmin_dy ? op.tdy[t] : tmin_dy; tmax_dy = op.tdy[t] > tmax_dy ? op.tdy[t] : tmax_dy;
-    tmin_dx = op.tdx[t] < tmin_dx ? op.tdx[t] : tmin_dx; tmax_dx = op.tdx[t] > tmax_dx ? op.tdx[t] : tmax_dx;
-  }
-  int pt = 0, pb = 0, pl = 0, pr = 0;
-  if (op.pad == PAD_REFLECT) {
-    pt = tmin_dy < 0 ? -tmin_dy : 0; pl = tmin_dx < 0 ? -tmin_dx : 0;
-    pb = (op.Ho - 1) * op.sy + tmax_dy - (H - 1); if (pb < 0) pb = 0;
-    pr = (op.Wo - 1) * op.sx + tmax_dx - (W - 1); if (pr < 0) pr = 0;
-  }
-  const int Hp = H + pt + pb, Wp = W + pl + pr;
-  const size_t elems = (size_t)N * Hp * Wp * Cp;
-  static DeviceScratch g_split;                                             // bf16 hi | mid of the current conv's input
-  uint16_t* hi = static_cast<uint16_t*>(g_split.get(2 * elems * sizeof(uint16_t))); uint16_t* mid = hi + elems;
-  if (op.in_split) {
-    // the producer conv already stored bf16 hi | mid into the bytes of this fp32 view (ConvOp::out_split)
-    MITB_CHECK(!padded_w && pt == 0 && pl == 0 && pb == 0 && pr == 0 && !op.in.planar && op.in.cs == C && op.in.coff == 0 && !op.in_scale,
-               "tma conv: in_split needs a dense NHWC input without halo or prologue");
-    hi = reinterpret_cast<uint16_t*>(const_cast<float*>(op.in.p)); mid = hi + elems;
-  }
-  // ---- split pass, skipped when the previous kernel launched by this library was a TMA conv over exactly the same input
-  // (the four sub-pixel phases of a transposed conv, sibling convs of one tensor): the scratch still holds its split.
-  // Safe by construction: ANY other launch in between bumps g_launch_epoch, and a conv whose output overlaps the cached
-  // input invalidates the entry.
+  const int cblks = (C + TC_BK - 1) / TC_BK;                          // K blocks per tap; channels >= C arrive as zeros (TMA bounds)
+  int pt, pb, pl, pr;
+  conv_halo(op.tdy, op.tdx, op.ntaps, op.pad, H, W, op.Ho, op.Wo, op.sy, op.sx, pt, pb, pl, pr);
+  SplitView sv; int sv_coff = 0;
+  int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+  // the split cache below: remembers which tensor the per-device scratch currently holds
   struct SplitKey {
-    const float* in; int N, H, W, C, Cp, cs, coff, planar, Hp, Wp, pt, pl, relu; const float* sc; const float* sh; cudaStream_t st;
+    const float* in; int N, H, W, C, cs, coff, planar, Hp, Wp, pt, pl, relu; const float* sc; const float* sh; cudaStream_t st; int dev;
     bool same(const SplitKey& o) const {
-      return in == o.in && N == o.N && H == o.H && W == o.W && C == o.C && Cp == o.Cp && cs == o.cs && coff == o.coff && planar == o.planar &&
-             Hp == o.Hp && Wp == o.Wp && pt == o.pt && pl == o.pl && relu == o.relu && sc == o.sc && sh == o.sh && st == o.st;
+      return in == o.in && N == o.N && H == o.H && W == o.W && C == o.C && cs == o.cs && coff == o.coff && planar == o.planar &&
+             Hp == o.Hp && Wp == o.Wp && pt == o.pt && pl == o.pl && relu == o.relu && sc == o.sc && sh == o.sh && st == o.st && dev == o.dev;
     }
   };
   static SplitKey g_key; static bool g_key_valid = false; static unsigned long g_key_epoch = 0; static const uint16_t* g_key_hi = nullptr;
-  const SplitKey key{op.in.p, N, H, W, C, Cp, op.in.cs, op.in.coff, op.in.planar, Hp, Wp, pt, pl, op.in_relu, op.in_scale, op.in_shift, st};
-  const bool reuse = g_key_valid && g_key_epoch == g_launch_epoch && g_key_hi == hi && key.same(g_key);
-  if (!reuse && !op.in_split) {
-    SplitParams q;
-    q.in = op.in.p; q.N = N; q.H = H; q.W = W; q.C = C; q.Cp = Cp; q.cs = op.in.cs; q.coff = op.in.coff; q.planar = op.in.planar;
-    q.Hp = Hp; q.Wp = Wp; q.pt = pt; q.pl = pl;
-    q.in_scale = op.in_scale; q.in_shift = op.in_shift; q.in_relu = op.in_relu;
-    q.hi = hi; q.mid = mid;
-    const long total = (long)(elems / 8);
-    long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
-    split_pad_kernel<<<(int)blocks, 256, 0, st>>>(q);
-    count_launch();
-  }
-  {
+  bool remember = false;
+  if (op.in_sv.valid()) {
+    // ---- the producer already wrote this conv's bf16 hi / mid operands (ConvOp::out_sv of an earlier op, or launch_split)
+    sv = op.in_sv; sv_coff = op.in_sv_coff;
+    MITB_CHECK(sv.N == N && sv.H == H && sv.W == W && sv_coff + C <= sv.C && sv.C % 8 == 0 && sv_coff % 8 == 0, "tma conv: in_sv shape mismatch");
+    MITB_CHECK(sv.pt >= pt && sv.pl >= pl && sv.Hp - sv.H - sv.pt >= pb && sv.Wp - sv.W - sv.pl >= pr, "tma conv: in_sv halo too small");
+    MITB_CHECK(op.pad == PAD_REFLECT || (sv.Hp == sv.H && sv.Wp == sv.W), "tma conv: zero padding needs a halo-free in_sv");
+    MITB_CHECK(!op.in_scale, "tma conv: in_sv carries its prologue already");
+    MITB_CHECK(!padded_w || sv_coff + C == sv.C, "tma conv: Cin %% 64 != 0 needs the slice to end at the tensor's last channel");
+  } else {
+    // ---- split pass into the per-device scratch, skipped when the previous kernel launched by this library was a TMA conv
+    // over exactly the same input (the four sub-pixel phases of a transposed conv, sibling convs of one tensor).
+    // Safe by construction: ANY other launch in between bumps g_launch_epoch, and a conv whose output overlaps the cached
+    // input invalidates the entry.
+    MITB_CHECK(C % 8 == 0, "tma conv: Cin must be a multiple of 8");
+    sv.N = N; sv.H = H; sv.W = W; sv.C = C; sv.pt = pt; sv.pl = pl; sv.Hp = H + pt + pb; sv.Wp = W + pl + pr;
+    static DeviceScratch g_split;                                             // bf16 hi | mid of the current conv's input
+    sv.hi = static_cast<uint16_t*>(g_split.get(2 * sv.elems() * sizeof(uint16_t))); sv.mid = sv.hi + sv.elems();
+    const SplitKey key{op.in.p, N, H, W, C, op.in.cs, op.in.coff, op.in.planar, sv.Hp, sv.Wp, pt, pl, op.in_relu, op.in_scale, op.in_shift, st, dev};
+    const bool reuse = g_key_valid && g_key_epoch == g_launch_epoch && g_key_hi == sv.hi && key.same(g_key);
+    if (!reuse) launch_split(op.in, sv, 0, op.in_scale, op.in_shift, op.in_relu, st);
     // remember this split unless the conv writes into the tensor it was made from
     const float* ib = op.in.p; const float* ie = ib + (size_t)op.in.N * op.in.H * op.in.W * op.in.cs;
     const float* ob = op.out.p; const float* oe = ob ? ob + (size_t)op.out.N * op.out.H * op.out.W * op.out.cs : ob;
     const bool overlap = ob && ob < ie && ib < oe;
-    g_key = key; g_key_hi = hi;
-    g_key_valid = !overlap && !op.in_split;            // g_key_epoch is stamped after this conv's own launch, below
+    g_key = key; g_key_hi = sv.hi; remember = !overlap;
   }
+  g_key_valid = remember;                                                    // g_key_epoch is stamped after this conv's own launch, below
 
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
-    CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int num_sms = device_sm_count();
+  static PerDeviceOnce tma_attr;
+  if (tma_attr.first()) {
     CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -588,10 +663,13 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
 
   TmaParams p;
   memset(&p, 0, sizeof(p));
-  p.ntaps = op.ntaps; p.cblks = Cp / TC_BK;
-  for (int t = 0; t < op.ntaps; ++t) { p.tdy[t] = (int8_t)(op.tdy[t] + pt); p.tdx[t] = (int8_t)(op.tdx[t] + pl); }
+  const bool two = op.seg2.sv.valid();
+  p.nseg = two ? 2 : 1;
+  p.seg[0].ntaps = op.ntaps; p.seg[0].cblks = cblks; p.seg[0].c0 = sv_coff;
+  for (int t = 0; t < op.ntaps; ++t) { p.seg[0].tdy[t] = (int8_t)(op.tdy[t] + sv.pt); p.seg[0].tdx[t] = (int8_t)(op.tdx[t] + sv.pl); }
   p.N = N; p.Ho = op.Ho; p.Wo = op.Wo; p.M = N * op.Ho * op.Wo; p.sy = op.sy; p.sx = op.sx;
-  const bool lin = op.ntaps == 1 && op.Ho == H && op.Wo == W && op.sy == 1 && op.sx == 1 && op.tdy[0] == 0 && op.tdx[0] == 0;
+  const bool lin = !two && op.ntaps == 1 && op.Ho == H && op.Wo == W && op.sy == 1 && op.sx == 1 && op.tdy[0] == 0 && op.tdx[0] == 0 &&
+                   sv.Hp == H && sv.Wp == W;
   p.lin = lin ? 1 : 0;                                              // 1x1: flattened [pixels][C] matrix
   int bw, bh;
   if (lin) { bw = 128; bh = 1; p.tiles_x = (p.M + 127) / 128; p.tiles_y = 1; p.N = 1; }
@@ -606,15 +684,30 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     p.tiles_x = (op.Wo + bw - 1) / bw; p.tiles_y = (op.Ho + bh - 1) / bh;
   }
   p.bw_log2 = 0; while ((1 << p.bw_log2) < bw) ++p.bw_log2;
-  if (lin) { make_act_tmap(&p.ta_hi, hi, 1, 1, N * Hp * Wp, Cp, bw, bh, 1, 1); make_act_tmap(&p.ta_mid, mid, 1, 1, N * Hp * Wp, Cp, bw, bh, 1, 1); }
-  else { make_act_tmap(&p.ta_hi, hi, N, Hp, Wp, Cp, bw, bh, op.sx, op.sy); make_act_tmap(&p.ta_mid, mid, N, Hp, Wp, Cp, bw, bh, op.sx, op.sy); }
+  if (lin) { make_act_tmap(&p.seg[0].ta_hi, sv.hi, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); make_act_tmap(&p.seg[0].ta_mid, sv.mid, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); }
+  else { make_act_tmap(&p.seg[0].ta_hi, sv.hi, N, sv.Hp, sv.Wp, sv.C, bw, bh, op.sx, op.sy); make_act_tmap(&p.seg[0].ta_mid, sv.mid, N, sv.Hp, sv.Wp, sv.C, bw, bh, op.sx, op.sy); }
+  int kdim = op.ntaps * cblks * TC_BK;
+  if (two) {
+    const ConvOp::Seg2& s2 = op.seg2;
+    MITB_CHECK(!padded_w && s2.C % 64 == 0 && s2.ntaps >= 1 && s2.sv.N == N && s2.sv.H == op.Ho && s2.sv.W == op.Wo && op.sy == 1 && op.sx == 1 &&
+               s2.coff + s2.C <= s2.sv.C && s2.sv.C % 8 == 0, "tma conv: bad second K segment");
+    int qt, qb, ql, qr;
+    conv_halo(s2.tdy, s2.tdx, s2.ntaps, s2.pad, s2.sv.H, s2.sv.W, op.Ho, op.Wo, 1, 1, qt, qb, ql, qr);
+    MITB_CHECK(s2.sv.pt >= qt && s2.sv.pl >= ql && s2.sv.Hp - s2.sv.H - s2.sv.pt >= qb && s2.sv.Wp - s2.sv.W - s2.sv.pl >= qr, "tma conv: seg2 halo too small");
+    MITB_CHECK(s2.pad == PAD_REFLECT || (s2.sv.Hp == s2.sv.H && s2.sv.Wp == s2.sv.W), "tma conv: zero padding needs a halo-free seg2");
+    p.seg[1].ntaps = s2.ntaps; p.seg[1].cblks = s2.C / TC_BK; p.seg[1].c0 = s2.coff;
+    for (int t = 0; t < s2.ntaps; ++t) { p.seg[1].tdy[t] = (int8_t)(s2.tdy[t] + s2.sv.pt); p.seg[1].tdx[t] = (int8_t)(s2.tdx[t] + s2.sv.pl); }
+    make_act_tmap(&p.seg[1].ta_hi, s2.sv.hi, N, s2.sv.Hp, s2.sv.Wp, s2.sv.C, bw, bh, 1, 1);
+    make_act_tmap(&p.seg[1].ta_mid, s2.sv.mid, N, s2.sv.Hp, s2.sv.Wp, s2.sv.C, bw, bh, 1, 1);
+    kdim += s2.ntaps * s2.C;
+    MITB_CHECK(op.tc_kpad == kdim, "tma conv: merged weight has K %d, segments need %d", op.tc_kpad, kdim);
+  }
+  p.nkb = kdim / TC_BK;
   // ---- N tile: fixed by the row-stat layout for the vocabulary head, otherwise chosen per launch against wave quantisation
   const long mtiles = (long)p.N * p.tiles_y * p.tiles_x;
-  const int nkb = p.ntaps * p.cblks;
-  p.BN = op.stat_max ? op.tc_bn : choose_bn(op.out.C, mtiles, nkb, num_sms);
+  p.BN = op.stat_max ? op.tc_bn : choose_bn(op.out.C, mtiles, p.nkb, num_sms);
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tma conv: bad BN %d", p.BN);
   p.npad = (op.out.C + p.BN - 1) / p.BN * p.BN;
-  const int kdim = p.ntaps * Cp;
   make_w_tmap(&p.tb_hi, padded_w ? op.whp : op.wh, kdim, op.tc_npad, p.BN);
   make_w_tmap(&p.tb_mid, padded_w ? op.wmp : op.wm, kdim, op.tc_npad, p.BN);
   p.out = op.out.p; p.oH = op.out.H; p.oW = op.out.W; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C;
@@ -623,15 +716,19 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   p.add1 = op.add1.p; p.add1_cs = op.add1.cs; p.add1_coff = op.add1.coff; p.add1_planar = op.add1.planar;
   p.scale = op.scale; p.shift = op.shift; p.mul1 = op.mul1; p.act = op.act;
   p.stat_max = op.stat_max; p.stat_sum = op.stat_sum; p.stat_idx = op.stat_idx; p.stat_ld = op.stat_ld;
-  if (op.out_split) {
-    MITB_CHECK(!op.out.planar && op.out.cs == op.out.C && op.out.coff == 0 && op.out.C % 4 == 0 && !op.stat_max && op.oy_mul == 1 &&
-               op.ox_mul == 1 && op.oy_add == 0 && op.ox_add == 0 && op.out.H == op.Ho && op.out.W == op.Wo &&
+  if (op.out_sv.valid()) {
+    const SplitView& o = op.out_sv;
+    MITB_CHECK(!op.out.planar && op.out.C % 4 == 0 && !op.stat_max && op.oy_mul == 1 && op.ox_mul == 1 && op.oy_add == 0 && op.ox_add == 0 &&
+               o.N == N && o.H == op.Ho && o.W == op.Wo && o.C % 4 == 0 && op.out_sv_coff % 4 == 0 && op.out_sv_coff + op.out.C <= o.C &&
+               (!op.out.p || (op.out.H == op.Ho && op.out.W == op.Wo && ((op.out.cs | op.out.coff) & 3) == 0)) &&
                (!op.add0.p || (!op.add0.planar && ((op.add0.cs | op.add0.coff) & 3) == 0)) &&
                (!op.add1.p || (!op.add1.planar && ((op.add1.cs | op.add1.coff) & 3) == 0)),
-               "tma conv: out_split needs a dense NHWC output on the conv's own pixel grid");
-    p.os_hi = reinterpret_cast<uint16_t*>(op.out.p);
-    p.os_mid = p.os_hi + (size_t)op.out.N * op.out.H * op.out.W * op.out.C;
-  }
+               "tma conv: out_sv needs an NHWC output on the conv's own pixel grid");
+    MITB_CHECK((size_t)o.N * o.Hp * o.Wp < ((size_t)1 << 32), "tma conv: out_sv too large for 32-bit pixel indices");
+    p.os_hi = o.hi; p.os_mid = o.mid; p.os_pitch = o.C; p.os_coff = op.out_sv_coff; p.os_Hp = o.Hp; p.os_Wp = o.Wp; p.os_pt = o.pt; p.os_pl = o.pl;
+    p.os_scale = op.os_scale; p.os_shift = op.os_shift; p.os_relu = op.os_relu;
+    if (!op.out.p) { p.oH = op.Ho; p.oW = op.Wo; }
+  } else MITB_CHECK(op.out.p, "tma conv: no output");
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;

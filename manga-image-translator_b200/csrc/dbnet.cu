@@ -131,7 +131,11 @@ static void run_block(Exec& e, const CnBlock& b, const View& x, const View& out)
   ConvOp op2 = Exec::op_from(b.fc2, hid, out); op2.mul1 = b.gamma; op2.add1 = sc;
   // fc1 -> GELU -> fc2: when both run on the TMA-fed kernel, fc1 stores fc2's bf16 hi/mid operands straight into `hid`
   // (same bytes as the fp32 tensor it replaces) and fc2 skips its split pass
-  if (!e.dry && conv_uses_tma(op1) && conv_uses_tma(op2)) { op1.out_split = true; op2.in_split = true; }
+  if (conv_uses_tma(op1) && conv_uses_tma(op2)) {
+    SplitView hs; hs.N = hid.N; hs.H = hs.Hp = hid.H; hs.W = hs.Wp = hid.W; hs.C = hid.C;
+    hs.hi = reinterpret_cast<uint16_t*>(hid.p); hs.mid = hs.hi + hs.elems();
+    op1.out_sv = hs; op1.out.p = nullptr; op2.in_sv = hs;
+  }
   e.conv(op1);
   e.conv(op2);
   ws.release(mk);

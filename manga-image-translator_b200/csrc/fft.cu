@@ -210,13 +210,12 @@ __global__ void __launch_bounds__(256) irfft_rows_kernel(const float2* tmp, floa
   }
 }
 
-static bool g_fft_attr = false;
+static PerDeviceOnce g_fft_attr;
 static void fft_attrs() {
-  if (g_fft_attr) return;
+  if (!g_fft_attr.first()) return;
   CUDA_OK(cudaFuncSetAttribute(rfft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(cudaFuncSetAttribute(irfft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(cudaFuncSetAttribute(fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  g_fft_attr = true;
 }
 
 static const float* planar_base(const View& v, int* planes) {

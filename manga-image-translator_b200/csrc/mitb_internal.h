@@ -34,6 +34,17 @@ struct View {              // NHWC slice: element (n,y,x,c) at p[((n*H+y)*W+x)*c
   size_t pixels() const { return (size_t)N * H * W; }
 };
 
+// bf16 hi/mid operand copies of an activation tensor for the tensor-core kernel (x ~ hi + mid, |x - hi - mid| <= 2^-17 |x|):
+// two dense bf16 NHWC tensors [N][Hp][Wp][C]; logical pixel (y, x) lives at (y + pt, x + pl).  A halo (pt/pl > 0, Hp > H + pt)
+// holds the reflect padding of the consuming conv (zero padding needs none: TMA out-of-bounds fill).
+struct SplitView {
+  uint16_t* hi = nullptr; uint16_t* mid = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;                 // logical grid, channels per pixel (pitch)
+  int pt = 0, pl = 0, Hp = 0, Wp = 0;
+  bool valid() const { return hi != nullptr; }
+  size_t elems() const { return (size_t)N * Hp * Wp * C; }
+};
+
 // ------------------------------------------------------------------ bump arena with mark/release
 struct Arena {
   char* base = nullptr; size_t cap = 0, off = 0, peak = 0; bool dry = false;
@@ -50,6 +61,11 @@ struct Arena {
   View view(int N, int H, int W, int C, bool planar = false) {
     View v; v.p = alloc_f((size_t)N * H * W * C); v.N = N; v.H = H; v.W = W; v.C = C; v.cs = C; v.coff = 0;
     v.planar = planar; return v;
+  }
+  SplitView split_view(int N, int H, int W, int C, int pt = 0, int pb = 0, int pl = 0, int pr = 0) {
+    SplitView s; s.N = N; s.H = H; s.W = W; s.C = C; s.pt = pt; s.pl = pl; s.Hp = H + pt + pb; s.Wp = W + pl + pr;
+    s.hi = (uint16_t*)alloc(2 * s.elems() * sizeof(uint16_t)); s.mid = s.hi + s.elems();
+    return s;
   }
 };
 
@@ -79,16 +95,28 @@ struct ConvOp {
   TmaDesc tmh, tmm;                   // TMA descriptors of wh / wm
   // per-tap channel-padded copies [tc_npad][ntaps*tc_cp] for the TMA-fed kernel when Cin % 64 != 0 (null otherwise)
   const uint16_t* whp = nullptr; const uint16_t* wmp = nullptr; int tc_cp = 0;
-  // TMA-path fusion of a conv -> conv pair (ConvNeXt fc1 -> fc2): the producer's epilogue stores bf16 hi | mid halves INTO the
-  // bytes of its fp32 output buffer (same size), the consumer reads them as its pre-split input and skips the split pass.
-  // Only legal when conv_uses_tma() holds for the op; dense NHWC views (cs == C, coff == 0), 1x1 consumer.
-  bool out_split = false, in_split = false;
+  // TMA-path operand fusion (only legal when conv_uses_tma() holds for the op):
+  //  * in_sv valid  -> the input already exists as bf16 hi/mid (written by its producer); channels [in_sv_coff, +in.C) of it are
+  //                    this conv's input, `in` then only carries the shape; the split pass is skipped;
+  //  * out_sv valid -> the epilogue ALSO stores the result as bf16 hi/mid at channel offset out_sv_coff of out_sv (interior only;
+  //                    launch_split_halo() fills a reflect halo); out.p may then be null (no fp32 store);
+  //  * os_scale/os_shift/os_relu: the consumer's BN(+ReLU) prologue applied to the value before it is split (pre-activation ResNet).
+  SplitView in_sv; int in_sv_coff = 0;
+  SplitView out_sv; int out_sv_coff = 0;
+  const float* os_scale = nullptr; const float* os_shift = nullptr; int os_relu = 0;
+  // optional second K segment accumulated into the same output (FFC: conv1x1(U) + conv3x3_{l->g}(x_l)): pre-split input only.
+  // The weight rows of segment 2 follow those of segment 1 in wh/wm (K-major, both Cin multiples of 64).
+  struct Seg2 { SplitView sv; int coff = 0, C = 0, ntaps = 0, pad = PAD_ZERO; int8_t tdy[kMaxTaps] = {0}, tdx[kMaxTaps] = {0}; } seg2;
   // optional fused row statistics (vocabulary head): no tensor output, per (row, column-block) partials
   float* stat_max = nullptr; float* stat_sum = nullptr; int* stat_idx = nullptr; int stat_ld = 0;
 };
 
 void launch_conv(const ConvOp& op, cudaStream_t st);
 bool conv_uses_tma(const ConvOp& op);      // true when launch_conv() will run this op on the TMA-fed tensor-core kernel
+// fill the reflect halo of channels [coff, coff+C) of a split tensor from its interior (pad <= 3)
+void launch_split_halo(const SplitView& sv, int coff, int C, cudaStream_t st);
+// fp32 NHWC view -> split tensor (channels [coff, coff+in.C)), optional BN+ReLU prologue, halo by reflection
+void launch_split(const View& in, const SplitView& sv, int coff, const float* in_scale, const float* in_shift, int in_relu, cudaStream_t st);
 int conv_stat_blocks(const ConvOp& op);   // number of column blocks the row-stat epilogue writes per row
 void launch_rowstat_final(const float* pmax, const float* psum, const int* pidx, int rows, int nblk,
                           int* idx, float* logprob, cudaStream_t st);
@@ -232,6 +260,25 @@ struct DeviceScratch {
     return ptr[dev];
   }
 };
+
+// One-shot per-DEVICE initialisation (kernel attributes, __constant__ uploads): get_engine() hands out one context per device in
+// the same process, so "static bool done" guards would leave every device but the first uninitialised.
+struct PerDeviceOnce {
+  bool done[DeviceScratch::kMaxDev] = {};
+  bool first() {
+    int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+    MITB_CHECK(dev >= 0 && dev < DeviceScratch::kMaxDev, "device ordinal %d out of range", dev);
+    if (done[dev]) return false;
+    done[dev] = true; return true;
+  }
+};
+inline int device_sm_count() {
+  static int sms[DeviceScratch::kMaxDev] = {};
+  int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+  MITB_CHECK(dev >= 0 && dev < DeviceScratch::kMaxDev, "device ordinal %d out of range", dev);
+  if (!sms[dev]) CUDA_OK(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  return sms[dev];
+}
 
 extern unsigned long g_launch_epoch;     // bumped by EVERY kernel launch of the library (conv_tma.cu's split reuse keys on it)
 inline void count_launch() { ++g_launch_epoch; if (g_launch_counter) ++*g_launch_counter; }

@@ -338,8 +338,8 @@ void launch_attention(const float* qk, const float* v, float* out, int N, int T,
   const int threads = 256;
   const size_t smem = ((size_t)2 * T * (hd + 1) + (size_t)(threads / 32) * T + (size_t)(threads / 32) * hd) * sizeof(float);
   MITB_CHECK(smem <= 200 * 1024, "attention: sequence too long (T=%d)", T);
-  static bool attr_set = false;
-  if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ProfScope ps("attention", 4.0 * N * heads * (double)T * T * hd, 16.0 * N * T * heads * hd, st);
   attention_kernel<<<N * heads, threads, smem, st>>>(qk, v, out, T, heads, hd, 1.0f / sqrtf((float)hd));
   LAUNCH_END();

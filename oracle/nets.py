@@ -184,7 +184,7 @@ def ocr_encoder_layer(sd: SD, p: str, x, heads: int = 8):
     N, T, D = x.shape
     hd = D // heads
     z = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
-    zp = z + sinusoid_pe(T, D)
+    zp = z + sinusoid_pe(T, D).to(z.device)
     W, B = sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"]
     q = F.linear(zp, W[:D], B[:D]).view(N, T, heads, hd).transpose(1, 2)
     k = F.linear(zp, W[D:2 * D], B[D:2 * D]).view(N, T, heads, hd).transpose(1, 2)
@@ -248,10 +248,11 @@ def fourier_unit(sd: SD, p: str, x):
     """FourierUnit.forward (inpainting_lama_mpe.py:214-257): ortho rfft2, (c,re/im) channel
     interleave, 1x1 conv + BN + ReLU, ortho irfft2 back to the input size."""
     n, c, h, w = x.shape
+    x = x.float()  # :225-226 -- the FFT runs in fp32 even under autocast (no-op on the CPU fp32 path)
     f = torch.fft.rfftn(x, dim=(-2, -1), norm="ortho")
     f = torch.stack((f.real, f.imag), dim=2).reshape(n, 2 * c, h, w // 2 + 1)
     f = F.relu(_bn(sd, p + "bn.", F.conv2d(f, sd[p + "conv_layer.weight"])))
-    f = f.reshape(n, -1, 2, h, w // 2 + 1)
+    f = f.reshape(n, -1, 2, h, w // 2 + 1).float()  # :247-248
     f = torch.complex(f[:, :, 0].contiguous(), f[:, :, 1].contiguous())
     return torch.fft.irfftn(f, s=(h, w), dim=(-2, -1), norm="ortho")
 
