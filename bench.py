@@ -289,11 +289,11 @@ def ffc_block_from_launches(launch_list, prof, pages_timed, peaks, H=None, W=Non
     W = W or PAGE_W
     h, w = H // 8, W // 8
     m_sp, m_fu = h * w, h * (w // 2 + 1)
-    ffc_shapes = {(m_sp, 9 * 512, 128), (m_sp, 9 * 128, 384), (m_sp, 384, 192), (m_fu, 384, 384), (m_sp, 192, 384)}
+    # generic path: l2g 3x3 and the 1x1 out-conv are separate launches; fused path: one launch with K = 192 + 9*128
+    ffc_shapes = {(m_sp, 9 * 512, 128), (m_sp, 9 * 128, 384), (m_sp, 384, 192), (m_fu, 384, 384), (m_sp, 192, 384), (m_sp, 192 + 9 * 128, 384)}
     conv_ms = sum(x[4] for x in launch_list if (x[1], x[2], x[3]) in ffc_shapes)
-    n_conv = sum(1 for x in launch_list if (x[1], x[2], x[3]) in ffc_shapes)
-    fft_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("fft_"))
-    layers = n_conv / 5.0
+    fft_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("fft_")) + prof.get("split_halo", {}).get("ms", 0.0)
+    layers = float(sum(1 for x in launch_list if (x[1], x[2], x[3]) == (m_sp, 384, 192)))     # one spectral in-conv per FFC layer
     if layers < 1 or conv_ms <= 0:
         return None
     sec_per_layer = (conv_ms + fft_ms) / 1e3 / layers

@@ -46,6 +46,10 @@ size_t mitb_workspace_bytes(const mitb_ctx* ctx);      /* current activation wor
 /* Process-wide switch between the tcgen05 (bf16x3 split, ~1e-5 relative) and the exact-fp32 SIMT convolution kernels.
  * Default on.  The SIMT kernels are the parity anchor of the tensor-core path (tests run both). */
 int mitb_set_tensor_cores(int on);
+/* LaMa FFC layer implementation (process-wide): 0 = generic planar path (any size), 1 = fused NHWC path (operand-fused GEMMs +
+ * channel-vectorised FFT; sizes whose bottleneck h/8, w/8 are {2,3,5}-smooth) when the page is large enough that no layer
+ * needs split-K (default), 2 = fused path whenever it is capable (tests). */
+int mitb_set_ffc_mode(int mode);
 
 /* Per-launch CUDA-event timing aggregated per kernel class (for bench.py's roofline block). report() synchronises the
  * recorded events, clears them and returns a JSON object {"class": {"launches","ms","flops","bytes"}, ...} valid until
@@ -119,6 +123,10 @@ int mitb_op_layernorm(mitb_ctx* ctx, const float* x, int rows, int c, const floa
 /* torch.fft.rfftn / irfftn over (h,w), norm='ortho', planar [c,h,w] <-> [2c,h,w/2+1] (re/im interleaved per channel). */
 int mitb_op_rfft2(mitb_ctx* ctx, const float* x, int c, int h, int w, float* spec, void* stream);
 int mitb_op_irfft2(mitb_ctx* ctx, const float* spec, int c, int h, int w, float* y, void* stream);
+/* Same transforms on NHWC tensors (the layout of the fused FFC path): x [n,h,w,c] -> spec [n,h,w/2+1,2c] (c0_re,c0_im,c1_re,...);
+ * irfft adds `add` [n,h,w,c] when non-NULL (the x + fu(x) residual, inpainting_lama_mpe.py:305).  h, w {2,3,5}-smooth, c even. */
+int mitb_op_rfft2_nhwc(mitb_ctx* ctx, const float* x, int n, int h, int w, int c, float* spec, void* stream);
+int mitb_op_irfft2_nhwc(mitb_ctx* ctx, const float* spec, const float* add, int n, int h, int w, int c, float* y, void* stream);
 /* Multi-head attention core: qk [n*t, 2*d] (q then k, already projected), v [n*t, d] -> out [n*t, d]. */
 int mitb_op_attention(mitb_ctx* ctx, const float* qk, const float* v, int n, int t, int heads, int head_dim,
                       float* out, void* stream);

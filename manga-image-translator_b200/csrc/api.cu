@@ -70,6 +70,7 @@ long long mitb_launch_count(const mitb_ctx* ctx) { return ctx ? ctx->c.launches 
 size_t mitb_workspace_bytes(const mitb_ctx* ctx) { return ctx ? ctx->c.ws.cap : 0; }
 
 int mitb_set_tensor_cores(int on) { conv_tc_set_enabled(on != 0); return 0; }
+int mitb_set_ffc_mode(int mode) { lama_set_ffc_mode(mode); return 0; }
 
 int mitb_profile_enable(mitb_ctx* ctx, int on) {
   API_BEGIN(ctx)
@@ -297,6 +298,34 @@ int mitb_op_irfft2(mitb_ctx* ctx, const float* spec, int c, int h, int w, float*
   run_with_workspace(ctx->c, st, [&](Exec& e) {
     float2* tmp = (float2*)e.ws().alloc((size_t)c * h * w2 * sizeof(float2));
     if (!e.dry) launch_irfft2(sp, out, nullptr, tmp, st);
+  });
+  CUDA_OK(cudaStreamSynchronize(st));
+  API_END(ctx)
+}
+
+int mitb_op_rfft2_nhwc(mitb_ctx* ctx, const float* x, int n, int h, int w, int c, float* spec, void* stream) {
+  API_BEGIN(ctx)
+  cudaStream_t st = (cudaStream_t)stream;
+  const int w2 = w / 2 + 1;
+  View in; in.p = const_cast<float*>(x); in.N = n; in.H = h; in.W = w; in.C = c; in.cs = c;
+  run_with_workspace(ctx->c, st, [&](Exec& e) {
+    float2* tmp = (float2*)e.ws().alloc((size_t)n * c * h * w2 * sizeof(float2));
+    if (!e.dry) launch_rfft2_nhwc(in, nullptr, spec, tmp, st);
+  });
+  CUDA_OK(cudaStreamSynchronize(st));
+  API_END(ctx)
+}
+
+int mitb_op_irfft2_nhwc(mitb_ctx* ctx, const float* spec, const float* add, int n, int h, int w, int c, float* y, void* stream) {
+  API_BEGIN(ctx)
+  cudaStream_t st = (cudaStream_t)stream;
+  const int w2 = w / 2 + 1;
+  View sp; sp.p = const_cast<float*>(spec); sp.N = n; sp.H = h; sp.W = w2; sp.C = 2 * c; sp.cs = 2 * c;
+  View out; out.p = y; out.N = n; out.H = h; out.W = w; out.C = c; out.cs = c;
+  View res = out; res.p = const_cast<float*>(add);
+  run_with_workspace(ctx->c, st, [&](Exec& e) {
+    float2* tmp = (float2*)e.ws().alloc((size_t)n * c * h * w2 * sizeof(float2));
+    if (!e.dry) launch_irfft2_nhwc(sp, out, nullptr, 0, add ? &res : nullptr, tmp, st);
   });
   CUDA_OK(cudaStreamSynchronize(st));
   API_END(ctx)

@@ -461,8 +461,9 @@ void launch_conv(const ConvOp& op, cudaStream_t st) {
   if (p.M == 0) return;
   const int Cout = op.out.C;
   // algorithmic work of this launch: 2*M*K*Cout flops; bytes = input view + weights + output (+ fused residual reads)
+  if (op.seg2.sv.valid()) p.K += op.seg2.ntaps * op.seg2.C;          // second K segment of an operand-fused launch
   const double flops = 2.0 * p.M * (double)p.K * Cout;
-  const double bytes = 4.0 * ((double)op.in.pixels() * op.in.C + (double)p.K * Cout +
+  const double bytes = 4.0 * ((double)op.in.pixels() * op.in.C + (op.seg2.sv.valid() ? (double)op.in.pixels() * op.seg2.C : 0.0) + (double)p.K * Cout +
                               (double)p.M * Cout * ((op.stat_max ? 0 : 1) + (op.add0.p ? 1 : 0) + (op.add1.p ? 1 : 0)));
   if (conv_thin_supported(op)) { ProfScope ps("conv7_thin", flops, bytes, st, p.M, p.K, Cout); launch_conv_thin(op, st); return; }
   if (conv_tc_supported(op)) { ProfScope ps(op.stat_max ? "conv_tc_rowstat" : "conv_tc", flops, bytes, st, p.M, p.K, Cout); launch_conv_tc(op, st); return; }

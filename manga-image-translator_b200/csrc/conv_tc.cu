@@ -641,6 +641,7 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st);
 
 static bool tma_dispatch(const ConvOp& op) {
   if (!conv_tma_supported(op)) return false;
+  if (op.in_sv.valid() || op.out_sv.valid() || op.seg2.sv.valid()) return true;   // operand-fused ops exist only on the TMA path
   // TMA-fed kernel unless the layer is so small that it needs split-K
   const int sms = device_sm_count();
   const long Mrows = (long)op.in.N * op.Ho * op.Wo;
@@ -648,6 +649,7 @@ static bool tma_dispatch(const ConvOp& op) {
   const bool would_split = !op.stat_max && tiles * 2 <= sms && op.tc_kpad / TC_BK >= 16;
   return !would_split;
 }
+bool conv_tma_capable(const ConvOp& op) { return op.out.C > 4 && conv_tc_supported(op) && conv_tma_supported(op); }
 bool conv_uses_tma(const ConvOp& op) { return op.out.C > 4 && conv_tc_supported(op) && tma_dispatch(op); }
 
 void launch_conv_tc(const ConvOp& op, cudaStream_t st) {

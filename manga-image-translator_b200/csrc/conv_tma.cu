@@ -119,13 +119,86 @@ __device__ __forceinline__ void tma_kblock(uint32_t bar, uint32_t bytes, uint32_
       "r"(c), "r"(x), "r"(y), "r"(n), "r"(k), "r"(n0) : "memory");
 }
 
-template <int ACT>
+// ---- CTA-pair (cta_group::2) variants: one 256 x BN tile per pair of SMs, each CTA stages its own 128 rows of A and HALF of B
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_kblock_x3_pair(uint32_t tmem_d, uint64_t dah, uint64_t dam, uint64_t dbh, uint64_t dbm, uint32_t idesc,
+                                                    uint32_t acc_first, uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe, pa, pt;\n"
+      ".reg .b64 ah, am, bh, bm;\n"
+      ".reg .b16 msk;\n"
+      "mov.b16 msk, 3;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 pa, %6, 0;\n"
+      "setp.eq.u32 pt, %5, %5;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %3, %5, pa;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %4, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %2, %3, %5, pt;\n"
+      "add.s64 ah, %1, 2;\n add.s64 am, %2, 2;\n add.s64 bh, %3, 2;\n add.s64 bm, %4, 2;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bh, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bm, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], am, bh, %5, pt;\n"
+      "add.s64 ah, %1, 4;\n add.s64 am, %2, 4;\n add.s64 bh, %3, 4;\n add.s64 bm, %4, 4;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bh, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bm, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], am, bh, %5, pt;\n"
+      "add.s64 ah, %1, 6;\n add.s64 am, %2, 6;\n add.s64 bh, %3, 6;\n add.s64 bm, %4, 6;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bh, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], ah, bm, %5, pt;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], am, bh, %5, pt;\n"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], msk;\n"
+      "}\n" ::"r"(tmem_d), "l"(dah), "l"(dam), "l"(dbh), "l"(dbm), "r"(idesc), "r"(acc_first), "r"(empty_bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect_pair(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      ".reg .b16 msk;\n"
+      "mov.b16 msk, 3;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], msk;\n"
+      "}\n" ::"r"(bar) : "memory");
+}
+// expect_tx on the LEADER's full barrier (cluster address) + this CTA's four operand boxes completing on it
+__device__ __forceinline__ void tma_kblock_pair(uint32_t lead_bar, uint32_t bytes, uint32_t a_hi, uint32_t a_mid, uint32_t b_hi, uint32_t b_mid,
+                                                const CUtensorMap* ta_hi, const CUtensorMap* ta_mid, const CUtensorMap* tb_hi,
+                                                const CUtensorMap* tb_mid, int c, int x, int y, int n, int k, int n0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;\n"
+      "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%6, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%7, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%8, {%14, %15}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%9, {%14, %15}], [%0];\n"
+      "}\n" ::"r"(lead_bar), "r"(bytes), "r"(a_hi), "r"(a_mid), "r"(b_hi), "r"(b_mid), "l"(ta_hi), "l"(ta_mid), "l"(tb_hi), "l"(tb_mid),
+      "r"(c), "r"(x), "r"(y), "r"(n), "r"(k), "r"(n0) : "memory");
+}
+
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: clusters of two CTAs (one SM pair) share a 256 x BN tile through tcgen05 cta_group::2:
+// CTA r owns rows [128 r, 128 r + 128) (its own activation boxes, its own TMEM accumulator, its own epilogue) and stages only rows
+// [r BN/2, (r+1) BN/2) of the weight tile, so the weight bytes each SM pulls from L2 halve - these GEMMs are bound by the ~42 B/clk
+// an SM gets from L2 (hi + mid operands), not by the tensor pipe.  The leader (rank 0) issues every MMA; full barriers live in the
+// leader and collect both CTAs' TMA bytes, tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both CTAs.
+template <int ACT, int CG>
 __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int BN = p.BN, S = p.stages;
-  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)BN * 128;
+  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)(BN / CG) * 128;         // CG = 2: half of the weight tile per CTA
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t crank = CG == 2 ? cluster_rank() : 0u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   float* estage = reinterpret_cast<float*>(bars + 2 * S + 6);          // [TM_EWARPS][32 rows][20 floats] epilogue transpose buffer
@@ -140,23 +213,27 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
   const int nkb = p.nkb;
   const int bw = 1 << p.bw_log2, bh = TC_BM >> p.bw_log2;
   const int mt = p.N * p.tiles_y * p.tiles_x, nt = p.npad / BN;
-  const int total_tiles = mt * nt;
+  const int total_tiles = ((mt + CG - 1) / CG) * nt;                 // CG = 2: pair tiles (two consecutive 128-row tiles)
+  const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t acc_stride = (uint32_t)(p.tmem_cols >> 1);
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TM_EWARPS); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), CG * TM_EWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TM_MMAWARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();             // peers must see initialised barriers before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile t -> (image, patch origin, N tile); N fastest so CTAs running together share the activation boxes in L2
+  // tile t -> (image, patch origin, N tile); N fastest so CTAs running together share the activation boxes in L2.
+  // A pair's second CTA may get an m-tile past the end (odd tile count): nimg == N there, TMA fills zeros, stores are masked.
   auto decode = [&](int t, int& nimg, int& oy0, int& ox0, int& n0) {
-    const int mtile = t / nt; n0 = (t - mtile * nt) * BN;
+    const int mpair = t / nt; n0 = (t - mpair * nt) * BN;
+    const int mtile = CG == 2 ? 2 * mpair + (int)crank : mpair;
     const int per_img = p.tiles_y * p.tiles_x;
     nimg = mtile / per_img; const int r = mtile - nimg * per_img;
     const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
@@ -173,16 +250,17 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     auto row_pixel = [&](int r, int nimg_t, int oy0, int ox0, int& nimg, int& oy, int& ox) -> bool {
       if (p.lin) {
         const int m = ox0 + r;
-        if (m >= p.M) return false;
+        if (m >= p.M || nimg_t >= p.N) return false;
         nimg = m / HoWo; const int pp = m - nimg * HoWo;
         oy = pp / p.Wo; ox = pp - oy * p.Wo;
         return true;
       }
       nimg = nimg_t; oy = oy0 + (r >> p.bw_log2); ox = ox0 + (r & (bw - 1));
-      return oy < p.Ho && ox < p.Wo;
+      return oy < p.Ho && ox < p.Wo && nimg < p.N;
     };
     int lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    const uint32_t tempty_lead0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : tempty_bar(0);   // the MMA issuer (leader) owns "accumulator drained"
+    for (int t = tile_first; t < total_tiles; t += tile_step, ++lt) {
       int nimg_t, oy0, ox0, n0;
       decode(t, nimg_t, oy0, ox0, n0);
       const int buf = lt & 1;
@@ -353,7 +431,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));        // accumulator drained -> the MMA warp may overwrite it
+      if (lane == 0) {                                     // accumulator drained -> the MMA warp may overwrite it
+        if (CG == 2) mbar_arrive_cluster(tempty_lead0 + 8u * buf); else mbar_arrive(tempty_bar(buf));
+      }
     }
   } else if (warp == TM_MMAWARP) {
     // =========================== MMA issuer ===========================
@@ -361,9 +441,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     // uniform registers and a K block costs ~40 SASS instructions.  With the loop inside `if (lane == 0)` the compiler
     // moved every operand of every tcgen05.mma through R2UR/ELECT sequences: ~350 dependent instructions per K block on this
     // single warp, i.e. ~1400 cycles against the 768-cycle tensor floor of a 128x128x64 bf16x3 block (ncu, r01).
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG * TC_BM) >> 4) << 24);
     int s = 0; uint32_t ph = 0; int lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    if (CG == 1 || crank == 0)
+    for (int t = tile_first; t < total_tiles; t += tile_step, ++lt) {
       const int buf = lt & 1;
       mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
       tc_fence_after();
@@ -373,17 +454,22 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         tc_fence_after();
         const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
         const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
-        umma_kblock_x3(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
-                       kb > 0 ? 1u : 0u, empty_bar(s));            // 12 MMAs + commit -> frees the stage when they retire
+        if (CG == 2)
+          umma_kblock_x3_pair(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
+                              kb > 0 ? 1u : 0u, empty_bar(s));       // 12 pair MMAs + commit multicast -> frees the stage in both CTAs
+        else
+          umma_kblock_x3(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
+                         kb > 0 ? 1u : 0u, empty_bar(s));            // 12 MMAs + commit -> frees the stage when they retire
         if (++s == S) { s = 0; ph ^= 1u; }
       }
-      umma_commit_elect(tfull_bar(buf));      // accumulator of this tile complete -> epilogue
+      if (CG == 2) umma_commit_elect_pair(tfull_bar(buf)); else umma_commit_elect(tfull_bar(buf));      // accumulator complete -> epilogue(s)
     }
     __syncwarp();
   } else if (warp == TM_TMAWARP) {
     // =========================== operand loader: four TMA boxes per K block (whole warp loops, one elected lane issues) =====
     int s = 0; uint32_t ph = 1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const uint32_t full_lead0 = CG == 2 ? mapa_rank(full_bar(0), 0) : full_bar(0);
+    for (int t = tile_first; t < total_tiles; t += tile_step) {
       int nimg, oy0, ox0, n0;
       decode(t, nimg, oy0, ox0, n0);
       int kb = 0;
@@ -396,8 +482,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
           const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
           const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
           const int x = ox0 * p.sx + sp.tdx[tap], y = oy0 * p.sy + sp.tdy[tap];
-          tma_kblock(full_bar(s), 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &sp.ta_hi, &sp.ta_mid, &p.tb_hi, &p.tb_mid,
-                     sp.c0 + cb * TC_BK, x, y, nimg, kb * TC_BK, n0);
+          if (CG == 2)
+            tma_kblock_pair(full_lead0 + 8u * s, 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &sp.ta_hi, &sp.ta_mid, &p.tb_hi, &p.tb_mid,
+                            sp.c0 + cb * TC_BK, x, y, nimg, kb * TC_BK, n0 + (int)crank * (BN / 2));
+          else
+            tma_kblock(full_bar(s), 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &sp.ta_hi, &sp.ta_mid, &p.tb_hi, &p.tb_mid,
+                       sp.c0 + cb * TC_BK, x, y, nimg, kb * TC_BK, n0);
           if (++cb == sp.cblks) { cb = 0; ++tap; }
           if (++s == S) { s = 0; ph ^= 1u; }
         }
@@ -406,7 +496,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     __syncwarp();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();             // pair: nobody leaves while the peer may still signal / read its smem
   if (warp == TM_MMAWARP) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
@@ -522,20 +612,29 @@ void make_w_tmap(CUtensorMap* m, const uint16_t* base, int kdim, int rows, int b
 
 // N tile width: minimise waves x tile time.  Tile time per K block = max(tensor floor 6*bn cycles, operand bytes over the
 // SM's share of L2 bandwidth ~42 B/clk); candidates split Cout into j equal tiles rounded up to 16.
-int choose_bn(int Cout, long mtiles, int nkb, int sms) {
+// cg = 2: tiles are 256-row pair tiles on sms/2 SM pairs, each CTA stages half of the weight tile.
+int choose_bn(int Cout, long mtiles, int nkb, int sms, int cg, double* cost_out) {
   double best = 1e30; int best_bn = 16;
+  const long units = sms / cg, mt = (mtiles + cg - 1) / cg;
   for (int j = 1; j <= 16; ++j) {
     int bn = ((Cout + j - 1) / j + 15) & ~15;
     if (bn > 256) continue;
     if (bn < 16) bn = 16;
     const long nt = (Cout + bn - 1) / bn;
-    const long waves = (mtiles * nt + sms - 1) / sms;
-    const double mma = 6.0 * bn, l2 = (32768.0 + 256.0 * bn) / 42.0;
+    const long waves = (mt * nt + units - 1) / units;
+    const double mma = 6.0 * bn, l2 = (32768.0 + 256.0 * bn / cg) / 42.0;
     const double tile = nkb * (mma > l2 ? mma : l2) + 40.0 * bn + 600.0;
     const double cost = waves * tile;
     if (cost < best * 0.999) { best = cost; best_bn = bn; }
   }
+  if (cost_out) *cost_out = best;
   return best_bn;
+}
+
+int pair_mode_env() {        // MITB_CG2: 0 never, 1 when the cost model prefers it (default), 2 whenever legal
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MITB_CG2"); v = e ? atoi(e) : 1; }
+  return v;
 }
 
 bool g_tma_enabled = true;
@@ -628,7 +727,11 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     sv = op.in_sv; sv_coff = op.in_sv_coff;
     MITB_CHECK(sv.N == N && sv.H == H && sv.W == W && sv_coff + C <= sv.C && sv.C % 8 == 0 && sv_coff % 8 == 0, "tma conv: in_sv shape mismatch");
     MITB_CHECK(sv.pt >= pt && sv.pl >= pl && sv.Hp - sv.H - sv.pt >= pb && sv.Wp - sv.W - sv.pl >= pr, "tma conv: in_sv halo too small");
-    MITB_CHECK(op.pad == PAD_REFLECT || (sv.Hp == sv.H && sv.Wp == sv.W), "tma conv: zero padding needs a halo-free in_sv");
+    if (op.pad != PAD_REFLECT && (sv.Hp != sv.H || sv.Wp != sv.W)) {      // zero padding over a halo'd tensor: only if no tap leaves the image
+      int zt, zb, zl, zr;
+      conv_halo(op.tdy, op.tdx, op.ntaps, PAD_REFLECT, H, W, op.Ho, op.Wo, op.sy, op.sx, zt, zb, zl, zr);
+      MITB_CHECK(zt == 0 && zb == 0 && zl == 0 && zr == 0, "tma conv: zero padding needs a halo-free in_sv");
+    }
     MITB_CHECK(!op.in_scale, "tma conv: in_sv carries its prologue already");
     MITB_CHECK(!padded_w || sv_coff + C == sv.C, "tma conv: Cin %% 64 != 0 needs the slice to end at the tensor's last channel");
   } else {
@@ -654,11 +757,11 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   const int num_sms = device_sm_count();
   static PerDeviceOnce tma_attr;
   if (tma_attr.first()) {
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define MITB_TMA_ATTR(A) \
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    CUDA_OK(cudaFuncSetAttribute(conv_tma_kernel<A, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MITB_TMA_ATTR(ACT_NONE) MITB_TMA_ATTR(ACT_RELU) MITB_TMA_ATTR(ACT_GELU) MITB_TMA_ATTR(ACT_SILU) MITB_TMA_ATTR(-1)
+#undef MITB_TMA_ATTR
   }
 
   TmaParams p;
@@ -694,7 +797,10 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     int qt, qb, ql, qr;
     conv_halo(s2.tdy, s2.tdx, s2.ntaps, s2.pad, s2.sv.H, s2.sv.W, op.Ho, op.Wo, 1, 1, qt, qb, ql, qr);
     MITB_CHECK(s2.sv.pt >= qt && s2.sv.pl >= ql && s2.sv.Hp - s2.sv.H - s2.sv.pt >= qb && s2.sv.Wp - s2.sv.W - s2.sv.pl >= qr, "tma conv: seg2 halo too small");
-    MITB_CHECK(s2.pad == PAD_REFLECT || (s2.sv.Hp == s2.sv.H && s2.sv.Wp == s2.sv.W), "tma conv: zero padding needs a halo-free seg2");
+    if (s2.pad != PAD_REFLECT && (s2.sv.Hp != s2.sv.H || s2.sv.Wp != s2.sv.W)) {
+      conv_halo(s2.tdy, s2.tdx, s2.ntaps, PAD_REFLECT, s2.sv.H, s2.sv.W, op.Ho, op.Wo, 1, 1, qt, qb, ql, qr);
+      MITB_CHECK(qt == 0 && qb == 0 && ql == 0 && qr == 0, "tma conv: zero padding needs a halo-free seg2");
+    }
     p.seg[1].ntaps = s2.ntaps; p.seg[1].cblks = s2.C / TC_BK; p.seg[1].c0 = s2.coff;
     for (int t = 0; t < s2.ntaps; ++t) { p.seg[1].tdy[t] = (int8_t)(s2.tdy[t] + s2.sv.pt); p.seg[1].tdx[t] = (int8_t)(s2.tdx[t] + s2.sv.pl); }
     make_act_tmap(&p.seg[1].ta_hi, s2.sv.hi, N, s2.sv.Hp, s2.sv.Wp, s2.sv.C, bw, bh, 1, 1);
@@ -705,11 +811,20 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   p.nkb = kdim / TC_BK;
   // ---- N tile: fixed by the row-stat layout for the vocabulary head, otherwise chosen per launch against wave quantisation
   const long mtiles = (long)p.N * p.tiles_y * p.tiles_x;
-  p.BN = op.stat_max ? op.tc_bn : choose_bn(op.out.C, mtiles, p.nkb, num_sms);
+  int cg = 1;
+  if (op.stat_max) p.BN = op.tc_bn;
+  else {
+    double c1 = 0, c2 = 0;
+    const int bn1 = choose_bn(op.out.C, mtiles, p.nkb, num_sms, 1, &c1);
+    const int bn2 = choose_bn(op.out.C, mtiles, p.nkb, num_sms, 2, &c2);
+    const int mode = pair_mode_env();
+    // CTA pairs (cta_group::2) when the per-SM L2 budget, not the tensor pipe, bounds the tile and there are enough pair tiles
+    if (mtiles >= 2 && num_sms % 2 == 0 && (mode >= 2 || (mode == 1 && c2 < 0.97 * c1))) { cg = 2; p.BN = bn2; } else p.BN = bn1;
+  }
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tma conv: bad BN %d", p.BN);
   p.npad = (op.out.C + p.BN - 1) / p.BN * p.BN;
-  make_w_tmap(&p.tb_hi, padded_w ? op.whp : op.wh, kdim, op.tc_npad, p.BN);
-  make_w_tmap(&p.tb_mid, padded_w ? op.wmp : op.wm, kdim, op.tc_npad, p.BN);
+  make_w_tmap(&p.tb_hi, padded_w ? op.whp : op.wh, kdim, op.tc_npad, p.BN / cg);
+  make_w_tmap(&p.tb_mid, padded_w ? op.wmp : op.wm, kdim, op.tc_npad, p.BN / cg);
   p.out = op.out.p; p.oH = op.out.H; p.oW = op.out.W; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C;
   p.out_planar = op.out.planar; p.oy_mul = op.oy_mul; p.oy_add = op.oy_add; p.ox_mul = op.ox_mul; p.ox_add = op.ox_add;
   p.add0 = op.add0.p; p.add0_cs = op.add0.cs; p.add0_coff = op.add0.coff; p.add0_planar = op.add0.planar;
@@ -728,25 +843,34 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     p.os_hi = o.hi; p.os_mid = o.mid; p.os_pitch = o.C; p.os_coff = op.out_sv_coff; p.os_Hp = o.Hp; p.os_Wp = o.Wp; p.os_pt = o.pt; p.os_pl = o.pl;
     p.os_scale = op.os_scale; p.os_shift = op.os_shift; p.os_relu = op.os_relu;
     if (!op.out.p) { p.oH = op.Ho; p.oW = op.Wo; }
-  } else MITB_CHECK(op.out.p, "tma conv: no output");
+  } else MITB_CHECK(op.out.p || op.stat_max, "tma conv: no output");
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;
-  const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)p.BN * 128;
+  const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)(p.BN / cg) * 128;
   const size_t epi_bytes = (size_t)TM_EWARPS * 32 * 20 * sizeof(float);
   int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes); if (stages > 6) stages = 6;
   MITB_CHECK(stages >= 2, "tma conv: tile does not fit shared memory");
   p.stages = stages;
   const size_t smem = stages * stage_bytes + (2 * stages + 6) * 8 + epi_bytes + 1024;
-  const long total_tiles = mtiles * (p.npad / p.BN);
-  const int grid = total_tiles < num_sms ? (int)total_tiles : num_sms;
+  const long total_tiles = ((mtiles + cg - 1) / cg) * (p.npad / p.BN);
+  const long units = num_sms / cg;
+  const int grid = (int)(total_tiles < units ? total_tiles : units) * cg;
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+#define MITB_TMA_LAUNCH(A) \
+  do { if (cg == 2) CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tma_kernel<A, 2>, p)); else CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tma_kernel<A, 1>, p)); } while (0)
   switch (op.stat_max ? ACT_NONE : p.act) {
-    case ACT_NONE: conv_tma_kernel<ACT_NONE><<<grid, TM_THREADS, smem, st>>>(p); break;
-    case ACT_RELU: conv_tma_kernel<ACT_RELU><<<grid, TM_THREADS, smem, st>>>(p); break;
-    case ACT_GELU: conv_tma_kernel<ACT_GELU><<<grid, TM_THREADS, smem, st>>>(p); break;
-    case ACT_SILU: conv_tma_kernel<ACT_SILU><<<grid, TM_THREADS, smem, st>>>(p); break;
-    default: conv_tma_kernel<-1><<<grid, TM_THREADS, smem, st>>>(p); break;
+    case ACT_NONE: MITB_TMA_LAUNCH(ACT_NONE); break;
+    case ACT_RELU: MITB_TMA_LAUNCH(ACT_RELU); break;
+    case ACT_GELU: MITB_TMA_LAUNCH(ACT_GELU); break;
+    case ACT_SILU: MITB_TMA_LAUNCH(ACT_SILU); break;
+    default: MITB_TMA_LAUNCH(-1); break;
   }
+#undef MITB_TMA_LAUNCH
   count_launch();
   g_key_epoch = g_launch_epoch;
   CUDA_OK(cudaGetLastError());

@@ -114,28 +114,29 @@ static void run_block(Exec& e, const CnBlock& b, const View& x, const View& out)
   Arena& ws = e.ws();
   const size_t mk = ws.mark();
   View t = ws.view(x.N, x.H, x.W, b.cout);
-  if (b.dense) {
-    ConvOp op = Exec::op_from(b.dense_w, x, t);
-    e.conv(op);
-    e.layernorm(t, t, b.ln_w, b.ln_b, kLnEps);
-  } else {
-    e.dwconv7_ln(x, t, b.dw_w, b.dw_b, b.ln_w, b.ln_b, kLnEps);
-  }
   View hid = ws.view(x.N, x.H, x.W, 4 * b.cout);
+  ConvOp op1 = Exec::op_from(b.fc1, t, hid); op1.act = ACT_GELU;
+  ConvOp op2 = Exec::op_from(b.fc2, hid, out); op2.mul1 = b.gamma;
+  // Operand fusion along LN -> fc1 -> GELU -> fc2 when both GEMMs run on the TMA-fed kernel: the LayerNorm kernel and fc1's
+  // epilogue store the NEXT GEMM's bf16 hi/mid operands into the bytes of `t` / `hid` (same size as the fp32 tensors they
+  // replace), so neither GEMM needs a split pass and the normalised / hidden activations never exist in fp32.
+  const bool fuse = conv_tma_capable(op1) && conv_tma_capable(op2) && conv_uses_tma(op1) && conv_uses_tma(op2);
+  SplitView ts, hs;
+  if (fuse) { ts = Exec::alias_split(t); hs = Exec::alias_split(hid); op1.in_sv = ts; op1.out_sv = hs; op1.out.p = nullptr; op2.in_sv = hs; }
+  if (b.dense) {
+    View d = fuse ? ws.view(x.N, x.H, x.W, b.cout) : t;        // the dense conv's fp32 result (LN input); `t` holds the operands
+    ConvOp op = Exec::op_from(b.dense_w, x, d);
+    e.conv(op);
+    e.layernorm(d, t, b.ln_w, b.ln_b, kLnEps, nullptr, nullptr, 1, fuse ? &ts : nullptr);
+  } else {
+    e.dwconv7_ln(x, t, b.dw_w, b.dw_b, b.ln_w, b.ln_b, kLnEps, fuse ? &ts : nullptr);
+  }
   View sc = x;
   if (b.has_sc) {
     sc = ws.view(x.N, x.H, x.W, b.cout);
     ConvOp op = Exec::op_from(b.sc, x, sc); e.conv(op);
   }
-  ConvOp op1 = Exec::op_from(b.fc1, t, hid); op1.act = ACT_GELU;
-  ConvOp op2 = Exec::op_from(b.fc2, hid, out); op2.mul1 = b.gamma; op2.add1 = sc;
-  // fc1 -> GELU -> fc2: when both run on the TMA-fed kernel, fc1 stores fc2's bf16 hi/mid operands straight into `hid`
-  // (same bytes as the fp32 tensor it replaces) and fc2 skips its split pass
-  if (conv_uses_tma(op1) && conv_uses_tma(op2)) {
-    SplitView hs; hs.N = hid.N; hs.H = hs.Hp = hid.H; hs.W = hs.Wp = hid.W; hs.C = hid.C;
-    hs.hi = reinterpret_cast<uint16_t*>(hid.p); hs.mid = hs.hi + hs.elems();
-    op1.out_sv = hs; op1.out.p = nullptr; op2.in_sv = hs;
-  }
+  op2.add1 = sc;
   e.conv(op1);
   e.conv(op2);
   ws.release(mk);
@@ -148,9 +149,13 @@ static void run_stage(Exec& e, const CnStage& s, const View& x, const View& out)
   View cur = x;
   if (s.has_ds) {
     View t = ws.view(x.N, x.H, x.W, x.C);
-    e.layernorm(x, t, s.ds_ln_w, s.ds_ln_b, kLnEps);
     View d = ws.view(x.N, x.H / 2, x.W / 2, s.ds.Cout);
-    ConvOp op = Exec::op_from(s.ds, t, d, 2); e.conv(op);
+    ConvOp op = Exec::op_from(s.ds, t, d, 2);
+    // LayerNorm2d -> 2x2 stride-2 conv: the LN kernel writes the conv's bf16 hi/mid operands directly (no split pass)
+    SplitView ts;
+    if (conv_tma_capable(op) && conv_uses_tma(op)) { ts = Exec::alias_split(t); op.in_sv = ts; }
+    e.layernorm(x, t, s.ds_ln_w, s.ds_ln_b, kLnEps, nullptr, nullptr, 1, ts.valid() ? &ts : nullptr);
+    e.conv(op);
     cur = d;
   }
   for (size_t k = 0; k < s.blocks.size(); ++k) run_block(e, s.blocks[k], cur, k + 1 == s.blocks.size() ? out : cur);

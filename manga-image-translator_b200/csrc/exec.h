@@ -32,9 +32,15 @@ struct Exec {
     }
   }
   void layernorm(const View& in, const View& out, const float* w, const float* b, float eps, const float* pe = nullptr,
-                 const View* out2 = nullptr, int T = 1) { if (!dry) launch_layernorm(in, out, w, b, eps, pe, out2, T, st); }
+                 const View* out2 = nullptr, int T = 1, const SplitView* osv = nullptr) { if (!dry) launch_layernorm(in, out, w, b, eps, pe, out2, T, st, osv); }
   void dwconv7_ln(const View& in, const View& out, const float* wdw, const float* bdw, const float* lnw, const float* lnb,
-                  float eps) { if (!dry) launch_dwconv7_ln(in, out, wdw, bdw, lnw, lnb, eps, st); }
+                  float eps, const SplitView* osv = nullptr) { if (!dry) launch_dwconv7_ln(in, out, wdw, bdw, lnw, lnb, eps, st, osv); }
+  // bf16 hi/mid operand tensor living in the bytes of a dense fp32 view of the same shape (2 x 2 bytes per element)
+  static SplitView alias_split(const View& v) {
+    SplitView s; s.N = v.N; s.H = s.Hp = v.H; s.W = s.Wp = v.W; s.C = v.C;
+    s.hi = reinterpret_cast<uint16_t*>(v.p); s.mid = s.hi + s.elems();
+    return s;
+  }
   void avgpool(const View& in, const View& out, int mode) { if (!dry) launch_avgpool(in, out, mode, st); }
 };
 

@@ -117,6 +117,18 @@ ConvW Loader::conv_padcin(const std::string& wname, int pad, int cin_pad) {
   return cw;
 }
 
+ConvW Loader::cat_k(const ConvW& a, const ConvW& b) {
+  MITB_CHECK(a.Cout == b.Cout && a.ldw == b.ldw && a.Cin % 64 == 0 && b.Cin % 64 == 0, "cat_k: incompatible weights");
+  const int Ka = a.ntaps * a.Cin, Kb = b.ntaps * b.Cin;
+  ConvW cw; cw.Cin = Ka + Kb; cw.Cout = a.Cout; cw.ntaps = 1; cw.ldw = a.ldw;
+  float* dst = blob.alloc_f((size_t)(Ka + Kb) * cw.ldw);
+  CUDA_OK(cudaMemcpyAsync(dst, a.w, (size_t)Ka * cw.ldw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dst + (size_t)Ka * cw.ldw, b.w, (size_t)Kb * cw.ldw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  cw.w = dst;
+  conv_tc_prepare(cw, blob, st);
+  return cw;
+}
+
 const float* Loader::vec(const std::string& name) { return vec_tiled(name, 1); }
 
 const float* Loader::vec_tiled(const std::string& name, int reps) {

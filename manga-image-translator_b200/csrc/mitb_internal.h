@@ -113,6 +113,7 @@ struct ConvOp {
 
 void launch_conv(const ConvOp& op, cudaStream_t st);
 bool conv_uses_tma(const ConvOp& op);      // true when launch_conv() will run this op on the TMA-fed tensor-core kernel
+bool conv_tma_capable(const ConvOp& op);   // the op CAN run there (launch_conv() does so whenever in_sv / out_sv / seg2 is set)
 // fill the reflect halo of channels [coff, coff+C) of a split tensor from its interior (pad <= 3)
 void launch_split_halo(const SplitView& sv, int coff, int C, cudaStream_t st);
 // fp32 NHWC view -> split tensor (channels [coff, coff+in.C)), optional BN+ReLU prologue, halo by reflection
@@ -126,10 +127,11 @@ void launch_repack(float* dst, const float* src, int Cout, int Cin, int ntaps, c
                    long s_co, long s_c, long s_ky, long s_kx, int ldw, cudaStream_t st);
 
 // ------------------------------------------------------------------ other kernels
+// osv (optional): write the result as the consumer conv's bf16 hi/mid operands (dense, halo-free) INSTEAD of fp32 `out`
 void launch_layernorm(const View& in, const View& out, const float* w, const float* b, float eps,
-                      const float* pe /*[T,C] added into out2*/, const View* out2, int T, cudaStream_t st);
+                      const float* pe /*[T,C] added into out2*/, const View* out2, int T, cudaStream_t st, const SplitView* osv = nullptr);
 void launch_dwconv7_ln(const View& in, const View& out, const float* wdw /*[49][C]*/, const float* bdw,
-                       const float* lnw, const float* lnb, float eps, cudaStream_t st);
+                       const float* lnw, const float* lnb, float eps, cudaStream_t st, const SplitView* osv = nullptr);
 void launch_avgpool(const View& in, const View& out, int mode /*0: 2x2s2, 1: k2 s(2,1) p(0,1)*/, cudaStream_t st);
 void launch_convT4_c1(const View& in, const float* w, const float* bias, int act, const View& out, cudaStream_t st);
 void launch_nchw_to_nhwc(const float* src, int N, int C, int H, int W, const View& dst, cudaStream_t st);
@@ -154,6 +156,11 @@ void launch_rfft2(const View& in /*planar [C][h][w]*/, const View& spec /*planar
                   cudaStream_t st);
 void launch_irfft2(const View& spec, const View& out, const View* add /*planar, optional residual*/, float2* tmp,
                    cudaStream_t st);
+
+// channel-vectorised NHWC variant (fft_nhwc.cu): h, w must be {2,3,5}-smooth and <= 512, C even
+bool fft_nhwc_supported(int h, int w, int C);
+void launch_rfft2_nhwc(const View& in, const SplitView* spec_sv, float* spec_f, float2* T, cudaStream_t st);
+void launch_irfft2_nhwc(const View& spec, const View& out, const SplitView* out_sv, int sv_coff, const View* add, float2* T, cudaStream_t st);
 
 // ------------------------------------------------------------------ weights
 struct Weights {
@@ -196,6 +203,8 @@ struct Loader {                        // helpers used by the network builders a
   ConvW linear_rows(const std::string& wname, int r0, int nr);
   const float* vec_slice(const std::string& name, int off, int n);
   ConvW conv_padcin(const std::string& wname, int pad, int cin_pad);   // zero-pad input channels (RGB -> 4)
+  // tensor-core-only weight whose K rows are those of `a` followed by those of `b` (same Cout): two K segments of one launch
+  ConvW cat_k(const ConvW& a, const ConvW& b);
   const float* vec(const std::string& name);                    // copy a 1-D tensor
   const float* vec_tiled(const std::string& name, int reps);
   void bn_fold(const std::string& prefix, float eps, const float** scale, const float** shift);
@@ -216,6 +225,7 @@ void ocr_run(Ctx&, OcrModel&, const float* x_nchw, const uint8_t* x_u8, int n, i
 int ocr_vocab(const OcrModel&);
 LamaModel* lama_build(Ctx&, const Weights&);
 void lama_free(LamaModel*);
+void lama_set_ffc_mode(int mode);     // 0 generic planar FFC path, 1 fused NHWC path when no layer needs split-K (default), 2 fused whenever capable
 struct LamaU8Io { const uint8_t* img = nullptr; const uint8_t* mask = nullptr; uint8_t* out = nullptr; int composite = 0; };
 void lama_run(Ctx&, LamaModel&, const float* img, const float* mask, const int* rel_pos, const int* direct, int th,
               int tw, int n, int h, int w, float* out, cudaStream_t st, const LamaU8Io* u8 = nullptr);

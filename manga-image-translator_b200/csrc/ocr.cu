@@ -111,18 +111,33 @@ OcrModel* ocr_build(Ctx& ctx, const Weights& W) {
 
 void ocr_free(OcrModel* m) { delete m; }
 
-// BasicBlock.forward (model_48px_ctc.py:389-403); x -> out may alias when there is no downsample path
-static void run_block(Exec& e, const OcrBlock& b, const View& x, const View& out) {
+static bool fusable(const ConvOp& op) { return conv_tma_capable(op) && conv_uses_tma(op); }   // runs on the TMA kernel, no split-K
+
+// BN(+ReLU) prologue of whichever conv consumes a tensor next (pre-activation ResNet: applied by the PRODUCER's epilogue when fused)
+struct NextBn { const float* s = nullptr; const float* b = nullptr; int relu = 0; };
+
+// BasicBlock.forward (model_48px_ctc.py:389-403); x -> out may alias when there is no downsample path.
+// Operand fusion: `xs` (valid or not) is relu(bn1(x)) already split into bf16 hi/mid by x's producer; conv1's epilogue (bn2 + relu)
+// writes conv2's operands directly; conv2's epilogue writes the fp32 residual stream AND, into `outs`, the next consumer's
+// operands relu(bn_next(out)).  Every fusion is taken only when both ends run on the TMA-fed kernel.
+static void run_block(Exec& e, const OcrBlock& b, const View& x, const View& out, const SplitView& xs, const NextBn& nxt, SplitView* outs) {
   Arena& ws = e.ws();
   const size_t mk = ws.mark();
   View y1 = ws.view(x.N, x.H, x.W, b.conv1.Cout);
-  { ConvOp op = Exec::op_from(b.conv1, x, y1); op.in_scale = b.bn1_s; op.in_shift = b.bn1_b; op.in_relu = 1; op.act = ACT_RELU; e.conv(op); }
+  ConvOp op1 = Exec::op_from(b.conv1, x, y1); op1.act = ACT_RELU;
+  if (xs.valid()) op1.in_sv = xs; else { op1.in_scale = b.bn1_s; op1.in_shift = b.bn1_b; op1.in_relu = 1; }
   View res = x;
+  ConvOp op2 = Exec::op_from(b.conv2, y1, out);
+  if (fusable(op1) && fusable(op2)) { SplitView ys = Exec::alias_split(y1); op1.out_sv = ys; op1.out.p = nullptr; op2.in_sv = ys; }
+  e.conv(op1);
   if (b.has_ds) {
     res = ws.view(x.N, x.H, x.W, b.ds.Cout);
     ConvOp op = Exec::op_from(b.ds, x, res); op.in_scale = b.ds_s; op.in_shift = b.ds_b; op.in_relu = 0; e.conv(op);
   }
-  { ConvOp op = Exec::op_from(b.conv2, y1, out); op.add1 = res; e.conv(op); }
+  op2.add1 = res;
+  if (outs && outs->valid() && fusable(op2)) { op2.out_sv = *outs; op2.os_scale = nxt.s; op2.os_shift = nxt.b; op2.os_relu = nxt.relu; }
+  else if (outs) *outs = SplitView();
+  e.conv(op2);
   ws.release(mk);
 }
 
@@ -144,29 +159,53 @@ void ocr_run(Ctx& ctx, OcrModel& m, const float* x_nchw, const uint8_t* x_u8, in
     View cur = ws.view(n, 24, w1, 40);
     e.avgpool(b, cur, 0);
     const int chans[4] = {80, 160, 320, 320};
+    SplitView cur_s;                              // relu(bn_next(cur)) as bf16 hi/mid operands, when cur's producer wrote them
     for (int l = 0; l < 4; ++l) {
+      SplitView layer_s = ws.split_view(cur.N, cur.H, cur.W, chans[l]);       // operands of the residual stream inside this layer
       for (size_t k = 0; k < m.layer[l].size(); ++k) {
         const OcrBlock& blk = m.layer[l][k];
+        NextBn nxt;                               // who consumes this block's output: the next block's conv1, else the layer's tail conv
+        if (k + 1 < m.layer[l].size()) { nxt.s = m.layer[l][k + 1].bn1_s; nxt.b = m.layer[l][k + 1].bn1_b; nxt.relu = 1; }
+        else if (l < 3) { nxt.s = m.tail[l].s; nxt.b = m.tail[l].b; nxt.relu = 1; }
+        else { nxt.s = m.t41.s; nxt.b = m.t41.b; nxt.relu = 1; }
+        SplitView outs = layer_s;
         if (blk.has_ds || cur.C != chans[l]) {
           View nx = ws.view(cur.N, cur.H, cur.W, chans[l]);
-          run_block(e, blk, cur, nx);
+          run_block(e, blk, cur, nx, cur_s, nxt, &outs);
           cur = nx;
         } else {
-          run_block(e, blk, cur, cur);
+          run_block(e, blk, cur, cur, cur_s, nxt, &outs);
         }
+        cur_s = outs;
       }
       if (l < 3) {
         View t = ws.view(cur.N, cur.H, cur.W, chans[l]);
-        ConvOp op = Exec::op_from(m.tail[l].conv, cur, t); op.in_scale = m.tail[l].s; op.in_shift = m.tail[l].b; op.in_relu = 1; e.conv(op);
+        ConvOp op = Exec::op_from(m.tail[l].conv, cur, t);
+        if (cur_s.valid() && fusable(op)) op.in_sv = cur_s; else { op.in_scale = m.tail[l].s; op.in_shift = m.tail[l].b; op.in_relu = 1; }
+        cur_s = SplitView();
+        if (l == 2) {                             // conv3 feeds layer4.0.conv1 directly (no pool, no downsample path): emit its operands
+          SplitView ts = ws.split_view(cur.N, cur.H, cur.W, chans[l]);
+          if (fusable(op) && !m.layer[3][0].has_ds) { op.out_sv = ts; op.os_scale = m.layer[3][0].bn1_s; op.os_shift = m.layer[3][0].bn1_b; op.os_relu = 1; cur_s = ts; }
+        }
+        e.conv(op);
         if (l == 0) { View pl = ws.view(n, 12, w2, chans[l]); e.avgpool(t, pl, 0); cur = pl; }
         else if (l == 1) { View pl = ws.view(n, 6, w3, chans[l]); e.avgpool(t, pl, 1); cur = pl; }
         else cur = t;
       }
     }
     View f1 = ws.view(n, 3, w3, 320);
-    { ConvOp op = Exec::op_from(m.t41.conv, cur, f1); op.sy = 2; op.sx = 1; op.in_scale = m.t41.s; op.in_shift = m.t41.b; op.in_relu = 1; e.conv(op); }
     View x = ws.view(n, 1, T, 320);               // tokens [n*T, 320]
-    { ConvOp op = Exec::op_from(m.t42.conv, f1, x); op.in_scale = m.t42.s; op.in_shift = m.t42.b; op.in_relu = 1; e.conv(op); }
+    {
+      ConvOp op41 = Exec::op_from(m.t41.conv, cur, f1); op41.sy = 2; op41.sx = 1;
+      if (cur_s.valid() && fusable(op41)) op41.in_sv = cur_s; else { op41.in_scale = m.t41.s; op41.in_shift = m.t41.b; op41.in_relu = 1; }
+      ConvOp op42 = Exec::op_from(m.t42.conv, f1, x);
+      if (fusable(op41) && fusable(op42)) {      // conv4_1's epilogue applies bn4_2 + relu and writes conv4_2's operands
+        SplitView fs = Exec::alias_split(f1);
+        op41.out_sv = fs; op41.os_scale = m.t42.s; op41.os_shift = m.t42.b; op41.os_relu = 1; op41.out.p = nullptr; op42.in_sv = fs;
+      } else { op42.in_scale = m.t42.s; op42.in_shift = m.t42.b; op42.in_relu = 1; }
+      e.conv(op41);
+      e.conv(op42);
+    }
     // ---- transformer encoder (model_48px_ctc.py:253-274)
     View z = ws.view(n, 1, T, 320), zp = ws.view(n, 1, T, 320), qk = ws.view(n, 1, T, 640), vv = ws.view(n, 1, T, 320),
          att = ws.view(n, 1, T, 320), hid = ws.view(n, 1, T, 1280);
@@ -178,8 +217,13 @@ void ocr_run(Ctx& ctx, OcrModel& m, const float* x_nchw, const uint8_t* x_u8, in
       if (!e.dry) launch_attention(qk.p, vv.p, att.p, n, T, 8, 40, st);
       { ConvOp op = Exec::op_from(L.out, att, x); op.add1 = x; e.conv(op); }
       e.layernorm(x, z, L.n2w, L.n2b, kLnEps5);
-      { ConvOp op = Exec::op_from(L.l1, z, hid); op.act = ACT_GELU; e.conv(op); }
-      { ConvOp op = Exec::op_from(L.l2, hid, x); op.add1 = x; e.conv(op); }
+      {
+        ConvOp o1 = Exec::op_from(L.l1, z, hid); o1.act = ACT_GELU;
+        ConvOp o2 = Exec::op_from(L.l2, hid, x); o2.add1 = x;
+        if (fusable(o1) && fusable(o2)) { SplitView hs = Exec::alias_split(hid); o1.out_sv = hs; o1.out.p = nullptr; o2.in_sv = hs; }
+        e.conv(o1);
+        e.conv(o2);
+      }
     }
     // ---- heads (model_48px_ctc.py:452-453, 460-463)
     View cv; cv.p = colors; cv.N = n; cv.H = 1; cv.W = T; cv.C = 6; cv.cs = 6; cv.coff = 0;

@@ -1,9 +1,25 @@
 // HBM-bound helper kernels: LayerNorm, fused depthwise-7x7 + LayerNorm, pooling, layout / dtype conversion,
 // the LaMa input pack / MPE add / final blend, and the small OCR attention core.
 // All operate on NHWC views (channel slice of a wider tensor) with 128-bit accesses along C where aligned.
+#include <cuda_bf16.h>
 #include "mitb_internal.h"
 
 namespace mitb {
+
+// fp32 -> bf16 hi / mid operand pair of the tensor-core convs (x ~ hi + mid), same rounding as split4 in tc_common.cuh
+__device__ __forceinline__ void split1_bf16(float v, uint16_t& hi, uint16_t& mid) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi = __bfloat16_as_ushort(h);
+  mid = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+}
+__device__ __forceinline__ void split4_bf16(const float4 v, uint2& hi, uint2& mid) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&h0), b1 = *reinterpret_cast<const uint32_t*>(&h1);
+  const __nv_bfloat162 m0 = __floats2bfloat162_rn(v.x - __uint_as_float(b0 << 16), v.y - __uint_as_float(b0 & 0xffff0000u));
+  const __nv_bfloat162 m1 = __floats2bfloat162_rn(v.z - __uint_as_float(b1 << 16), v.w - __uint_as_float(b1 & 0xffff0000u));
+  hi = make_uint2(b0, b1);
+  mid = make_uint2(*reinterpret_cast<const uint32_t*>(&m0), *reinterpret_cast<const uint32_t*>(&m1));
+}
 
 #define LAUNCH_END() do { count_launch(); CUDA_OK(cudaGetLastError()); } while (0)
 
@@ -14,7 +30,7 @@ namespace mitb {
 template <int PER_LANE>
 __global__ void layernorm_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs, int out_coff,
                                  const float* w, const float* b, float eps, long rows, int C, const float* pe,
-                                 float* out2, int out2_cs, int out2_coff, int T) {
+                                 float* out2, int out2_cs, int out2_coff, int T, uint16_t* o_hi, uint16_t* o_mid) {
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -40,22 +56,28 @@ __global__ void layernorm_kernel(const float* in, int in_cs, int in_coff, float*
     int c = lane + 32 * i;
     if (c < C) {
       float y = (v[i] - mean) * rstd * w[c] + b[c];
-      dst[c] = y;
+      if (o_hi) { uint16_t hh, mm; split1_bf16(y, hh, mm); o_hi[row * C + c] = hh; o_mid[row * C + c] = mm; }   // consumer conv's operands
+      else dst[c] = y;
       if (dst2) dst2[c] = y + per[c];
     }
   }
 }
 
 void launch_layernorm(const View& in, const View& out, const float* w, const float* b, float eps, const float* pe,
-                      const View* out2, int T, cudaStream_t st) {
+                      const View* out2, int T, cudaStream_t st, const SplitView* osv) {
   MITB_CHECK(!in.planar && !out.planar, "layernorm expects NHWC views");
   const int C = in.C; const long rows = (long)in.pixels();
   MITB_CHECK(C <= 1024 && out.C == C, "layernorm: C=%d unsupported", C);
+  uint16_t* ohi = nullptr; uint16_t* omid = nullptr;
+  if (osv && osv->valid()) {
+    MITB_CHECK(osv->C == C && osv->Hp == osv->H && osv->Wp == osv->W && (long)osv->N * osv->H * osv->W == rows, "layernorm: split output mismatch");
+    ohi = osv->hi; omid = osv->mid;
+  }
   const int per = (C + 31) / 32;
   dim3 grid((unsigned)((rows + 7) / 8));
   ProfScope ps("layernorm", 8.0 * rows * C, 8.0 * rows * C, st);
   float* o2 = out2 ? out2->p : nullptr; int o2cs = out2 ? out2->cs : 0, o2off = out2 ? out2->coff : 0;
-#define LN_CASE(P) layernorm_kernel<P><<<grid, 256, 0, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, w, b, eps, rows, C, pe, o2, o2cs, o2off, T)
+#define LN_CASE(P) layernorm_kernel<P><<<grid, 256, 0, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, w, b, eps, rows, C, pe, o2, o2cs, o2off, T, ohi, omid)
   if (per <= 4) LN_CASE(4); else if (per <= 8) LN_CASE(8); else if (per <= 10) LN_CASE(10);
   else if (per <= 16) LN_CASE(16); else LN_CASE(32);
 #undef LN_CASE
@@ -70,7 +92,8 @@ constexpr int DW_TX = 8;
 
 __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs,
                                                          int out_coff, const float* wdw, const float* bdw, const float* lnw,
-                                                         const float* lnb, float eps, int N, int H, int W, int C) {
+                                                         const float* lnb, float eps, int N, int H, int W, int C, uint16_t* o_hi,
+                                                         uint16_t* o_mid) {
   extern __shared__ float red[];                 // [PY][nwarps_per_row][DW_TX]
   const int c = threadIdx.x * 4;
   const int xt = blockIdx.x * DW_TX;
@@ -152,14 +175,23 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* in, int in
       float4 r;
       r.x = (acc[i].x - mean[i]) * rstd[i] * g.x + be.x; r.y = (acc[i].y - mean[i]) * rstd[i] * g.y + be.y;
       r.z = (acc[i].z - mean[i]) * rstd[i] * g.z + be.z; r.w = (acc[i].w - mean[i]) * rstd[i] * g.w + be.w;
-      *reinterpret_cast<float4*>(orow + (size_t)x * out_cs) = r;
+      if (o_hi) {                       // the only consumer is the fc1 GEMM: store its bf16 hi / mid operands, dense [pixel][C]
+        uint2 hh, mm; split4_bf16(r, hh, mm);
+        const size_t o = ((size_t)(n * H + y) * W + x) * C + c;
+        *reinterpret_cast<uint2*>(o_hi + o) = hh; *reinterpret_cast<uint2*>(o_mid + o) = mm;
+      } else *reinterpret_cast<float4*>(orow + (size_t)x * out_cs) = r;
     }
   }
 }
 
 void launch_dwconv7_ln(const View& in, const View& out, const float* wdw, const float* bdw, const float* lnw,
-                       const float* lnb, float eps, cudaStream_t st) {
+                       const float* lnb, float eps, cudaStream_t st, const SplitView* osv) {
   const int C = in.C;
+  uint16_t* ohi = nullptr; uint16_t* omid = nullptr;
+  if (osv && osv->valid()) {
+    MITB_CHECK(osv->C == C && osv->N == in.N && osv->H == in.H && osv->W == in.W && osv->Hp == in.H && osv->Wp == in.W, "dwconv7_ln: split output mismatch");
+    ohi = osv->hi; omid = osv->mid;
+  }
   MITB_CHECK(C % 128 == 0 && C <= 1024, "dwconv7_ln: C=%d must be a multiple of 128 (<=1024)", C);
   MITB_CHECK(in.cs % 4 == 0 && in.coff % 4 == 0 && out.cs % 4 == 0 && out.coff % 4 == 0, "dwconv7_ln alignment");
   const int tx = C / 4;
@@ -168,7 +200,7 @@ void launch_dwconv7_ln(const View& in, const View& out, const float* wdw, const 
   const size_t smem = (size_t)py * (tx / 32) * DW_TX * sizeof(float);
   ProfScope ps("dwconv7_ln", (98.0 + 8.0) * in.pixels() * C, 8.0 * in.pixels() * C + 4.0 * 51 * C, st);
   dwconv7_ln_kernel<<<grid, block, smem, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, wdw, bdw, lnw, lnb, eps,
-                                               in.N, in.H, in.W, C);
+                                               in.N, in.H, in.W, C, ohi, omid);
   LAUNCH_END();
 }
 
@@ -292,6 +324,8 @@ void launch_affine_act(const View& in, const View& out, const float* scale, cons
 // OCR self-attention core (model_48px_ctc.py:263-269 -> F.multi_head_attention_forward): one CTA per
 // (line, head); K and V of that head staged in shared memory (stride hd+1), one warp per query row,
 // softmax(q.k / sqrt(hd)) v with no padding mask.
+// gridDim.y row blocks per (line, head): each CTA re-stages K/V (L2 resident) and takes every gridDim.y-th group of query rows,
+// so the 128 (line, head) pairs of a 16-line chunk fill all 148 SMs several CTAs deep instead of 128 SMs one CTA deep.
 __global__ void attention_kernel(const float* qk, const float* v, float* out, int T, int heads, int hd, float scale) {
   extern __shared__ float sm[];
   const int D = heads * hd;
@@ -308,7 +342,7 @@ __global__ void attention_kernel(const float* qk, const float* v, float* out, in
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float* P = Ps + (size_t)warp * T; float* Q = Qs + warp * hd;
-  for (int t = warp; t < T; t += nw) {
+  for (int t = blockIdx.y * nw + warp; t < T; t += nw * gridDim.y) {
     for (int d = lane; d < hd; d += 32) Q[d] = qk[((size_t)n * T + t) * 2 * D + h * hd + d];
     __syncwarp();
     float mx = -INFINITY;
@@ -341,7 +375,8 @@ void launch_attention(const float* qk, const float* v, float* out, int N, int T,
   static PerDeviceOnce attr_set;
   if (attr_set.first()) CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ProfScope ps("attention", 4.0 * N * heads * (double)T * T * hd, 16.0 * N * T * heads * hd, st);
-  attention_kernel<<<N * heads, threads, smem, st>>>(qk, v, out, T, heads, hd, 1.0f / sqrtf((float)hd));
+  int rb = (T + 31) / 32; if (rb > 6) rb = 6; if (rb < 1) rb = 1;       // row blocks: >= 4 query rows per warp, <= 6 CTAs per (line, head)
+  attention_kernel<<<dim3(N * heads, rb), threads, smem, st>>>(qk, v, out, T, heads, hd, 1.0f / sqrtf((float)hd));
   LAUNCH_END();
 }
 

@@ -22,7 +22,7 @@ class MitbError(RuntimeError):
 
 _lib = None
 
-# name -> (restype, argtypes); mirrors include/mitb.h one to one (checked by tests/test_abi.py)
+# name -> (restype, argtypes); mirrors include/mitb.h one to one (checked by tests/test_host.py::test_abi_header_and_library_agree)
 P, I, F = C.c_void_p, C.c_int, C.c_float
 SIGNATURES = {
     "mitb_create": (I, [I, C.POINTER(P)]),
@@ -32,6 +32,7 @@ SIGNATURES = {
     "mitb_launch_count": (C.c_longlong, [P]),
     "mitb_workspace_bytes": (C.c_size_t, [P]),
     "mitb_set_tensor_cores": (I, [I]),
+    "mitb_set_ffc_mode": (I, [I]),
     "mitb_profile_enable": (I, [P, I]),
     "mitb_profile_report": (C.c_char_p, [P]),
     "mitb_dbnet_load": (I, [P, C.POINTER(MitbTensor), I]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "mitb_op_layernorm": (I, [P, P, I, I, P, P, F, P, P]),
     "mitb_op_rfft2": (I, [P, P, I, I, I, P, P]),
     "mitb_op_irfft2": (I, [P, P, I, I, I, P, P]),
+    "mitb_op_rfft2_nhwc": (I, [P, P, I, I, I, I, P, P]),
+    "mitb_op_irfft2_nhwc": (I, [P, P, P, I, I, I, I, P, P]),
     "mitb_op_attention": (I, [P, P, P, I, I, I, I, P, P]),
     "mitb_op_bilateral17": (I, [P, P, I, I, P, P]),
 }

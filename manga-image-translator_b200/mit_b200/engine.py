@@ -96,6 +96,11 @@ class Engine:
         """Process-wide: route eligible convolutions to the tcgen05 kernel (default) or keep everything on the fp32 SIMT kernel."""
         self.lib.mitb_set_tensor_cores(1 if on else 0)
 
+    def set_ffc_mode(self, mode: int):
+        """Process-wide LaMa FFC implementation: 0 generic planar, 1 fused NHWC when no layer needs split-K (default), 2 fused whenever capable."""
+        with self._lock:
+            self.lib.mitb_set_ffc_mode(int(mode))
+
     def profile(self, on: bool):
         self._call(self.lib.mitb_profile_enable, 1 if on else 0)
 
@@ -262,6 +267,20 @@ class Engine:
         c2, h, _ = spec.shape
         y = torch.empty((c2 // 2, h, w), dtype=torch.float32, device=self.device)
         self._call(self.lib.mitb_op_irfft2, _ptr(spec), c2 // 2, h, w, _ptr(y), self._stream())
+        return y
+
+    def rfft2_nhwc(self, x):
+        x = self._dev(x)
+        n, h, w, c = x.shape
+        spec = torch.empty((n, h, w // 2 + 1, 2 * c), dtype=torch.float32, device=self.device)
+        self._call(self.lib.mitb_op_rfft2_nhwc, _ptr(x), n, h, w, c, _ptr(spec), self._stream())
+        return spec
+
+    def irfft2_nhwc(self, spec, w, add=None):
+        spec, add = self._dev(spec), self._dev(add)
+        n, h, _, c2 = spec.shape
+        y = torch.empty((n, h, w, c2 // 2), dtype=torch.float32, device=self.device)
+        self._call(self.lib.mitb_op_irfft2_nhwc, _ptr(spec), _ptr(add), n, h, w, c2 // 2, _ptr(y), self._stream())
         return y
 
     def attention(self, qk, v, n, t, heads, hd):

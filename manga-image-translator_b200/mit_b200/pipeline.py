@@ -16,7 +16,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from . import plugins, synth
+from . import exchange, plugins, synth
 from .compat import InpainterConfig, OcrConfig, chunks
 from .engine import get_engine
 from .host import mpe
@@ -66,21 +66,26 @@ class HotPath:
             asyncio.run(p.unload())
 
     # ------------------------------------------------------------------ user-facing path (host buffers)
-    def process_page(self, page: np.ndarray, quads, mask: np.ndarray) -> PageResult:
+    def process_page(self, page: np.ndarray, quads, mask: np.ndarray, keep_on_device: bool = False) -> PageResult:
+        """`keep_on_device`: leave the inpainted page in HBM (torch uint8 CUDA tensor) for the NCCL exchange instead of copying it
+        to the host - the multi-GPU driver's ranks hand their results to rank 0 over NVLink, not through their own host."""
         textlines, raw_mask, _ = asyncio.run(self.det.infer(page, self.detect_size, 0.5, 0.7, 2.3))
         lines = asyncio.run(self.ocr.infer(page, quads, OcrConfig(prob=0.0)))
-        out = asyncio.run(self.inp.infer(page, mask, InpainterConfig(), self.inpainting_size))
+        if keep_on_device:
+            out = asyncio.run(self.inp.infer(page, mask, InpainterConfig(), self.inpainting_size, _device_out=True))
+        else:
+            out = asyncio.run(self.inp.infer(page, mask, InpainterConfig(), self.inpainting_size))
         return PageResult(textlines, raw_mask, lines, out)
 
-    def process_pages(self, items, workers: int = 4) -> List[PageResult]:
+    def process_pages(self, items, workers: int = 4, keep_on_device: bool = False) -> List[PageResult]:
         """A batch of (page, quads, mask) through the same three ``infer`` calls per page, with `workers` host threads so one
         page's host work (H2D/D2H, contours, crops, CTC collapse) overlaps other pages' kernels.  GPU submissions are
         serialised by the engine lock and execute in stream order; results come back in input order."""
         if workers <= 1 or len(items) <= 1:
-            return [self.process_page(*it) for it in items]
+            return [self.process_page(*it, keep_on_device=keep_on_device) for it in items]
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=workers) as ex:
-            return list(ex.map(lambda it: self.process_page(*it), items))
+            return list(ex.map(lambda it: self.process_page(*it, keep_on_device=keep_on_device), items))
 
     # ------------------------------------------------------------------ device-resident path
     def stage(self, page: np.ndarray, quads, mask: np.ndarray) -> StagedPage:
@@ -118,11 +123,35 @@ def shard_indices(n_pages_total: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_pages_total, world))
 
 
+class ResultExchange:
+    """Per-rank fixed-size result buffer + the single all-gather that brings every page's boxes / text / mask / inpainted page to
+    rank 0 (exchange.py has the record layout).  One instance per rank, reused every step."""
+
+    def __init__(self, device, pages_per_rank: int, H: int, W: int, kmax: int = exchange.KMAX, lmax: int = exchange.LMAX):
+        self.lay = exchange.Layout(H, W, kmax, lmax)
+        self.device = torch.device(device)
+        self.buf = torch.zeros((pages_per_rank, self.lay.record_bytes), dtype=torch.uint8, device=self.device)
+        self._pinned = None
+
+    def pack(self, results: List[PageResult]):
+        assert len(results) == self.buf.shape[0]
+        for i, r in enumerate(results):
+            exchange.pack_page(self.lay, self.buf[i], r.textlines, r.ocr_lines, r.raw_mask, r.inpainted)
+
+    def exchange(self, world: int, rank: int, n_pages_total: int):
+        """Collective.  Returns the pages in original order on rank 0, None elsewhere."""
+        g = exchange.gather_records(self.buf, world)
+        if rank != 0:
+            return None
+        if g.is_cuda and (self._pinned is None or self._pinned.shape != g.shape):
+            self._pinned = torch.empty(g.shape, dtype=torch.uint8, pin_memory=True)
+        return exchange.unpack_gathered(self.lay, g, n_pages_total, self._pinned)
+
+    @property
+    def gathered_bytes(self) -> int:
+        return self.buf.numel()
+
+
 def gather_results(local_u8: torch.Tensor, world: int) -> Optional[torch.Tensor]:
     """All-gather equal-size per-rank result buffers over NCCL (NVLink); returns [world, ...] on every rank."""
-    import torch.distributed as dist
-    if world == 1:
-        return local_u8[None]
-    out = torch.empty((world,) + tuple(local_u8.shape), dtype=local_u8.dtype, device=local_u8.device)
-    dist.all_gather_into_tensor(out, local_u8.contiguous())
-    return out
+    return exchange.gather_records(local_u8, world)

@@ -238,7 +238,11 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
         self.engine.unload_lama()
 
     async def _infer(self, image: np.ndarray, mask: np.ndarray, config: InpainterConfig, inpainting_size: int = 1024,
-                     verbose: bool = False) -> np.ndarray:
+                     verbose: bool = False, _device_out: bool = False) -> np.ndarray:
+        """`_device_out` (not part of the reference signature; used by the multi-GPU driver): when the page needed no host-side
+        resize, return the composited uint8 page as a CUDA tensor instead of copying it to the host."""
+        if image.dtype != np.uint8 or mask.dtype != np.uint8:
+            raise MitbError(f"inpainter expects uint8 image and mask (got {image.dtype}, {mask.dtype}), like the reference pipeline passes")
         img_original, mask_full = image, mask          # inputs are borrowed: never written; the host composite below (only taken
         height, width, _ = image.shape                 # when the page had to be resized) derives its own {0,1} mask from them
         if max(image.shape[0:2]) > inpainting_size:
@@ -268,6 +272,8 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
         # composite with the original page all run on the device; only uint8 crosses the bus.
         out_dev = eng.lama_infer_u8(eng.h2d(np.ascontiguousarray(image)), eng.h2d(np.ascontiguousarray(mask)), rel_pos, direct,
                                     composite=not resized)
+        if _device_out and not resized:
+            return out_dev
         img_inpainted = eng.d2h(out_dev, scratch=True).copy()      # pinned staging for the bus, then an owned array for the caller
         if not resized:
             return img_inpainted

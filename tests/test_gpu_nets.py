@@ -138,6 +138,37 @@ def test_lama_golden_and_oracle(eng, golden_dir):
     eng.unload_lama()
 
 
+@pytest.mark.parametrize("hw", [(128, 96), (256, 160), (320, 240)])
+def test_lama_fused_ffc_path_matches_generic_and_oracle(eng, hw):
+    """mitb_set_ffc_mode: 2 forces the fused NHWC FFC path (operand-fused GEMMs with two K segments + channel-vectorised FFT) at sizes
+    where the default would keep the generic planar path; both must match the oracle."""
+    h, w = hw
+    sd, msd = weights.lama_weights(9), weights.mpe_weights()
+    img, mask = cases.lama_case(h, w, seed=h + w)
+    rel, direct = nets.mpe_tables(mask[0, 0].numpy())
+    o = nets.lama_forward(sd, msd, img, mask, torch.from_numpy(rel)[None], torch.from_numpy(direct)[None])
+    eng.load_lama(sd, msd)
+    try:
+        outs = {}
+        for mode in (0, 2):
+            eng.set_ffc_mode(mode)
+            l0 = eng.launches
+            outs[mode] = eng.lama_forward(img, mask, rel[None], direct[None]).cpu()
+            outs[(mode, "launches")] = eng.launches - l0
+            e = _err(outs[mode], o)
+            print(f"lama {h}x{w} ffc_mode {mode}: err {e:.2e} launches {outs[(mode, 'launches')]}")
+            assert e < TOL
+        if (h // 8) * (w // 16 + 1) >= 128:                              # below that the spectral GEMM has < 128 rows: generic path
+            assert outs[(2, "launches")] < outs[(0, "launches")]      # the fused path really ran (fewer, fatter kernels)
+        # batch of 2 through the fused path
+        eng.set_ffc_mode(2)
+        out2 = eng.lama_forward(img.repeat(2, 1, 1, 1), mask.repeat(2, 1, 1, 1), np.stack([rel, rel]), np.stack([direct, direct])).cpu()
+        assert _err(out2[0], o[0]) < TOL and _err(out2[1], o[0]) < TOL
+    finally:
+        eng.set_ffc_mode(1)
+        eng.unload_lama()
+
+
 def test_lama_full_size_properties(eng):
     """At BASELINE's full size the oracle is too slow for CI; use size-independent properties instead:
     pixels outside the mask are returned untouched, output is finite and inside [0,1], and the run is deterministic."""

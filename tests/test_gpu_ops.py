@@ -121,6 +121,25 @@ def test_rfft2_irfft2(eng, h, w):
     _close(eng.irfft2(s, w), ref, 2e-5, what=f"irfft2 {h}x{w}")
 
 
+@pytest.mark.parametrize("n,h,w,c", [(1, 16, 12, 64), (2, 8, 8, 2), (1, 20, 30, 6), (1, 256, 192, 64), (1, 320, 240, 64), (2, 32, 24, 192),
+                                     (1, 5, 9, 70), (1, 64, 50, 34)])
+def test_rfft2_irfft2_nhwc(eng, n, h, w, c):
+    """Channel-vectorised NHWC FFT (fft_nhwc.cu) against torch.fft, incl. channel counts that are not multiples of the 32-lane
+    chunk (plain-load path instead of the TMA box), odd widths and the 256x192 / 320x240 sizes of the bench configs."""
+    g = torch.Generator().manual_seed(n * 7 + h * 1000 + w + c)
+    x = torch.randn(n, h, w, c, generator=g)
+    f = torch.fft.rfftn(x.permute(0, 3, 1, 2), dim=(-2, -1), norm="ortho")                  # [n,c,h,w2]
+    ref = torch.stack((f.real, f.imag), dim=2).permute(0, 3, 4, 1, 2).reshape(n, h, w // 2 + 1, 2 * c)
+    _close(eng.rfft2_nhwc(x), ref, 2e-5, what=f"rfft2_nhwc {h}x{w}x{c}")
+    s = torch.randn(n, h, w // 2 + 1, 2 * c, generator=g)
+    add = torch.randn(n, h, w, c, generator=g)
+    sc = s.view(n, h, w // 2 + 1, c, 2).permute(0, 3, 1, 2, 4)
+    z = torch.complex(sc[..., 0].contiguous(), sc[..., 1].contiguous())
+    ref = torch.fft.irfftn(z, s=(h, w), dim=(-2, -1), norm="ortho").permute(0, 2, 3, 1)
+    _close(eng.irfft2_nhwc(s, w), ref, 2e-5, what=f"irfft2_nhwc {h}x{w}x{c}")
+    _close(eng.irfft2_nhwc(s, w, add), ref + add, 2e-5, what=f"irfft2_nhwc+add {h}x{w}x{c}")
+
+
 def test_fft_impulse_and_roundtrip(eng):
     x = torch.zeros(2, 24, 20)
     x[0, 0, 0] = 1.0
