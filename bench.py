@@ -312,7 +312,7 @@ def ffc_block_from_launches(launch_list, prof, pages_timed, peaks, H=None, W=Non
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from mit_b200 import synth
-    from mit_b200.pipeline import HotPath, gather_results, shard_indices
+    from mit_b200.pipeline import HotPath, ResultExchange, shard_indices
     torch.set_grad_enabled(False)
     os.environ.setdefault("MITB_PROFILE_LAUNCHES", "1")    # per-launch conv list for the LaMa FFC figure
     dev = f"cuda:{local_rank}"
@@ -349,7 +349,8 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    result_buf = torch.empty((len(pages), PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
+    # multi-GPU: fixed-size result records (boxes, scores, OCR text / colours, raw mask, inpainted page) all-gathered over NCCL
+    xchg = ResultExchange(dev, len(pages), PAGE_H, PAGE_W) if world > 1 else None
 
     def resident_step():
         for i, sp in enumerate(staged):
@@ -381,18 +382,27 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- end-to-end through the plugin API with host buffers (`e2e`)
     def e2e_step():
-        outs = hp.process_pages([(p, synth.make_quads(b), m) for (p, b, m) in pages], workers=args.workers)
-        if world > 1:   # results back to every rank (rank 0 consumes them): inpainted pages + raw masks over NCCL
-            for i, r in enumerate(outs):
-                result_buf[i].copy_(torch.from_numpy(r.inpainted), non_blocking=True)
-            gather_results(result_buf, world)
-        return outs
+        items = [(p, synth.make_quads(b), m) for (p, b, m) in pages]
+        if world == 1:
+            return hp.process_pages(items, workers=args.workers)            # the user-facing call: host arrays in, host results out
+        # N > 1: every rank keeps its inpainted pages in HBM, packs one record per page and ONE all-gather brings boxes / text /
+        # masks / pages to rank 0 over NVLink; rank 0 reads them back to the host (the only D2H of page-sized results)
+        outs = hp.process_pages(items, workers=args.workers, keep_on_device=True)
+        xchg.pack(outs)
+        got = xchg.exchange(world, rank, n_pages * world)
+        if rank == 0:
+            eng.d2h_bytes += xchg.gathered_bytes * world
+            assert len(got) == n_pages * world
+        return got
 
     e2e_warm = min(args.warmup, 1) if args.fast_e2e else args.warmup
     for _ in range(e2e_warm):
         e2e_step()
     barrier()
     eng.h2d_bytes = eng.d2h_bytes = 0
+    if os.environ.get("MITB_E2E_TRACE"):
+        from mit_b200.engine import trace_report
+        trace_report()                                     # drop the warm-up's numbers
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
@@ -400,6 +410,11 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
+    if os.environ.get("MITB_E2E_TRACE"):
+        from mit_b200.engine import trace_report
+        log(f"[e2e trace] wall {e2e_ms / 1e3:.3f} s over {args.steps} step(s) x {n_pages} pages, {args.workers} workers; seconds summed over threads:")
+        for k, (sec, cnt) in trace_report().items():
+            log(f"[e2e trace]   {k:24s} {sec:8.3f} s  ({cnt} calls)")
     e2e_value = args.steps * n_pages * world / (e2e_ms / 1e3)
     h2d, d2h = eng.h2d_bytes / args.steps, eng.d2h_bytes / args.steps
 

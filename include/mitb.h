@@ -130,6 +130,9 @@ int mitb_op_irfft2_nhwc(mitb_ctx* ctx, const float* spec, const float* add, int 
 /* Multi-head attention core: qk [n*t, 2*d] (q then k, already projected), v [n*t, d] -> out [n*t, d]. */
 int mitb_op_attention(mitb_ctx* ctx, const float* qk, const float* v, int n, int t, int heads, int head_dim,
                       float* out, void* stream);
+/* LamaFourier.load_masked_position_encoding at its 256x256 working resolution (inpainting_lama_mpe.py:763-803): small = the
+ * INTER_AREA-reduced uint8 mask [n,256,256] (hole where != 0) -> rel_pos int32 [n,256,256] in [0,127], direct int32 [n,256,256,4]. */
+int mitb_op_mpe_tables(mitb_ctx* ctx, const uint8_t* small, int n, int32_t* rel_pos, int32_t* direct, void* stream);
 /* cv2.bilateralFilter(img, 17, 80, 80) on a uint8 HWC3 device image (detector pre-filter, dbnet_convnext.py:549). */
 int mitb_op_bilateral17(mitb_ctx* ctx, const uint8_t* img, int h, int w, uint8_t* out, void* stream);
 

@@ -339,6 +339,14 @@ int mitb_op_attention(mitb_ctx* ctx, const float* qk, const float* v, int n, int
   API_END(ctx)
 }
 
+int mitb_op_mpe_tables(mitb_ctx* ctx, const uint8_t* small, int n, int32_t* rel_pos, int32_t* direct, void* stream) {
+  API_BEGIN(ctx)
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;
+  launch_mpe_tables(small, n, rel_pos, direct, (cudaStream_t)stream);
+  g_launch_counter = nullptr;
+  API_END(ctx)
+}
+
 int mitb_op_bilateral17(mitb_ctx* ctx, const uint8_t* img, int h, int w, uint8_t* out, void* stream) {
   API_BEGIN(ctx)
   g_launch_counter = &ctx->c.launches; ++g_launch_epoch;

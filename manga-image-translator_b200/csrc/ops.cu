@@ -505,6 +505,59 @@ __global__ void mpe_add_kernel(float* x, int cs, int coff, int N, int H, int W, 
     *reinterpret_cast<float4*>(x + pix * cs + coff + c) = v;
   }
 }
+// ---------------------------------------------------------------------------------------------------
+// LamaFourier.load_masked_position_encoding at its 256x256 working resolution (inpainting_lama_mpe.py:763-803) on the device.
+// Input: the INTER_AREA-reduced uint8 mask (hole where != 0).  known = (small == 0) is grown by a 3x3 box per step
+// (BORDER_REFLECT_101 like cv2.filter2D); a pixel first covered at step i gets pos = i, and direct[k] = 1 when the k-th 2x2 corner
+// neighbourhood already touched the known region at that step.  rel_pos = clip(pos, 0, 127) (pos/128*128 is exact in fp32).
+// One CTA per image, the whole bitmap ping-pongs in shared memory; ~max-distance iterations of 64 pixels per thread.
+constexpr int MPE_N = 256, MPE_T = 1024;
+__global__ void __launch_bounds__(MPE_T) mpe_tables_kernel(const uint8_t* small, int* rel_pos, int* direct) {
+  extern __shared__ uint8_t mp_sm[];
+  uint8_t* A = mp_sm; uint8_t* B = mp_sm + MPE_N * MPE_N;
+  const uint8_t* src = small + (size_t)blockIdx.x * MPE_N * MPE_N;
+  int* rel = rel_pos + (size_t)blockIdx.x * MPE_N * MPE_N;
+  int* dir = direct + (size_t)blockIdx.x * MPE_N * MPE_N * 4;
+  int any_known = 0, all_known = 1;
+  for (int p = threadIdx.x; p < MPE_N * MPE_N; p += MPE_T) {
+    const uint8_t k = src[p] == 0 ? 1 : 0;
+    A[p] = k; any_known |= k; all_known &= k;
+    rel[p] = 0;
+    *reinterpret_cast<int4*>(dir + (size_t)p * 4) = make_int4(0, 0, 0, 0);
+  }
+  any_known = __syncthreads_or(any_known);
+  all_known = __syncthreads_and(all_known);
+  if (!any_known) return;                                       // no known pixel: the reference loop never runs, tables stay 0
+  auto refl = [](int i) { return i < 0 ? -i : (i >= MPE_N ? 2 * MPE_N - 2 - i : i); };
+  int step = 0;
+  while (!all_known) {
+    ++step;
+    int all_now = 1;
+    for (int p = threadIdx.x; p < MPE_N * MPE_N; p += MPE_T) {
+      const int y = p >> 8, x = p & 255;
+      uint8_t g = A[p];
+      if (!g) {
+        const int ym = refl(y - 1) << 8, y0 = y << 8, yp = refl(y + 1) << 8, xm = refl(x - 1), xp = refl(x + 1);
+        const uint8_t a = A[ym + xm], b = A[ym + x], c = A[ym + xp], d = A[y0 + xm], e = A[y0 + xp], f = A[yp + xm], h = A[yp + x], i = A[yp + xp];
+        g = a | b | c | d | e | f | h | i;
+        if (g) {
+          rel[p] = step < 127 ? step : 127;
+          *reinterpret_cast<int4*>(dir + (size_t)p * 4) = make_int4((a | b | d) ? 1 : 0, (d | f | h) ? 1 : 0, (b | c | e) ? 1 : 0, (e | h | i) ? 1 : 0);
+        }
+      }
+      B[p] = g; all_now &= g;
+    }
+    all_known = __syncthreads_and(all_now);
+    uint8_t* t = A; A = B; B = t;
+  }
+}
+void launch_mpe_tables(const uint8_t* small, int n, int* rel_pos, int* direct, cudaStream_t st) {
+  static PerDeviceOnce attr;
+  if (attr.first()) CUDA_OK(cudaFuncSetAttribute(mpe_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MPE_N * MPE_N));
+  mpe_tables_kernel<<<n, MPE_T, 2 * MPE_N * MPE_N, st>>>(small, rel_pos, direct);
+  LAUNCH_END();
+}
+
 void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, int th, int tw, const float* mask, const float* table,
                     const float* dirw, float a5, float a6, cudaStream_t st) {
   MITB_CHECK(x.C == 64 && x.cs % 4 == 0 && x.coff % 4 == 0, "mpe_add expects the 64-channel stem output");

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mitb_op_rfft2_nhwc": (I, [P, P, I, I, I, I, P, P]),
     "mitb_op_irfft2_nhwc": (I, [P, P, P, I, I, I, I, P, P]),
     "mitb_op_attention": (I, [P, P, P, I, I, I, I, P, P]),
+    "mitb_op_mpe_tables": (I, [P, P, I, P, P, P]),
     "mitb_op_bilateral17": (I, [P, P, I, I, P, P]),
 }
 

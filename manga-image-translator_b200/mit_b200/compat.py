@@ -107,12 +107,59 @@ except Exception:  # noqa: BLE001
         async def detect(self, image: np.ndarray, detect_size: int, text_threshold: float, box_threshold: float,
                          unclip_ratio: float, invert: bool = False, gamma_correct: bool = False, rotate: bool = False,
                          auto_rotate: bool = False, verbose: bool = False):
-            """CommonDetector.detect (detection/common.py:12-64) without the optional rotate/invert/gamma/border variants."""
-            if invert or gamma_correct or rotate or auto_rotate:
-                raise NotImplementedError("stand-alone detect() supports the plain path only; install manga_translator "
-                                          "for the rotate/invert/gamma wrappers (they are inherited unchanged)")
-            textlines, raw_mask, mask = await self.infer(image, detect_size, text_threshold, box_threshold, unclip_ratio, verbose)
+            """CommonDetector.detect (detection/common.py:12-64): optional input variants around `_detect`, undone on the results.
+            Order as in the reference: rotate 90 deg clockwise, zero border to a >= 400 px square when the short side is < 400,
+            invert, gamma; then filter area > 1, crop the border, (auto_rotate: rerun rotated when most lines are horizontal),
+            rotate the results back."""
+            import cv2
+            from collections import Counter
+            page_h, page_w = image.shape[:2]
+            original = image.copy()
+            bordered = min(page_w, page_h) < 400
+            work = image
+            if rotate:
+                work = np.rot90(work, k=-1)
+            if bordered:
+                side = max(work.shape[1], work.shape[0], 400)
+                canvas = np.zeros((side, side, 3), np.uint8)
+                canvas[:work.shape[0], :work.shape[1]] = work
+                work = canvas
+            if invert:
+                work = cv2.bitwise_not(work)
+            if gamma_correct:
+                mean = np.mean(cv2.cvtColor(work, cv2.COLOR_BGR2GRAY))
+                work = np.power(work, np.log(0.5 * 255) / np.log(mean)).clip(0, 255).astype(np.uint8)
+            textlines, raw_mask, mask = await self._detect(work, detect_size, text_threshold, box_threshold, unclip_ratio, verbose)
             textlines = [t for t in textlines if t.area > 1]
+            if bordered:
+                bh, bw = work.shape[:2]
+                raw_mask = cv2.resize(raw_mask, (bw, bh), interpolation=cv2.INTER_LINEAR)[:page_h, :page_w]
+                if mask is not None:
+                    mask = cv2.resize(mask, (bw, bh), interpolation=cv2.INTER_LINEAR)[:page_h, :page_w]
+                kept = []
+                for t in textlines:
+                    if t.xyxy[0] >= page_w and t.xyxy[1] >= page_h:        # entirely inside the added border
+                        continue
+                    pts = t.pts
+                    pts[:, 0] = np.clip(pts[:, 0], 0, page_w)
+                    pts[:, 1] = np.clip(pts[:, 1], 0, page_h)
+                    kept.append(Quadrilateral(pts, t.text, t.prob))
+                textlines = kept
+            if auto_rotate:
+                votes = Counter("h" if t.aspect_ratio > 1 else "v" for t in textlines)
+                if not textlines or votes.most_common(1)[0][0] == "h":
+                    return await self.detect(original, detect_size, text_threshold, box_threshold, unclip_ratio, invert, gamma_correct,
+                                             rotate=(not rotate), auto_rotate=False, verbose=verbose)
+            if rotate:
+                raw_mask = np.ascontiguousarray(np.rot90(raw_mask))
+                if mask is not None:
+                    mask = np.ascontiguousarray(np.rot90(mask).astype(np.uint8))
+                back = []
+                for t in textlines:
+                    p = t.pts[:, [1, 0]]
+                    p[:, 1] = page_h - p[:, 1]
+                    back.append(Quadrilateral(p, t.text, t.prob))
+                textlines = back
             return textlines, raw_mask, mask
 
         async def _detect(self, *args, **kwargs):

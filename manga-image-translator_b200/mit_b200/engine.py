@@ -13,6 +13,45 @@ from . import _lib
 from ._lib import MitbError, MitbTensor
 
 
+class _Trace:
+    """Wall-clock accounting of the host path (MITB_E2E_TRACE=1): seconds per label summed over all threads."""
+    import os as _os
+    on = bool(int(_os.environ.get("MITB_E2E_TRACE", "0") or 0))
+    acc: Dict[str, float] = {}
+    cnt: Dict[str, int] = {}
+    lock = threading.Lock()
+
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if _Trace.on:
+            import time
+            self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *a):
+        if _Trace.on:
+            import time
+            dt = time.perf_counter() - self.t0
+            with _Trace.lock:
+                _Trace.acc[self.label] = _Trace.acc.get(self.label, 0.0) + dt
+                _Trace.cnt[self.label] = _Trace.cnt.get(self.label, 0) + 1
+
+
+def trace(label):
+    return _Trace(label)
+
+
+def trace_report(reset=True):
+    with _Trace.lock:
+        r = {k: (round(v, 4), _Trace.cnt[k]) for k, v in sorted(_Trace.acc.items(), key=lambda kv: -kv[1])}
+        if reset:
+            _Trace.acc.clear()
+            _Trace.cnt.clear()
+    return r
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -52,6 +91,10 @@ class Engine:
         e.g. the detector's probability map) lands in a per-thread pinned buffer: the copy runs at full PCIe rate instead of
         staging through pageable memory while the page threads' kernels queue behind it on the shared stream.  The returned
         array is a view of that buffer - never hand it to the caller of the plugin."""
+        with trace("d2h"):
+            return self._d2h(t, scratch)
+
+    def _d2h(self, t: torch.Tensor, scratch: bool = False) -> np.ndarray:
         self.d2h_bytes += t.numel() * t.element_size()
         if scratch and self._pinned is not None and t.is_cuda and t.numel() * t.element_size() >= (1 << 20):
             try:
@@ -86,8 +129,9 @@ class Engine:
             raise MitbError(self.lib.mitb_last_error(self._h).decode())
 
     def _call(self, fn, *args):
-        with self._lock:
-            self._check(fn(self._h, *args))
+        with trace("enqueue(lock+launch)"):
+            with self._lock:
+                self._check(fn(self._h, *args))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -288,6 +332,18 @@ class Engine:
         out = torch.empty_like(v)
         self._call(self.lib.mitb_op_attention, _ptr(qk), _ptr(v), n, t, heads, hd, _ptr(out), self._stream())
         return out
+
+    def mpe_tables_256(self, small_u8):
+        """Device version of host.mpe._tables_256: INTER_AREA-reduced uint8 mask [256,256] (or [n,256,256]) -> (rel_pos, direct) int32."""
+        s = torch.as_tensor(small_u8)
+        if s.device.type == "cpu":
+            s = self.h2d(s)
+        s = s.to(torch.uint8).contiguous()
+        n = 1 if s.dim() == 2 else s.shape[0]
+        rel = torch.empty((n, 256, 256), dtype=torch.int32, device=self.device)
+        direct = torch.empty((n, 256, 256, 4), dtype=torch.int32, device=self.device)
+        self._call(self.lib.mitb_op_mpe_tables, _ptr(s), n, _ptr(rel), _ptr(direct), self._stream())
+        return rel, direct
 
     def bilateral17(self, img_u8):
         img = torch.as_tensor(img_u8).to(self.device, torch.uint8).contiguous()

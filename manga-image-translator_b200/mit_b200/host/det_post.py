@@ -2,9 +2,13 @@
   imgproc.resize_aspect_ratio          detection/default_utils/imgproc.py:37-70
   SegDetectorRepresenter               detection/default_utils/dbnet_utils.py:8-187
   adjustResultCoordinates              detection/default_utils/craft_utils.py:238-244
-The reference offsets the box with pyclipper (JT_ROUND) and re-fits a minAreaRect; pyclipper/shapely are third-party and
-absent here, so ``unclip`` expands the (integer-truncated, as Clipper does) rectangle analytically by the same distance
-area*ratio/perimeter -- identical up to Clipper's integer rounding of the arc points (+-1 px, documented in DESIGN.md).
+The reference offsets the box with pyclipper (JT_ROUND, ET_CLOSEDPOLYGON) and re-fits a minAreaRect.  pyclipper/shapely are
+third-party and absent here (pyclipper is unpinned in requirements.txt; every release since 1.0 bundles Angus Johnson's
+Clipper 6.4.2), so ``clipper_offset_round`` restates ClipperOffset (AddPath / FixOrientations / DoOffset / OffsetPoint /
+DoRound, clipper.cpp 6.4.2) for one closed path: integer input (pyclipper truncates floats), unit normals, arc step count from
+ArcTolerance 0.25, every output vertex rounded half away from zero.  The union pass Clipper runs afterwards only removes
+duplicate / collinear vertices of an outward offset of a convex quad, which cannot change the minAreaRect fitted next.
+Parity unpinned by a run of the real library (absent offline); pinned by hand-derived vectors in tests/test_host.py.
 """
 from __future__ import annotations
 
@@ -51,20 +55,103 @@ def box_score(prob: np.ndarray, contour: np.ndarray) -> float:
     return cv2.mean(prob[ymin:ymax + 1, xmin:xmax + 1], m)[0]
 
 
+def _c_round(v: float) -> int:
+    """Clipper's Round(): half away from zero, via truncation of v +- 0.5."""
+    return int(v - 0.5) if v < 0 else int(v + 0.5)
+
+
+def clipper_offset_round(path, delta: float, arc_tolerance: float = 0.25):
+    """ClipperOffset().AddPath(path, JT_ROUND, ET_CLOSEDPOLYGON); Execute(delta) for ONE closed path (Clipper 6.4.2).
+    `path`: sequence of (x, y), truncated to integers like pyclipper does.  Returns the offset polygon's vertices as a list of
+    integer (x, y) (before Clipper's clean-up union), or [] when Clipper would drop the path (< 3 distinct vertices)."""
+    import math
+    pts = [(int(p[0]), int(p[1])) for p in path]                     # int(): truncation toward zero
+    # ---- AddPath: strip the closing duplicate and consecutive duplicates
+    hi = len(pts) - 1
+    while hi > 0 and pts[0] == pts[hi]:
+        hi -= 1
+    src = [pts[0]]
+    for i in range(1, hi + 1):
+        if src[-1] != pts[i]:
+            src.append(pts[i])
+    if len(src) < 3:
+        return []
+    # ---- FixOrientations: closed polygons must have Orientation() == true, i.e. Clipper's Area() >= 0
+    a = 0.0
+    j = len(src) - 1
+    for i in range(len(src)):
+        a += (float(src[j][0]) + src[i][0]) * (float(src[j][1]) - src[i][1])
+        j = i
+    if -a * 0.5 < 0:
+        src.reverse()
+    n = len(src)
+    if delta == 0:
+        return list(src)
+    # ---- DoOffset: arc discretisation
+    y = arc_tolerance
+    if arc_tolerance <= 0.0:
+        y = 0.25
+    elif arc_tolerance > abs(delta) * 0.25:
+        y = abs(delta) * 0.25
+    steps = math.pi / math.acos(1 - y / abs(delta))
+    if steps > abs(delta) * math.pi:
+        steps = abs(delta) * math.pi
+    m_sin, m_cos = math.sin(2 * math.pi / steps), math.cos(2 * math.pi / steps)
+    steps_per_rad = steps / (2 * math.pi)
+    if delta < 0.0:
+        m_sin = -m_sin
+
+    def unit_normal(p1, p2):
+        if p1 == p2:
+            return (0.0, 0.0)
+        dx, dy = float(p2[0] - p1[0]), float(p2[1] - p1[1])
+        f = 1.0 / math.sqrt(dx * dx + dy * dy)
+        return (dy * f, -dx * f)
+
+    normals = [unit_normal(src[i], src[(i + 1) % n]) for i in range(n)]
+    out = []
+    k = n - 1
+    for j in range(n):
+        # ---- OffsetPoint(j, k, jtRound)
+        sin_a = normals[k][0] * normals[j][1] - normals[j][0] * normals[k][1]
+        done = False
+        if abs(sin_a * delta) < 1.0:
+            cos_a = normals[k][0] * normals[j][0] + normals[j][1] * normals[k][1]
+            if cos_a > 0:                                         # nearly straight: one vertex
+                out.append((_c_round(src[j][0] + normals[k][0] * delta), _c_round(src[j][1] + normals[k][1] * delta)))
+                done = True
+        elif sin_a > 1.0:
+            sin_a = 1.0
+        elif sin_a < -1.0:
+            sin_a = -1.0
+        if not done:
+            if sin_a * delta < 0:                                 # concave corner
+                out.append((_c_round(src[j][0] + normals[k][0] * delta), _c_round(src[j][1] + normals[k][1] * delta)))
+                out.append(src[j])
+                out.append((_c_round(src[j][0] + normals[j][0] * delta), _c_round(src[j][1] + normals[j][1] * delta)))
+            else:                                                 # DoRound
+                ang = math.atan2(sin_a, normals[k][0] * normals[j][0] + normals[k][1] * normals[j][1])
+                nsteps = max(int(_c_round(steps_per_rad * abs(ang))), 1)
+                x, yy = normals[k]
+                for _ in range(nsteps):
+                    out.append((_c_round(src[j][0] + x * delta), _c_round(src[j][1] + yy * delta)))
+                    x2 = x
+                    x = x * m_cos - m_sin * yy
+                    yy = x2 * m_sin + yy * m_cos
+                out.append((_c_round(src[j][0] + normals[j][0] * delta), _c_round(src[j][1] + normals[j][1] * delta)))
+        k = j
+    return out
+
+
 def unclip(box4: np.ndarray, unclip_ratio: float) -> np.ndarray:
-    """Offset a rectangle outwards by area*ratio/perimeter (dbnet_utils.py:146-152)."""
+    """SegDetectorRepresenter.unclip (dbnet_utils.py:146-152): offset the box outwards by area*ratio/perimeter with a round join.
+    shapely's Polygon(box).area / .length are the shoelace area and the perimeter of the float box."""
     pts = np.asarray(box4, dtype=np.float64)
     d = polygon_area(pts) * unclip_ratio / max(polygon_perimeter(pts), 1e-9)
-    q = np.trunc(pts)                       # Clipper works on integers; pyclipper truncates the float input
-    c = q.mean(axis=0)
-    e1, e2 = q[1] - q[0], q[3] - q[0]
-    n1, n2 = np.linalg.norm(e1), np.linalg.norm(e2)
-    if n1 == 0 or n2 == 0:
-        return q.reshape(-1, 1, 2).astype(np.float32)
-    u1, u2 = e1 / n1, e2 / n2
-    h1, h2 = n1 / 2 + d, n2 / 2 + d
-    out = np.array([c - u1 * h1 - u2 * h2, c + u1 * h1 - u2 * h2, c + u1 * h1 + u2 * h2, c - u1 * h1 + u2 * h2])
-    return np.round(out).reshape(-1, 1, 2).astype(np.float32)
+    poly = clipper_offset_round(pts, d)
+    if not poly:                                                  # Clipper drops degenerate paths; the reference would then fail in minAreaRect
+        return np.trunc(pts).reshape(-1, 1, 2).astype(np.float32)
+    return np.array(poly, dtype=np.int32).reshape(-1, 1, 2)
 
 
 def boxes_from_prob(prob: np.ndarray, thresh: float, box_thresh: float, unclip_ratio: float, dest_w: int, dest_h: int,
@@ -79,6 +166,8 @@ def boxes_from_prob(prob: np.ndarray, thresh: float, box_thresh: float, unclip_r
     boxes = np.zeros((n, 4, 2), dtype=np.int64)
     scores = np.zeros((n,), dtype=np.float32)
     for i in range(n):
+        if contours[i].shape[0] < 3 and min_size > 0:
+            continue        # 1- or 2-point contour: its minAreaRect has a zero side, i.e. sside = 0 < min_size (same row left all-zero)
         contour = contours[i].squeeze(1)
         pts, sside = mini_box(contour)
         if sside < min_size:

@@ -33,6 +33,12 @@ def _mask_u8(mask01) -> np.ndarray:
     return (a.astype(np.float32) * 255).astype(np.uint8)
 
 
+def small_mask_256(mask01) -> np.ndarray:
+    """The reduction step of load_masked_position_encoding (:763-765): (mask*255) u8 -> cv2 INTER_AREA 256x256 (any value > 0 is
+    hole).  Stays on the host (cv2's fixed-point area filter is the definition); the distance sweep runs on the device."""
+    return cv2.resize(_mask_u8(mask01), (256, 256), interpolation=cv2.INTER_AREA)
+
+
 def _tables_256(m: np.ndarray):
     small = cv2.resize(m, (256, 256), interpolation=cv2.INTER_AREA)
     known = (small == 0).astype(np.uint8)

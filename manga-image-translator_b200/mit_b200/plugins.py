@@ -25,7 +25,7 @@ import torch
 
 from . import compat
 from .compat import InpainterConfig, OcrConfig, OfflineDetector, OfflineInpainter, OfflineOCR, Quadrilateral, chunks
-from .engine import Engine, get_engine
+from .engine import Engine, get_engine, trace
 from ._lib import MitbError
 from .host import det_post, mpe, rearrange
 
@@ -98,16 +98,18 @@ class DBConvNextDetector(_InjectableWeights, OfflineDetector):
         self.logger.info(f"Detection resolution: {img_resized_w}x{img_resized_h}")
 
         mask = mask[0, 0, :, :]
-        boxes, scores = det_post.boxes_from_prob(db[0, 0], text_threshold, box_threshold, unclip_ratio, img_resized_w, img_resized_h)
-        polys = det_post.polys_from_boxes(boxes, scores, ratio_w, ratio_h)
-        textlines = [Quadrilateral(pts.astype(int), "", score) for pts, score in zip(polys, scores)]
-        textlines = list(filter(lambda q: q.area > 16, textlines))
-        mask_resized = cv2.resize(mask, (mask.shape[1] * 2, mask.shape[0] * 2), interpolation=cv2.INTER_LINEAR)
-        if pad_h > 0:
-            mask_resized = mask_resized[:-pad_h, :]
-        elif pad_w > 0:
-            mask_resized = mask_resized[:, :-pad_w]
-        raw_mask = np.clip(mask_resized * 255, 0, 255).astype(np.uint8)
+        with trace("host:det_post"):
+            boxes, scores = det_post.boxes_from_prob(db[0, 0], text_threshold, box_threshold, unclip_ratio, img_resized_w, img_resized_h)
+            polys = det_post.polys_from_boxes(boxes, scores, ratio_w, ratio_h)
+            textlines = [Quadrilateral(pts.astype(int), "", score) for pts, score in zip(polys, scores)]
+            textlines = list(filter(lambda q: q.area > 16, textlines))
+        with trace("host:det_mask"):
+            mask_resized = cv2.resize(mask, (mask.shape[1] * 2, mask.shape[0] * 2), interpolation=cv2.INTER_LINEAR)
+            if pad_h > 0:
+                mask_resized = mask_resized[:-pad_h, :]
+            elif pad_w > 0:
+                mask_resized = mask_resized[:, :-pad_w]
+            raw_mask = np.clip(mask_resized * 255, 0, 255).astype(np.uint8)
         return textlines, raw_mask, None
 
 
@@ -164,8 +166,10 @@ class Model48pxCTCOCR(_InjectableWeights, OfflineOCR):
         text_height, max_chunk_size = 48, 16
         ignore_bubble = getattr(config, "ignore_bubble", 0)
         threshold = 0.5 if getattr(config, "prob", None) is None else config.prob
-        quadrilaterals = list(self._generate_text_direction(textlines))
-        region_imgs = [q.get_transformed_region(image, d, text_height) for q, d in quadrilaterals]
+        with trace("host:ocr_direction"):
+            quadrilaterals = list(self._generate_text_direction(textlines))
+        with trace("host:ocr_crops"):
+            region_imgs = [q.get_transformed_region(image, d, text_height) for q, d in quadrilaterals]
         out_regions = []
         perm = range(len(region_imgs))
         is_quadrilaterals = False
@@ -173,9 +177,7 @@ class Model48pxCTCOCR(_InjectableWeights, OfflineOCR):
             is_quadrilaterals = True
             perm = sorted(range(len(region_imgs)), key=lambda x: region_imgs[x].shape[1])
         if 1 <= ignore_bubble <= 50:
-            if not compat.HAVE_REFERENCE:
-                raise NotImplementedError("ignore_bubble needs manga_translator.utils.bubble.is_ignore")
-            from manga_translator.utils.bubble import is_ignore  # type: ignore
+            from .host.bubble import is_ignore
         for indices in chunks(perm, max_chunk_size):
             N = len(indices)
             widths = [region_imgs[i].shape[1] for i in indices]
@@ -266,8 +268,10 @@ class LamaMPEInpainter(_InjectableWeights, OfflineInpainter):
                 mask01 = mask >= 128                   # == (mask / 255 >= 0.5) for uint8: 127/255 < 0.5 <= 128/255
             else:
                 mask01 = ((mask.astype(np.float32) / 255.0) >= 0.5).astype(np.float32)
-            rel_pos, direct = mpe.mpe_tables_256(mask01)
-            rel_pos, direct = eng.h2d(rel_pos[None]), eng.h2d(direct[None])
+            # 256x256 INTER_AREA reduction on the host (cv2 defines it), the iterative distance / direction sweep on the device
+            with trace("host:mpe_small"):
+                small = mpe.small_mask_256(mask01)
+            rel_pos, direct = eng.mpe_tables_256(small)
         # /255, mask binarisation, pre-masking, network, blend, (x*255) truncation and (when no resize happened) the final
         # composite with the original page all run on the device; only uint8 crosses the bus.
         out_dev = eng.lama_infer_u8(eng.h2d(np.ascontiguousarray(image)), eng.h2d(np.ascontiguousarray(mask)), rel_pos, direct,

@@ -149,6 +149,28 @@ def test_fft_impulse_and_roundtrip(eng):
     _close(eng.irfft2(spec, 20), x, 2e-6, what="fft round trip")
 
 
+def test_mpe_tables_device_equals_host(eng):
+    """The device distance / direction sweep (mitb_op_mpe_tables) is bit-identical to the host restatement of
+    load_masked_position_encoding (inpainting_lama_mpe.py:751-815), incl. the degenerate all-hole / no-hole masks."""
+    from mit_b200.host import mpe
+    rng = np.random.default_rng(5)
+    masks = [np.zeros((300, 500), np.float32), np.ones((256, 256), np.float32)]
+    for (h, w) in ((256, 256), (300, 500), (2048, 1536), (97, 1200)):
+        m = np.zeros((h, w), np.float32)
+        for _ in range(int(rng.integers(1, 9))):
+            bh, bw = int(rng.integers(2, max(3, h // 2))), int(rng.integers(2, max(3, w // 2)))
+            y0, x0 = int(rng.integers(0, h - bh)), int(rng.integers(0, w - bw))
+            m[y0:y0 + bh, x0:x0 + bw] = 1
+        masks.append(m)
+    m = np.ones((512, 512), np.float32); m[200:203, 100:400] = 0          # a thin known strip inside a page-wide hole: > 127 steps
+    masks.append(m)
+    for m in masks:
+        rel_h, dir_h = mpe.mpe_tables_256(m)
+        rel_d, dir_d = eng.mpe_tables_256(mpe.small_mask_256(m))
+        assert np.array_equal(rel_d[0].cpu().numpy(), rel_h), m.shape
+        assert np.array_equal(dir_d[0].cpu().numpy(), dir_h), m.shape
+
+
 def test_attention(eng):
     g = torch.Generator().manual_seed(9)
     n, t, heads, hd = 3, 57, 8, 40

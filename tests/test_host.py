@@ -100,6 +100,30 @@ def test_unclip_and_boxes_on_synthetic_prob_map():
     assert p.sum(axis=1).argmin() == 0                              # starts at the top-left corner
 
 
+def test_clipper_round_offset_hand_derived_vectors():
+    """ClipperOffset (6.4.2) restatement behind `unclip` (dbnet_utils.py:146-152), against vectors derived by hand from the published
+    algorithm: square (0,0)-(10,10), delta 2 -> ArcTolerance 0.25 gives pi/acos(1-0.125) = 6.2165 steps per turn, i.e. a 57.91 degree
+    rotation per step and round(1.554) = 2 steps per right-angle corner; every vertex = Round(corner + normal*delta), half away from zero:
+    corner (0,0): normal (-1,0) -> (-2,0); rotated 57.91 deg -> (-1.063,-1.694) -> (-1,-2); closing normal (0,-1) -> (0,-2); and so on."""
+    want = [(-2, 0), (-1, -2), (0, -2), (10, -2), (12, -1), (12, 0), (12, 10), (11, 12), (10, 12), (0, 12), (-2, 11), (-2, 10)]
+    sq = [(0, 0), (10, 0), (10, 10), (0, 10)]
+    assert det_post.clipper_offset_round(sq, 2.0) == want
+    assert det_post.clipper_offset_round(sq[::-1], 2.0) == want                      # FixOrientations: input winding does not matter
+    assert det_post.clipper_offset_round(sq + [sq[0]], 2.0) == want                  # closing duplicate stripped by AddPath
+    # pyclipper truncates float coordinates toward zero before Clipper sees them
+    assert det_post.clipper_offset_round([(0.9, 0.9), (10.9, 0.2), (10.5, 10.7), (0.1, 10.99)], 2.0) == want
+    assert det_post.clipper_offset_round([(0, 0), (0, 0), (5, 5)], 2.0) == []        # < 3 distinct vertices: path dropped
+    assert det_post.clipper_offset_round(sq, 0) == sq
+    # DBNet's use: rectangle 100 x 20, ratio 2.3 -> distance A*r/L = 2000*2.3/240 = 19.1667; sides land on Round(10 - 19.17) = -9,
+    # Round(110 + 19.17) = 129, Round(30 + 19.17) = 49; six vertices per corner (round(19.43/4) = 5 arc steps + the closing one)
+    box = np.array([[10, 10], [110, 10], [110, 30], [10, 30]], np.float32)
+    poly = det_post.clipper_offset_round(box, 2000 * 2.3 / 240)
+    xs, ys = [p[0] for p in poly], [p[1] for p in poly]
+    assert len(poly) == 24 and (min(xs), max(xs), min(ys), max(ys)) == (-9, 129, -9, 49) and poly[0] == (-9, 10)
+    pts, sside = det_post.mini_box(det_post.unclip(box, 2.3))
+    assert sside == 58.0 and sorted(map(tuple, np.array(pts).tolist())) == [(-9.0, -9.0), (-9.0, 49.0), (129.0, -9.0), (129.0, 49.0)]
+
+
 def test_synthetic_page_is_deterministic():
     p1, b1, m1 = synth.make_page(3, 512, 384, 6)
     p2, b2, m2 = synth.make_page(3, 512, 384, 6)
@@ -170,6 +194,48 @@ def test_detector_helpers_match_reference():
     for size in (512, 256, 300):
         a, b = det_post.resize_aspect_ratio(img, size, cv2.INTER_LINEAR), ip.resize_aspect_ratio(img, size, cv2.INTER_LINEAR, mag_ratio=1)
         assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+
+
+@needs_ref
+def test_boxes_from_prob_equals_reference_representer():
+    """D9 end to end: the reference's own SegDetectorRepresenter.boxes_from_bitmap (dbnet_utils.py:96-144) executed here, with the
+    two absent third-party calls adapted (pyclipper.PyclipperOffset -> our Clipper 6.4.2 restatement, shapely Polygon.area/.length ->
+    shoelace / perimeter), against host.det_post.boxes_from_prob: contour order, mini boxes, scores, thresholds, unclip call,
+    scale / clip / round / roll must agree EXACTLY (boxes int64 and scores)."""
+    warnings.filterwarnings("ignore")
+    refload.load()
+    import importlib
+    du = importlib.import_module("manga_translator.detection.default_utils.dbnet_utils")
+
+    class _Offset:
+        def AddPath(self, box, jt, et):
+            self.box = box
+
+        def Execute(self, d):
+            return [det_post.clipper_offset_round(self.box, d)]
+
+    class _Poly:
+        def __init__(self, b):
+            self.area, self.length = geometry.polygon_area(np.asarray(b, np.float64)), geometry.polygon_perimeter(np.asarray(b, np.float64))
+    saved = (du.pyclipper, du.Polygon)
+    du.pyclipper = type("pc", (), dict(PyclipperOffset=_Offset, JT_ROUND=1, ET_CLOSEDPOLYGON=2))
+    du.Polygon = _Poly
+    try:
+        rng = np.random.default_rng(11)
+        prob = (0.05 * rng.random((400, 600))).astype(np.float32)
+        for k in range(14):                                        # rotated / thin / tiny blobs, some below box_thresh
+            cx, cy, w, h, ang = rng.integers(40, 560), rng.integers(40, 360), rng.integers(3, 120), rng.integers(3, 40), rng.uniform(0, 180)
+            pts = cv2.boxPoints(((float(cx), float(cy)), (float(w), float(h)), float(ang))).astype(np.int32)
+            cv2.fillPoly(prob, [pts], float(rng.uniform(0.55, 0.99)))
+        rep = du.SegDetectorRepresenter(0.5, 0.7, unclip_ratio=2.3)
+        for (dw, dh) in ((600, 400), (1500, 1000)):
+            rb, rs = rep.boxes_from_bitmap(prob, prob > 0.5, dw, dh)
+            mb, ms = det_post.boxes_from_prob(prob, 0.5, 0.7, 2.3, dw, dh)
+            assert rb.shape == mb.shape and len(rb) >= 8
+            assert np.array_equal(rb, mb) and np.array_equal(rs, ms)
+            assert (mb.reshape(len(mb), -1).sum(1) > 0).sum() >= 3
+    finally:
+        du.pyclipper, du.Polygon = saved
 
 
 def test_bench_roofline_object_from_profile():
@@ -259,6 +325,11 @@ class _FakeEngine:
         colors = rng.random((n, self.T, 6)).astype(np.float32)
         self.calls.append(("ocr", region.shape))
         return pred, logprob, colors
+
+    def mpe_tables_256(self, small):
+        import numpy as np
+        assert small.shape == (256, 256) and small.dtype == np.uint8
+        return np.zeros((1, 256, 256), np.int32), np.zeros((1, 256, 256, 4), np.int32)
 
     def lama_infer_u8(self, img, mask, rel, direct, composite=True):
         self.calls.append(("lama", img.shape, mask.shape, None if rel is None else rel.shape, composite))
