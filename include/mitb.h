@@ -60,7 +60,7 @@ const char* mitb_profile_report(mitb_ctx* ctx);
 /* ---- DBNet-ConvNeXt text detector (state_dict keys of DBNetConvNext, dbnet_convnext.py:450-472) ---- */
 int mitb_dbnet_load(mitb_ctx* ctx, const mitb_tensor* weights, int n_weights);
 int mitb_dbnet_unload(mitb_ctx* ctx);
-/* x: [n,3,h,w] already normalised (u8/127.5-1), h and w multiples of 256.
+/* x: [n,3,h,w] already normalised (u8/127.5-1), h and w multiples of 128 (the reference pads to 256).
  * db: [n,2,h,w] = sigmoid(DBHead output) (channel 1 is sigmoid applied twice, as the reference does);
  * mask: [n,1,h/2,w/2]. */
 int mitb_dbnet_forward(mitb_ctx* ctx, const float* x, int n, int h, int w, float* db, float* mask, void* stream);

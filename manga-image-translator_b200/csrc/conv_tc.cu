@@ -598,6 +598,20 @@ static void make_weight_tmap(TmaDesc* out, const uint16_t* base, int kpad, int n
   memcpy(out, &m, sizeof(m));
 }
 
+// fp32 K-major [(ky*kw+kx)*4 + c][ldw] -> bf16 hi/mid [npad][kh*64] with k = ky*64 + kx*8 + c (zero elsewhere): Cin = 4 stems
+__global__ void split_weights_stem8_kernel(const float* w, int kh, int kw, int Cout, int ldw, uint16_t* wh, uint16_t* wm, int npad) {
+  const int kp = kh * 64;
+  const long total = (long)npad * kp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kp), n = (int)(i / kp);
+    const int ky = k >> 6, kx = (k & 63) >> 3, c = k & 7;
+    float x = (kx < kw && c < 4 && n < Cout) ? w[(size_t)((ky * kw + kx) * 4 + c) * ldw + n] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 m = __float2bfloat16_rn(x - __bfloat162float(h));
+    wh[i] = __bfloat16_as_ushort(h); wm[i] = __bfloat16_as_ushort(m);
+  }
+}
+
 // Build the tensor-core weight copies for a conv (called at load time by the Loader)
 void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
   const int K = cw.ntaps * cw.Cin;
@@ -624,6 +638,22 @@ void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st) {
     CUDA_OK(cudaGetLastError());
     cw.whp = whp; cw.wmp = wmp; cw.tc_cp = cp;
   }
+  if (cw.Cin == 4 && cw.ntaps > 1) {
+    // full kh x kw tap grid in row-major order (what Loader::conv / conv_padcin produce)? then pack the stem layout
+    int kw = 1; while (kw < cw.ntaps && cw.tdy[kw] == cw.tdy[0]) ++kw;
+    const int kh = cw.ntaps / kw;
+    bool grid = kh * kw == cw.ntaps && kw <= 8;
+    for (int t = 0; t < cw.ntaps && grid; ++t) grid = cw.tdy[t] == cw.tdy[0] + t / kw && cw.tdx[t] == cw.tdx[0] + t % kw;
+    if (grid) {
+      const size_t n8 = (size_t)cw.tc_npad * kh * 64;
+      uint16_t* w8h = (uint16_t*)blob.alloc_f((n8 + 1) / 2 + 4);
+      uint16_t* w8m = (uint16_t*)blob.alloc_f((n8 + 1) / 2 + 4);
+      int b3 = (int)((n8 + 255) / 256); if (b3 > 148 * 16) b3 = 148 * 16;
+      split_weights_stem8_kernel<<<b3, 256, 0, st>>>(cw.w, kh, kw, cw.Cout, cw.ldw, w8h, w8m, cw.tc_npad);
+      CUDA_OK(cudaGetLastError());
+      cw.w8h = w8h; cw.w8m = w8m; cw.w8_kh = kh; cw.w8_kw = kw;
+    }
+  }
 }
 
 int conv_tc_stat_blocks(const ConvOp& op) { return 2 * (op.tc_npad / op.tc_bn); }   // two column halves per N tile
@@ -638,6 +668,8 @@ bool conv_tc_supported(const ConvOp& op) {
 
 bool conv_tma_supported(const ConvOp& op);     // conv_tma.cu
 void launch_conv_tma(const ConvOp& op, cudaStream_t st);
+bool conv_stem8_supported(const ConvOp& op);
+void launch_conv_stem8(const ConvOp& op, cudaStream_t st);
 
 static bool tma_dispatch(const ConvOp& op) {
   if (!conv_tma_supported(op)) return false;
@@ -653,6 +685,7 @@ bool conv_tma_capable(const ConvOp& op) { return op.out.C > 4 && conv_tc_support
 bool conv_uses_tma(const ConvOp& op) { return op.out.C > 4 && conv_tc_supported(op) && tma_dispatch(op); }
 
 void launch_conv_tc(const ConvOp& op, cudaStream_t st) {
+  if (conv_stem8_supported(op)) { launch_conv_stem8(op, st); return; }
   if (tma_dispatch(op)) { launch_conv_tma(op, st); return; }
   MITB_CHECK(!op.in_sv.valid() && !op.out_sv.valid() && !op.seg2.sv.valid(), "conv: operand-fused ops must run on the TMA path");
   TcParams p;

@@ -573,6 +573,27 @@ __global__ void __launch_bounds__(256) split_halo_kernel(uint16_t* hi, uint16_t*
   }
 }
 
+// Cin = 4 stem: fp32 NHWC (4 channels) -> bf16 hi / mid [N][Hp][Wp][8] (channels 4..7 zero), halo materialised for BOTH padding modes
+// (reflect, or zeros): the stem's tensor map reads 8-pixel windows that straddle the image border, so out-of-bounds fill cannot help.
+__global__ void __launch_bounds__(256) split_stem8_kernel(const float* in, int N, int H, int W, int cs, int coff, int Hp, int Wp, int pt, int pl,
+                                                          int reflect, uint16_t* hi, uint16_t* mid) {
+  const long npix = (long)N * Hp * Wp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wp); const long r = i / Wp;
+    const int y = (int)(r % Hp), n = (int)(r / Hp);
+    int sy = y - pt, sx = x - pl;
+    bool ok = true;
+    if (reflect) { sy = reflect_tc(sy, H); sx = reflect_tc(sx, W); ok = sx >= 0 && sx < W && sy >= 0 && sy < H; }
+    else ok = sy >= 0 && sy < H && sx >= 0 && sx < W;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)(n * H + sy) * W + sx) * cs + coff));
+    uint2 h, m;
+    split4(v, h, m);
+    *reinterpret_cast<uint4*>(hi + (size_t)i * 8) = make_uint4(h.x, h.y, 0u, 0u);
+    *reinterpret_cast<uint4*>(mid + (size_t)i * 8) = make_uint4(m.x, m.y, 0u, 0u);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -599,6 +620,18 @@ void make_act_tmap(CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, 
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MITB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for activations [%d,%d,%d,%d] box %dx%d stride %dx%d", (int)r, N, Hp, Wp, C,
              bw, bh, sx, sy);
+}
+
+// Stem map over the 8-channel-padded tensor [N][Hp][Wp][8]: dimension 0 = 64 consecutive elements = an 8-pixel x 8-channel window,
+// dimension 1 = the window's first pixel with a stride of ONE pixel (16 bytes) - consecutive windows overlap by 7 pixels, which a
+// tensor map is free to describe (addresses are just sum(coord * stride)).  One box row = one output pixel's kernel row.
+bool make_stem_tmap(CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int bw, int bh) {
+  const cuuint64_t gdim[4] = {64, (cuuint64_t)(Wp - 7), (cuuint64_t)Hp, (cuuint64_t)N};
+  const cuuint64_t gstride[3] = {16, (cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16};
+  const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // weight map over bf16 [rows][kdim] K-major: box {64 k, bn}; rows beyond `rows` are zero filled
@@ -707,12 +740,30 @@ bool conv_tma_supported(const ConvOp& op) {
   return true;
 }
 
-void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
+static bool g_stem_map_failed = false;       // the driver refused the overlapping-stride map once: keep the gather kernel for stems
+
+bool conv_stem8_supported(const ConvOp& op) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("MITB_NO_STEM8"); env = (e && atoi(e)) ? 0 : 1; }
+  if (!g_tma_enabled || !env || g_stem_map_failed || !op.w8h || !op.w8m) return false;
+  if (op.in.C != 4 || op.in.planar || op.sx != 1 || op.sy != 1 || op.ntaps != op.w8_kh * op.w8_kw) return false;
+  if ((op.in.cs | op.in.coff) & 3) return false;
+  if (op.in_sv.valid() || op.seg2.sv.valid() || op.stat_max || op.out.C <= 4) return false;
+  if (op.pad == PAD_REFLECT && (-op.tdy[0] >= op.in.H || -op.tdx[0] >= op.in.W)) return false;
+  return (long)op.in.N * op.Ho * op.Wo >= 128;
+}
+
+static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem);
+void launch_conv_tma(const ConvOp& op, cudaStream_t st) { tma_launch(op, st, false); }
+void launch_conv_stem8(const ConvOp& op, cudaStream_t st) { tma_launch(op, st, true); }
+
+static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
   const int C = op.in.C, N = op.in.N, H = op.in.H, W = op.in.W;
-  const bool padded_w = C % 64 != 0;
-  const int cblks = (C + TC_BK - 1) / TC_BK;                          // K blocks per tap; channels >= C arrive as zeros (TMA bounds)
+  const bool padded_w = !stem && C % 64 != 0;
+  const int cblks = stem ? 1 : (C + TC_BK - 1) / TC_BK;              // K blocks per tap; channels >= C arrive as zeros (TMA bounds)
   int pt, pb, pl, pr;
-  conv_halo(op.tdy, op.tdx, op.ntaps, op.pad, H, W, op.Ho, op.Wo, op.sy, op.sx, pt, pb, pl, pr);
+  conv_halo(op.tdy, op.tdx, op.ntaps, stem ? PAD_REFLECT : op.pad, H, W, op.Ho, op.Wo, op.sy, op.sx, pt, pb, pl, pr);
+  if (stem) pr += 8 - op.w8_kw;                                       // every window is 8 pixels wide (the extra taps have zero weights)
   SplitView sv; int sv_coff = 0;
   int dev = 0; CUDA_OK(cudaGetDevice(&dev));
   // the split cache below: remembers which tensor the per-device scratch currently holds
@@ -737,6 +788,16 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     }
     MITB_CHECK(!op.in_scale, "tma conv: in_sv carries its prologue already");
     MITB_CHECK(!padded_w || sv_coff + C == sv.C, "tma conv: Cin %% 64 != 0 needs the slice to end at the tensor's last channel");
+  } else if (stem) {
+    sv.N = N; sv.H = H; sv.W = W; sv.C = 8; sv.pt = pt; sv.pl = pl; sv.Hp = H + pt + pb; sv.Wp = W + pl + pr;
+    static DeviceScratch g_stem;
+    sv.hi = static_cast<uint16_t*>(g_stem.get(2 * sv.elems() * sizeof(uint16_t))); sv.mid = sv.hi + sv.elems();
+    const long npix = (long)N * sv.Hp * sv.Wp;
+    long blocks = (npix + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+    split_stem8_kernel<<<(int)blocks, 256, 0, st>>>(op.in.p, N, H, W, op.in.cs, op.in.coff, sv.Hp, sv.Wp, pt, pl, op.pad == PAD_REFLECT ? 1 : 0,
+                                                    sv.hi, sv.mid);
+    count_launch();
+    MITB_CHECK(!op.in_scale, "stem conv: no input prologue");
   } else {
     // ---- split pass into the per-device scratch, skipped when the previous kernel launched by this library was a TMA conv
     // over exactly the same input (the four sub-pixel phases of a transposed conv, sibling convs of one tensor).
@@ -771,10 +832,11 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   const bool two = op.seg2.sv.valid();
   p.nseg = two ? 2 : 1;
-  p.seg[0].ntaps = op.ntaps; p.seg[0].cblks = cblks; p.seg[0].c0 = sv_coff;
-  for (int t = 0; t < op.ntaps; ++t) { p.seg[0].tdy[t] = (int8_t)(op.tdy[t] + sv.pt); p.seg[0].tdx[t] = (int8_t)(op.tdx[t] + sv.pl); }
+  p.seg[0].ntaps = stem ? op.w8_kh : op.ntaps; p.seg[0].cblks = cblks; p.seg[0].c0 = sv_coff;
+  if (stem) for (int t = 0; t < op.w8_kh; ++t) { p.seg[0].tdy[t] = (int8_t)(op.tdy[t * op.w8_kw] + sv.pt); p.seg[0].tdx[t] = (int8_t)(op.tdx[0] + sv.pl); }
+  else for (int t = 0; t < op.ntaps; ++t) { p.seg[0].tdy[t] = (int8_t)(op.tdy[t] + sv.pt); p.seg[0].tdx[t] = (int8_t)(op.tdx[t] + sv.pl); }
   p.N = N; p.Ho = op.Ho; p.Wo = op.Wo; p.M = N * op.Ho * op.Wo; p.sy = op.sy; p.sx = op.sx;
-  const bool lin = !two && op.ntaps == 1 && op.Ho == H && op.Wo == W && op.sy == 1 && op.sx == 1 && op.tdy[0] == 0 && op.tdx[0] == 0 &&
+  const bool lin = !stem && !two && op.ntaps == 1 && op.Ho == H && op.Wo == W && op.sy == 1 && op.sx == 1 && op.tdy[0] == 0 && op.tdx[0] == 0 &&
                    sv.Hp == H && sv.Wp == W;
   p.lin = lin ? 1 : 0;                                              // 1x1: flattened [pixels][C] matrix
   int bw, bh;
@@ -790,9 +852,15 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
     p.tiles_x = (op.Wo + bw - 1) / bw; p.tiles_y = (op.Ho + bh - 1) / bh;
   }
   p.bw_log2 = 0; while ((1 << p.bw_log2) < bw) ++p.bw_log2;
-  if (lin) { make_act_tmap(&p.seg[0].ta_hi, sv.hi, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); make_act_tmap(&p.seg[0].ta_mid, sv.mid, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); }
+  if (stem) {
+    if (!make_stem_tmap(&p.seg[0].ta_hi, sv.hi, N, sv.Hp, sv.Wp, bw, bh) || !make_stem_tmap(&p.seg[0].ta_mid, sv.mid, N, sv.Hp, sv.Wp, bw, bh)) {
+      g_stem_map_failed = true;                                        // fall back for good: conv_stem8_supported() is false from now on
+      launch_conv(op, st);
+      return;
+    }
+  } else if (lin) { make_act_tmap(&p.seg[0].ta_hi, sv.hi, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); make_act_tmap(&p.seg[0].ta_mid, sv.mid, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); }
   else { make_act_tmap(&p.seg[0].ta_hi, sv.hi, N, sv.Hp, sv.Wp, sv.C, bw, bh, op.sx, op.sy); make_act_tmap(&p.seg[0].ta_mid, sv.mid, N, sv.Hp, sv.Wp, sv.C, bw, bh, op.sx, op.sy); }
-  int kdim = op.ntaps * cblks * TC_BK;
+  int kdim = (stem ? op.w8_kh : op.ntaps) * cblks * TC_BK;
   if (two) {
     const ConvOp::Seg2& s2 = op.seg2;
     MITB_CHECK(!padded_w && s2.C % 64 == 0 && s2.ntaps >= 1 && s2.sv.N == N && s2.sv.H == op.Ho && s2.sv.W == op.Wo && op.sy == 1 && op.sx == 1 &&
@@ -826,8 +894,8 @@ void launch_conv_tma(const ConvOp& op, cudaStream_t st) {
   }
   MITB_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "tma conv: bad BN %d", p.BN);
   p.npad = (op.out.C + p.BN - 1) / p.BN * p.BN;
-  make_w_tmap(&p.tb_hi, padded_w ? op.whp : op.wh, kdim, op.tc_npad, p.BN / cg);
-  make_w_tmap(&p.tb_mid, padded_w ? op.wmp : op.wm, kdim, op.tc_npad, p.BN / cg);
+  make_w_tmap(&p.tb_hi, stem ? op.w8h : padded_w ? op.whp : op.wh, kdim, op.tc_npad, p.BN / cg);
+  make_w_tmap(&p.tb_mid, stem ? op.w8m : padded_w ? op.wmp : op.wm, kdim, op.tc_npad, p.BN / cg);
   p.out = op.out.p; p.oH = op.out.H; p.oW = op.out.W; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C;
   p.out_planar = op.out.planar; p.oy_mul = op.oy_mul; p.oy_add = op.oy_add; p.ox_mul = op.ox_mul; p.ox_add = op.ox_add;
   p.add0 = op.add0.p; p.add0_cs = op.add0.cs; p.add0_coff = op.add0.coff; p.add0_planar = op.add0.planar;

@@ -174,7 +174,8 @@ static void run_upconv(Exec& e, const Upconv& u, const View& x, const View& out)
 
 void dbnet_run(Ctx& ctx, DbnetModel& m, const float* x_nchw, const uint8_t* x_u8, int n, int h, int w, float* db, float* mask,
                cudaStream_t st) {
-  MITB_CHECK(n >= 1 && h % 256 == 0 && w % 256 == 0 && h > 0 && w > 0, "dbnet: input %dx%d must be a positive multiple of 256", h, w);
+  // every stride of the network divides 128 (coarsest map = 1/128); the reference's own pre-processing pads to 256 (imgproc.py:37-70)
+  MITB_CHECK(n >= 1 && h % 128 == 0 && w % 128 == 0 && h > 0 && w > 0, "dbnet: input %dx%d must be a positive multiple of 128", h, w);
   run_with_workspace(ctx, st, [&](Exec& e) {
     Arena& ws = e.ws();
     // persistent buffers: concat inputs of the decoder. cat_k = [ up (128) | skip ]

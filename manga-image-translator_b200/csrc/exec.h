@@ -17,6 +17,7 @@ struct Exec {
     op.scale = w.scale; op.shift = w.shift;
     op.wh = w.wh; op.wm = w.wm; op.tc_bn = w.tc_bn; op.tc_kpad = w.tc_kpad; op.tc_npad = w.tc_npad; op.tmh = w.tmh; op.tmm = w.tmm;
     op.whp = w.whp; op.wmp = w.wmp; op.tc_cp = w.tc_cp;
+    op.w8h = w.w8h; op.w8m = w.w8m; op.w8_kh = w.w8_kh; op.w8_kw = w.w8_kw;
     return op;
   }
   void conv(const ConvOp& op) { if (!dry) launch_conv(op, st); }

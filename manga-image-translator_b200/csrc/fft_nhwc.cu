@@ -33,7 +33,7 @@ constexpr int FV = 32;                 // complex channels per CTA (= lanes of a
 constexpr int FT = 256, FW = FT / 32;  // threads / warps per CTA
 constexpr int kMaxSt = 10;
 
-struct FftNDev { int n, nst; int radix[kMaxSt]; const float2* tw; const uint16_t* rev; };
+struct FftNDev { int n, nst, nbt; int radix[kMaxSt]; const float2* tw; const uint16_t* rev; };   // nbt: butterflies over all stages
 
 #include "tc_common.cuh"
 
@@ -45,34 +45,45 @@ __device__ __forceinline__ float2 rot90(float2 a, bool inv) { return inv ? make_
 
 // In-place decimation-in-frequency FFT of FV interleaved sequences X[i * FV + lane], i < n: natural-order input, the
 // output element k ends at position rev[k].  All threads of the CTA call it; `tw` is the shared-memory twiddle table
-// exp(-2 pi i j / n), j < n.  inv conjugates twiddles (unscaled inverse).
-__device__ __forceinline__ void fft_dif(float2* X, const float2* tw, const FftNDev& pl, bool inv, int lane, int warp) {
+// exp(-2 pi i j / n), j < n; `bt` the shared-memory butterfly table (one entry per butterfly of every stage: first element
+// index | twiddle step << 16), so the hot loop has no integer division.  INV conjugates twiddles (unscaled inverse).
+template <bool INV>
+__device__ __forceinline__ float2 twc(const float2* tw, int i) { float2 w = tw[i]; if (INV) w.y = -w.y; return w; }
+
+template <bool INV>
+__device__ __forceinline__ void fft_dif(float2* X, const float2* tw, const uint32_t* bt, const FftNDev& pl, int lane, int warp) {
   int L = pl.n;
   for (int st = 0; st < pl.nst; ++st) {
     const int r = pl.radix[st];
     const int m = L / r;                 // length of the sub-sequences this stage produces
     const int nb = pl.n / r;
-    const int ts = pl.n / L;             // twiddle w_L^j = tw[j * ts]
-    for (int b = warp; b < nb; b += FW) {
-      const int g = b / m, k = b - g * m;
-      float2* x = X + (size_t)(g * L + k) * FV + lane;
-      const size_t sm = (size_t)m * FV;
-      if (r == 4) {
+    const uint32_t sm = (uint32_t)m * FV;
+    if (r == 4) {
+      for (int b = warp; b < nb; b += FW) {
+        const uint32_t e = bt[b];
+        float2* x = X + (e & 0xffffu) * FV + lane;
+        const int kt = (int)(e >> 16);
         const float2 a0 = x[0], a1 = x[sm], a2 = x[2 * sm], a3 = x[3 * sm];
-        const float2 t0 = caddf(a0, a2), t1 = csubf(a0, a2), t2 = caddf(a1, a3), t3 = rot90(csubf(a1, a3), inv);
+        const float2 t0 = caddf(a0, a2), t1 = csubf(a0, a2), t2 = caddf(a1, a3), t3 = rot90(csubf(a1, a3), INV);
         float2 y1 = caddf(t1, t3), y2 = csubf(t0, t2), y3 = csubf(t1, t3);
-        if (k) {
-          float2 w1 = tw[k * ts], w2 = tw[2 * k * ts], w3 = tw[3 * k * ts];
-          if (inv) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-          y1 = cmulf(y1, w1); y2 = cmulf(y2, w2); y3 = cmulf(y3, w3);
-        }
+        if (kt) { y1 = cmulf(y1, twc<INV>(tw, kt)); y2 = cmulf(y2, twc<INV>(tw, 2 * kt)); y3 = cmulf(y3, twc<INV>(tw, 3 * kt)); }
         x[0] = caddf(t0, t2); x[sm] = y1; x[2 * sm] = y2; x[3 * sm] = y3;
-      } else if (r == 2) {
+      }
+    } else if (r == 2) {
+      for (int b = warp; b < nb; b += FW) {
+        const uint32_t e = bt[b];
+        float2* x = X + (e & 0xffffu) * FV + lane;
+        const int kt = (int)(e >> 16);
         const float2 a0 = x[0], a1 = x[sm];
         float2 y1 = csubf(a0, a1);
-        if (k) { float2 w1 = tw[k * ts]; if (inv) w1.y = -w1.y; y1 = cmulf(y1, w1); }
+        if (kt) y1 = cmulf(y1, twc<INV>(tw, kt));
         x[0] = caddf(a0, a1); x[sm] = y1;
-      } else if (r == 3) {
+      }
+    } else if (r == 3) {
+      for (int b = warp; b < nb; b += FW) {
+        const uint32_t e = bt[b];
+        float2* x = X + (e & 0xffffu) * FV + lane;
+        const int kt = (int)(e >> 16);
         const float2 a0 = x[0], a1 = x[sm], a2 = x[2 * sm];
         const float2 t1 = caddf(a1, a2);
         const float2 t2 = make_float2(a0.x - 0.5f * t1.x, a0.y - 0.5f * t1.y);
@@ -80,16 +91,17 @@ __device__ __forceinline__ void fft_dif(float2* X, const float2* tw, const FftND
         const float2 t3 = make_float2(0.86602540378443864676f * d.x, 0.86602540378443864676f * d.y);
         // forward: y1 = t2 - i t3, y2 = t2 + i t3 ; inverse: swapped
         float2 y1 = make_float2(t2.x + t3.y, t2.y - t3.x), y2 = make_float2(t2.x - t3.y, t2.y + t3.x);
-        if (inv) { const float2 t = y1; y1 = y2; y2 = t; }
-        if (k) {
-          float2 w1 = tw[k * ts], w2 = tw[2 * k * ts];
-          if (inv) { w1.y = -w1.y; w2.y = -w2.y; }
-          y1 = cmulf(y1, w1); y2 = cmulf(y2, w2);
-        }
+        if (INV) { const float2 t = y1; y1 = y2; y2 = t; }
+        if (kt) { y1 = cmulf(y1, twc<INV>(tw, kt)); y2 = cmulf(y2, twc<INV>(tw, 2 * kt)); }
         x[0] = caddf(a0, t1); x[sm] = y1; x[2 * sm] = y2;
-      } else {   // r == 5
-        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+      }
+    } else {   // r == 5
+      const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+      const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+      for (int b = warp; b < nb; b += FW) {
+        const uint32_t e = bt[b];
+        float2* x = X + (e & 0xffffu) * FV + lane;
+        const int kt = (int)(e >> 16);
         const float2 a0 = x[0], a1 = x[sm], a2 = x[2 * sm], a3 = x[3 * sm], a4 = x[4 * sm];
         const float2 b1 = caddf(a1, a4), b2 = caddf(a2, a3), d1 = csubf(a1, a4), d2 = csubf(a2, a3);
         const float2 p1 = make_float2(a0.x + c1 * b1.x + c2 * b2.x, a0.y + c1 * b1.y + c2 * b2.y);
@@ -99,17 +111,27 @@ __device__ __forceinline__ void fft_dif(float2* X, const float2* tw, const FftND
         // forward: y1 = p1 - i q1, y4 = p1 + i q1, y2 = p2 - i q2, y3 = p2 + i q2 ; inverse: signs flipped
         float2 y1 = make_float2(p1.x + q1.y, p1.y - q1.x), y4 = make_float2(p1.x - q1.y, p1.y + q1.x);
         float2 y2 = make_float2(p2.x + q2.y, p2.y - q2.x), y3 = make_float2(p2.x - q2.y, p2.y + q2.x);
-        if (inv) { float2 t = y1; y1 = y4; y4 = t; t = y2; y2 = y3; y3 = t; }
-        if (k) {
-          float2 w1 = tw[k * ts], w2 = tw[2 * k * ts], w3 = tw[3 * k * ts], w4 = tw[4 * k * ts];
-          if (inv) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
-          y1 = cmulf(y1, w1); y2 = cmulf(y2, w2); y3 = cmulf(y3, w3); y4 = cmulf(y4, w4);
-        }
+        if (INV) { float2 t = y1; y1 = y4; y4 = t; t = y2; y2 = y3; y3 = t; }
+        if (kt) { y1 = cmulf(y1, twc<INV>(tw, kt)); y2 = cmulf(y2, twc<INV>(tw, 2 * kt)); y3 = cmulf(y3, twc<INV>(tw, 3 * kt)); y4 = cmulf(y4, twc<INV>(tw, 4 * kt)); }
         x[0] = caddf(a0, caddf(b1, b2)); x[sm] = y1; x[2 * sm] = y2; x[3 * sm] = y3; x[4 * sm] = y4;
       }
     }
     __syncthreads();
+    bt += nb;
     L = m;
+  }
+}
+
+// butterfly table of every stage (see fft_dif): entry = (g * L + k) | (k * (n / L)) << 16 for butterfly b = g * m + k
+__device__ __forceinline__ void build_btab(const FftNDev& pl, uint32_t* bt) {
+  int L = pl.n, off = 0;
+  for (int st = 0; st < pl.nst; ++st) {
+    const int r = pl.radix[st], m = L / r, nb = pl.n / r, ts = pl.n / L;
+    for (int b = threadIdx.x; b < nb; b += FT) {
+      const int g = b / m, k = b - g * m;
+      bt[off + b] = (uint32_t)(g * L + k) | ((uint32_t)(k * ts) << 16);
+    }
+    off += nb; L = m;
   }
 }
 
@@ -125,8 +147,9 @@ struct FftKParams {
   float scale;
 };
 
-__device__ __forceinline__ void load_tables(const FftNDev& pl, float2* tw, uint16_t* rev) {
+__device__ __forceinline__ void load_tables(const FftNDev& pl, float2* tw, uint16_t* rev, uint32_t* bt) {
   for (int i = threadIdx.x; i < pl.n; i += FT) { tw[i] = __ldg(pl.tw + i); rev[i] = __ldg(pl.rev + i); }
+  build_btab(pl, bt);
 }
 
 // tile rows -> X[row * FV + lane] (float2): one TMA box {64 floats, box_rows} per `box_rows` rows, or plain coalesced loads
@@ -157,13 +180,14 @@ __device__ __forceinline__ void store_pair(const FftKParams& p, size_t pix, int 
   }
 }
 
-// smem: X[n][FV] float2 | tw[n] float2 | rev[n] u16 | mbarrier
+// smem: X[n][FV] float2 | tw[n] float2 | bt[nbt] u32 | rev[n] u16 | mbarrier
 #define FFT_SMEM_CARVE(n)                                                                   \
   extern __shared__ __align__(128) uint8_t fsm_raw[];                                       \
   float2* X = reinterpret_cast<float2*>(fsm_raw);                                           \
   float2* tw = X + (size_t)(n) * FV;                                                        \
-  uint16_t* rev = reinterpret_cast<uint16_t*>(tw + (n));                                    \
-  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm_raw + (((size_t)(n) * FV * 8 + (size_t)(n) * 10 + 15) & ~(size_t)15)); \
+  uint32_t* bt = reinterpret_cast<uint32_t*>(tw + (n));                                     \
+  uint16_t* rev = reinterpret_cast<uint16_t*>(bt + p.pl.nbt);                               \
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm_raw + (((size_t)(n) * FV * 8 + (size_t)(n) * 10 + (size_t)p.pl.nbt * 4 + 15) & ~(size_t)15)); \
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                               \
   if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -173,12 +197,12 @@ __global__ void __launch_bounds__(FT) rfft_rows_nhwc_kernel(const __grid_constan
   const int row = blockIdx.x, chunk = blockIdx.y;
   const int pair = chunk * FV + lane;
   const bool ok = 2 * pair < p.C;
-  load_tables(p.pl, tw, rev);
+  load_tables(p.pl, tw, rev, bt);
   __syncthreads();
   stage_tile(p, X, bar, p.w, p.in_coff + chunk * 2 * FV, (long)row * p.w, p.in + ((size_t)row * p.w) * p.in_cs + p.in_coff + chunk * 2 * FV,
              p.in_cs, ok, lane, warp);
   __syncthreads();
-  fft_dif(X, tw, p.pl, false, lane, warp);
+  fft_dif<false>(X, tw, bt, p.pl, lane, warp);
   float2* dst = reinterpret_cast<float2*>(p.out_f) + (size_t)row * p.w2 * p.C;
   for (int k = warp; k < p.w2; k += FW) {
     const int kc = k ? p.w - k : 0;
@@ -198,14 +222,14 @@ __global__ void __launch_bounds__(FT) fft_cols_nhwc_kernel(const __grid_constant
   const int n = blockIdx.x / p.w2, kx = blockIdx.x - n * p.w2, chunk = blockIdx.y;
   const int ch = chunk * FV + lane;                     // complex channel
   const bool ok = ch < p.C;
-  load_tables(p.pl, tw, rev);
+  load_tables(p.pl, tw, rev, bt);
   __syncthreads();
   // input element (ky, kx, ch) as float2 at in + (((n*h + ky)*w2 + kx) * in_cs + in_coff + 2*ch) floats
   const size_t pix0 = (size_t)n * p.h * p.w2 + kx;
   stage_tile(p, X, bar, p.h, kx * p.in_cs + p.in_coff + chunk * 2 * FV, (long)n * p.h,
              p.in + pix0 * p.in_cs + p.in_coff + chunk * 2 * FV, (long)p.w2 * p.in_cs, ok, lane, warp);
   __syncthreads();
-  fft_dif(X, tw, p.pl, INV, lane, warp);
+  fft_dif<INV>(X, tw, bt, p.pl, lane, warp);
   for (int ky = warp; ky < p.h; ky += FW) {
     float2 z = X[(size_t)rev[ky] * FV + lane];
     if (!ok) continue;
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(FT) irfft_rows_nhwc_kernel(const __grid_consta
   const int row = blockIdx.x, chunk = blockIdx.y;
   const int pair = chunk * FV + lane;
   const bool ok = 2 * pair < p.C;
-  load_tables(p.pl, tw, rev);
+  load_tables(p.pl, tw, rev, bt);
   const float2* src = reinterpret_cast<const float2*>(p.in) + (size_t)row * p.w2 * p.C;
   for (int k = warp; k < p.w2; k += FW) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -233,7 +257,7 @@ __global__ void __launch_bounds__(FT) irfft_rows_nhwc_kernel(const __grid_consta
     if (!self) X[(size_t)(p.w - k) * FV + lane] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
   }
   __syncthreads();
-  fft_dif(X, tw, p.pl, true, lane, warp);
+  fft_dif<true>(X, tw, bt, p.pl, lane, warp);
   for (int x = warp; x < p.w; x += FW) {
     float2 z = X[(size_t)rev[x] * FV + lane];
     if (!ok) continue;
@@ -269,6 +293,8 @@ PlanN* plan_get(int n) {
   PlanN* p = new PlanN();
   p->dev.n = n;
   MITB_CHECK(factor(n, p->dev.radix, &p->dev.nst), "fft_nhwc: length %d is not {2,3,5}-smooth", n);
+  p->dev.nbt = 0;
+  for (int s = 0; s < p->dev.nst; ++s) p->dev.nbt += n / p->dev.radix[s];
   std::vector<float2> tw(n);
   for (int i = 0; i < n; ++i) { const double a = -2.0 * M_PI * (double)i / (double)n; tw[i] = make_float2((float)cos(a), (float)sin(a)); }
   // position of output k after the in-place DIF stages: pos(k; L; r1..) = (k % r1) * (L / r1) + pos(k / r1; L / r1; r2..)
@@ -313,7 +339,8 @@ bool make_tile_map(CUtensorMap* m, const float* base, long rows, long cols_f, lo
 }
 int box_rows_for(int n) { int b = n; while (b > 256) { int d = 2; while (b % d) ++d; b /= d; } return b; }   // largest "nice" divisor <= 256
 
-size_t smem_for(int n) { return (((size_t)n * FV * 8 + (size_t)n * 10 + 15) & ~(size_t)15) + 16; }
+int nbt_for(int n) { int radix[kMaxSt], nst = 0, t = 0; if (!factor(n, radix, &nst)) return 0; for (int s = 0; s < nst; ++s) t += n / radix[s]; return t; }
+size_t smem_for(int n) { return (((size_t)n * FV * 8 + (size_t)n * 10 + (size_t)nbt_for(n) * 4 + 15) & ~(size_t)15) + 16; }
 
 bool use_tma_env() {
   static int v = -1;

@@ -95,6 +95,9 @@ struct ConvOp {
   TmaDesc tmh, tmm;                   // TMA descriptors of wh / wm
   // per-tap channel-padded copies [tc_npad][ntaps*tc_cp] for the TMA-fed kernel when Cin % 64 != 0 (null otherwise)
   const uint16_t* whp = nullptr; const uint16_t* wmp = nullptr; int tc_cp = 0;
+  // Cin = 4 stems on the tensor cores: weights packed [tc_npad][kh*64], k = ky*64 + kx*8 + c (kx < kw <= 8, c < 4, rest zero): one
+  // K block per kernel row, fed by an OVERLAPPING-stride tensor map over the 8-channel-padded input (conv_tma.cu)
+  const uint16_t* w8h = nullptr; const uint16_t* w8m = nullptr; int w8_kh = 0, w8_kw = 0;
   // TMA-path operand fusion (only legal when conv_uses_tma() holds for the op):
   //  * in_sv valid  -> the input already exists as bf16 hi/mid (written by its producer); channels [in_sv_coff, +in.C) of it are
   //                    this conv's input, `in` then only carries the shape; the split pass is skipped;
@@ -187,6 +190,7 @@ struct ConvW {
   const uint16_t* wh = nullptr; const uint16_t* wm = nullptr; int tc_bn = 0, tc_kpad = 0, tc_npad = 0;
   TmaDesc tmh, tmm;
   const uint16_t* whp = nullptr; const uint16_t* wmp = nullptr; int tc_cp = 0;   // per-tap channel-padded copies (conv_tma.cu)
+  const uint16_t* w8h = nullptr; const uint16_t* w8m = nullptr; int w8_kh = 0, w8_kw = 0;   // Cin = 4 stem packing (conv_tma.cu)
 };
 struct DevBlob;
 void conv_tc_prepare(ConvW& cw, DevBlob& blob, cudaStream_t st);   // build the bf16 hi/mid tensor-core weight copies

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+from collections import OrderedDict
 from typing import Dict, Optional
 
 import numpy as np
@@ -74,7 +75,8 @@ class Engine:
         self._h = h
         self._keep = {}
         self._lock = threading.RLock()   # the context is not re-entrant: page-pipeline threads serialise their ENQUEUES here
-        self._pinned = {}       # (thread, shape, dtype) -> pinned staging tensor of d2h(scratch=True)
+        self._pin_lock = threading.Lock()
+        self._pinned = OrderedDict()   # (thread, shape, dtype) -> pinned staging tensor of d2h(scratch=True), LRU, <= 64 entries
         self.h2d_bytes = 0      # bytes moved host->device / device->host through h2d()/d2h() (bench.py e2e accounting)
         self.d2h_bytes = 0
 
@@ -97,19 +99,24 @@ class Engine:
     def _d2h(self, t: torch.Tensor, scratch: bool = False) -> np.ndarray:
         self.d2h_bytes += t.numel() * t.element_size()
         if scratch and self._pinned is not None and t.is_cuda and t.numel() * t.element_size() >= (1 << 20):
-            try:
-                key = (threading.get_ident(), tuple(t.shape), t.dtype)
+            key = (threading.get_ident(), tuple(t.shape), t.dtype)
+            with self._pin_lock:
                 buf = self._pinned.get(key)
-                if buf is None:
-                    if len(self._pinned) >= 64:          # page sizes changed often: stop growing the pinned pool
-                        raise RuntimeError("pinned pool full")
+                if buf is not None:
+                    self._pinned.move_to_end(key)
+            if buf is None:
+                try:
                     buf = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+                except RuntimeError:                      # the host cannot pin more memory: pageable copies from now on
+                    self._pinned = None
+                    return t.cpu().numpy()
+                with self._pin_lock:
                     self._pinned[key] = buf
-                buf.copy_(t, non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
-                return buf.numpy()
-            except Exception:                             # any trouble with pinned memory: permanent fallback to the plain path
-                self._pinned = None
+                    while len(self._pinned) > 64:         # page sizes / worker threads changed: drop the least recently used buffer
+                        self._pinned.popitem(last=False)
+            buf.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return buf.numpy()
         return t.cpu().numpy()
 
     # ------------------------------------------------------------------ plumbing
@@ -138,7 +145,8 @@ class Engine:
 
     def set_tensor_cores(self, on: bool):
         """Process-wide: route eligible convolutions to the tcgen05 kernel (default) or keep everything on the fp32 SIMT kernel."""
-        self.lib.mitb_set_tensor_cores(1 if on else 0)
+        with self._lock:
+            self.lib.mitb_set_tensor_cores(1 if on else 0)
 
     def set_ffc_mode(self, mode: int):
         """Process-wide LaMa FFC implementation: 0 generic planar, 1 fused NHWC when no layer needs split-K (default), 2 fused whenever capable."""
@@ -150,7 +158,8 @@ class Engine:
 
     def profile_report(self) -> dict:
         import json
-        return json.loads(self.lib.mitb_profile_report(self._h).decode())
+        with self._lock:
+            return json.loads(self.lib.mitb_profile_report(self._h).decode())
 
     @property
     def launches(self) -> int:
@@ -183,7 +192,8 @@ class Engine:
         torch.cuda.synchronize(self.device)
 
     def unload_dbnet(self):
-        self._check(self.lib.mitb_dbnet_unload(self._h))
+        with self._lock:          # never free a model while another thread is enqueueing its forward
+            self._check(self.lib.mitb_dbnet_unload(self._h))
 
     def dbnet_forward(self, x: torch.Tensor):
         """x: float32 [n,3,h,w] normalised, or uint8 [n,h,w,3]; returns (db sigmoid [n,2,h,w], mask [n,1,h/2,w/2])."""
@@ -208,7 +218,8 @@ class Engine:
         torch.cuda.synchronize(self.device)
 
     def unload_ocr(self):
-        self._check(self.lib.mitb_ocr_unload(self._h))
+        with self._lock:          # never free a model while another thread is enqueueing its forward
+            self._check(self.lib.mitb_ocr_unload(self._h))
 
     def ocr_forward(self, x: torch.Tensor):
         """x: float32 [n,3,48,wp] normalised or uint8 [n,48,wp,3]; returns (argmax int32 [n,T], logprob [n,T], colors [n,T,6])."""
@@ -235,7 +246,8 @@ class Engine:
         torch.cuda.synchronize(self.device)
 
     def unload_lama(self):
-        self._check(self.lib.mitb_lama_unload(self._h))
+        with self._lock:          # never free a model while another thread is enqueueing its forward
+            self._check(self.lib.mitb_lama_unload(self._h))
 
     def lama_forward(self, img: torch.Tensor, mask: torch.Tensor, rel_pos=None, direct=None, tables256=False):
         """rel_pos/direct: full-resolution MPE tables [n,h,w]/[n,h,w,4], or (tables256=True) the 256x256 ones."""

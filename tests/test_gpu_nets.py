@@ -59,7 +59,13 @@ def test_dbnet_rejects_bad_shapes(eng):
         eng.dbnet_forward(torch.zeros(1, 3, 256, 256))   # not loaded
     eng.load_dbnet(weights.dbnet_weights())
     with pytest.raises(MitbError):
-        eng.dbnet_forward(torch.zeros(1, 3, 200, 256))   # not a multiple of 256
+        eng.dbnet_forward(torch.zeros(1, 3, 200, 256))   # not a multiple of 128
+    # multiples of 128 that are not multiples of 256 are legal (all strides divide 128), e.g. rearranged strips at detect_size 1152
+    sd = weights.dbnet_weights()
+    _, x = cases.dbnet_case(384, 128, seed=77)
+    db, mask = eng.dbnet_forward(x)
+    o_db, o_mask = nets.dbnet_forward(sd, x)
+    assert _err(db, o_db.sigmoid()) < TOL and _err(mask, o_mask) < TOL
     eng.unload_dbnet()
 
 

@@ -369,3 +369,100 @@ def test_plugin_host_logic_with_a_fake_engine():
     assert res.shape == page.shape and inp.engine.calls[-1][-1] is False
     assert (res[~np.broadcast_to(m01, res.shape)] == page0[~np.broadcast_to(m01, page0.shape)]).all()   # untouched outside the mask
     assert (page == page0).all() and (mask == mask0).all()                               # borrowed inputs were not written
+
+
+def test_register_swaps_the_reference_registries(monkeypatch):
+    """X1: plugins.register() against stand-ins for manga_translator.{detection,ocr,inpainting} that carry the reference's registry
+    and cache names (detection/__init__.py:12-27, ocr/__init__.py:11-25, inpainting/__init__.py:13-28) and its Config enums
+    (config.py:84-108): the four entries are replaced, stale cached instances are dropped, `get_*` then constructs OUR class with
+    no arguments, and other entries are left alone."""
+    import enum
+    import sys
+    import types
+    from mit_b200 import compat, plugins
+
+    class Detector(enum.Enum):
+        default = "default"
+        dbconvnext = "dbconvnext"
+
+    class Ocr(enum.Enum):
+        ocr32px = "32px"
+        ocr48px_ctc = "48px_ctc"
+
+    class Inpainter(enum.Enum):
+        default = "default"
+        lama_mpe = "lama_mpe"
+        lama_large = "lama_large"
+
+    class Old:
+        pass
+
+    det = types.ModuleType("manga_translator.detection")
+    det.DETECTORS, det.detector_cache = {Detector.default: Old, Detector.dbconvnext: Old}, {Detector.dbconvnext: Old(), Detector.default: Old()}
+    ocr = types.ModuleType("manga_translator.ocr")
+    ocr.OCRS, ocr.ocr_cache = {Ocr.ocr32px: Old, Ocr.ocr48px_ctc: Old}, {Ocr.ocr48px_ctc: Old()}
+    inp = types.ModuleType("manga_translator.inpainting")
+    inp.INPAINTERS, inp.inpainter_cache = {Inpainter.default: Old, Inpainter.lama_mpe: Old, Inpainter.lama_large: Old}, {Inpainter.lama_large: Old()}
+    cfg = types.ModuleType("manga_translator.config")
+    cfg.Detector, cfg.Ocr, cfg.Inpainter = Detector, Ocr, Inpainter
+    root = types.ModuleType("manga_translator")
+    root.detection, root.ocr, root.inpainting, root.config = det, ocr, inp, cfg
+    for name, mod in (("manga_translator", root), ("manga_translator.detection", det), ("manga_translator.ocr", ocr),
+                      ("manga_translator.inpainting", inp), ("manga_translator.config", cfg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    monkeypatch.setattr(compat, "HAVE_REFERENCE", True)
+    plugins.register()
+    assert det.DETECTORS[Detector.dbconvnext] is plugins.DBConvNextDetector and det.DETECTORS[Detector.default] is Old
+    assert ocr.OCRS[Ocr.ocr48px_ctc] is plugins.Model48pxCTCOCR and ocr.OCRS[Ocr.ocr32px] is Old
+    assert inp.INPAINTERS[Inpainter.lama_mpe] is plugins.LamaMPEInpainter and inp.INPAINTERS[Inpainter.lama_large] is plugins.LamaLargeInpainter
+    assert inp.INPAINTERS[Inpainter.default] is Old
+    assert Detector.dbconvnext not in det.detector_cache and Detector.default in det.detector_cache
+    assert not ocr.ocr_cache and not inp.inpainter_cache
+    # the registries construct plugins with no arguments (detection/__init__.py:25-27)
+    for cls in (det.DETECTORS[Detector.dbconvnext], ocr.OCRS[Ocr.ocr48px_ctc], inp.INPAINTERS[Inpainter.lama_mpe], inp.INPAINTERS[Inpainter.lama_large]):
+        obj = cls()
+        with pytest.raises(Exception):
+            asyncio.run(obj.infer())                                   # infer before load raises (inference.py:349-350)
+    monkeypatch.setattr(compat, "HAVE_REFERENCE", False)
+    from mit_b200 import MitbError
+    with pytest.raises(MitbError):
+        plugins.register()
+
+
+def test_detect_variants_and_bubble_filter_standalone():
+    """D12 / O10 without the reference package: CommonDetector.detect's border / rotate / invert / gamma variants around a stub `_detect`
+    (detection/common.py:12-135) and utils/bubble.is_ignore."""
+    from mit_b200 import plugins
+    from mit_b200.compat import Quadrilateral
+    from mit_b200.host import bubble
+
+    class Stub(plugins.DBConvNextDetector):
+        async def _detect(self, image, *a, **k):
+            self.seen = image.copy()
+            h, w = image.shape[:2]
+            q = Quadrilateral(np.array([[10, 20], [60, 20], [60, 40], [10, 40]]), "", 0.9)
+            far = Quadrilateral(np.array([[w - 30, h - 30], [w - 5, h - 30], [w - 5, h - 5], [w - 30, h - 5]]), "", 0.8)
+            return [q, far], np.full((h // 2, w // 2), 7, np.uint8), None
+
+    det = Stub()
+    img = np.full((300, 200, 3), 200, np.uint8)
+    img[20:40, 10:60] = 30
+    # short side < 400: zero border to a 400 square, results cropped back, lines wholly inside the border dropped
+    tl, raw, _ = asyncio.run(det.detect(img, 2048, 0.5, 0.7, 2.3, False, False, False))
+    assert det.seen.shape == (400, 400, 3) and (det.seen[:300, :200] == img).all() and det.seen[300:].max() == 0
+    assert raw.shape == (300, 200) and len(tl) == 1 and tl[0].pts.max() <= 300
+    # inversion and gamma are applied to what the network sees
+    asyncio.run(det.detect(img, 2048, 0.5, 0.7, 2.3, True, False, False))
+    assert det.seen[25, 20, 0] == 255 - 30
+    asyncio.run(det.detect(img, 2048, 0.5, 0.7, 2.3, False, True, False))
+    assert det.seen.dtype == np.uint8
+    # rotation: the network sees the page rotated clockwise, boxes and mask come back in page coordinates
+    big = np.full((500, 450, 3), 200, np.uint8)
+    tl, raw, _ = asyncio.run(det.detect(big, 2048, 0.5, 0.7, 2.3, False, False, True))
+    assert det.seen.shape == (450, 500, 3) and raw.shape == (250, 225)
+    assert all(0 <= p[0] <= 450 and 0 <= p[1] <= 500 for t in tl for p in t.pts)
+    # bubble filter: plain white frame -> keep, mixed frame -> ignore, coloured crop -> ignore, parameter out of range -> off
+    white = np.full((48, 120, 3), 250, np.uint8)
+    mixed = white.copy(); mixed[:, :60] = 5
+    colour = white.copy(); colour[10:30, 10:60] = (250, 20, 20)
+    assert not bubble.is_ignore(white, 10) and bubble.is_ignore(mixed, 10) and bubble.is_ignore(colour, 10) and not bubble.is_ignore(mixed, 0)
