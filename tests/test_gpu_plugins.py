@@ -1,6 +1,6 @@
 """Plugin-level parity on the GPU: the drop-in classes' ``_infer`` against the CPU restatement of the reference's
 ``_infer`` (oracle/pipeline_ref.py) on synthetic pages, through the same call sequence the reference dispatcher uses
-(load(device) -> infer(...)).  Bars: OCR strings identical, detector quads identical and raw-mask IoU >= 0.999,
+(load(device) -> infer(...)).  Bars: OCR strings identical, detector quads identical up to threshold flips and raw-mask IoU >= 0.999,
 inpainted uint8 image within 1 LSB (the reference truncates x*255) on <0.1 % of bytes."""
 import asyncio
 
@@ -21,13 +21,16 @@ def run(coro):
 
 
 def _assert_same_detections(lines, r_lines, raw_mask, r_mask):
-    """The GPU bilateral filter may differ from this host's cv2 build by 1 LSB on a few bytes per million (FMA order), which
-    moves the (random-weight, high-gain) probability map locally; tensor-level 1e-3 parity on identical inputs is covered
-    by test_gpu_nets.py.  Here: same boxes up to rare local flips, mask IoU >= 0.999."""
-    assert abs(len(lines) - len(r_lines)) <= max(2, len(r_lines) // 20), (len(lines), len(r_lines))
+    """The pre-filter is bit-exact and the post-processing is pinned against the reference representer (tests/test_host.py); what
+    remains is the network's ~1e-5 difference from the CPU oracle, which can flip single pixels of the (random-weight, high-gain)
+    probability map at the 0.5 threshold and so move or split a box here and there.  Tensor-level 1e-3 parity on identical inputs is
+    covered by test_gpu_nets.py / test_gpu_fullsize.py.  Here: >= 95 % of the boxes identical (the rest within 1 px or flipped)."""
+    assert abs(len(lines) - len(r_lines)) <= max(1, len(r_lines) // 20), (len(lines), len(r_lines))
     ref_pts = [b.pts for b in r_lines]
-    matched = sum(1 for a in lines if any(np.abs(a.pts - p).max() <= 1 for p in ref_pts))
-    assert matched >= 0.9 * len(r_lines), (matched, len(r_lines))
+    exact = sum(1 for a in lines if any(np.array_equal(a.pts, p) for p in ref_pts))
+    near = sum(1 for a in lines if any(np.abs(a.pts - p).max() <= 1 for p in ref_pts))
+    print(f"detector boxes: {len(lines)} vs {len(r_lines)} reference, identical {exact}, within 1 px {near}")
+    assert exact >= 0.95 * len(r_lines) and near >= 0.97 * len(r_lines), (exact, near, len(r_lines))
     inter = ((raw_mask > 127) & (r_mask > 127)).sum()
     union = ((raw_mask > 127) | (r_mask > 127)).sum()
     assert union == 0 or inter / union >= 0.999
