@@ -96,21 +96,33 @@ def _inside(poly, p):
     return cv2.pointPolygonTest(poly.astype(np.float32).reshape(-1, 1, 2), (float(p[0]), float(p[1])), False) >= 0
 
 
+def _orient(p, q, r):
+    return (q[..., 0] - p[..., 0]) * (r[..., 1] - p[..., 1]) - (q[..., 1] - p[..., 1]) * (r[..., 0] - p[..., 0])
+
+
+def _points_to_segments(P, s0, s1) -> float:
+    """min over points P [n,2] and segments s0[j] -> s1[j] of the point-to-segment distance (all pairs at once)."""
+    ab = (s1 - s0)[None]
+    ap = P[:, None] - s0[None]
+    den = (ab * ab).sum(-1)
+    t = np.where(den == 0, 0.0, np.clip((ap * ab).sum(-1) / np.where(den == 0, 1.0, den), 0.0, 1.0))
+    off = P[:, None] - (s0[None] + t[..., None] * ab)
+    return float(np.sqrt((off * off).sum(-1)).min())
+
+
 def polygon_distance(p1: np.ndarray, p2: np.ndarray) -> float:
-    """shapely Polygon.distance for two simple quads."""
+    """shapely Polygon.distance for two simple polygons: 0 when any edges properly cross or one contains the other, else the
+    smallest vertex-to-edge distance.  All edge pairs are evaluated in a few array operations (the text-direction graph calls this
+    for every nearby pair of lines)."""
     p1, p2 = np.asarray(p1, np.float64), np.asarray(p2, np.float64)
-    for i in range(len(p1)):
-        for j in range(len(p2)):
-            if _segments_cross(p1[i], p1[(i + 1) % len(p1)], p2[j], p2[(j + 1) % len(p2)]):
-                return 0.0
+    a, b = p1, np.roll(p1, -1, axis=0)
+    c, d = p2, np.roll(p2, -1, axis=0)
+    A, B, C, D = a[:, None], b[:, None], c[None], d[None]
+    if ((_orient(A, B, C) * _orient(A, B, D) < 0) & (_orient(C, D, A) * _orient(C, D, B) < 0)).any():
+        return 0.0
     if _inside(p1, p2[0]) or _inside(p2, p1[0]):
         return 0.0
-    d = np.inf
-    for a, b in ((p1, p2), (p2, p1)):
-        for p in a:
-            for j in range(len(b)):
-                d = min(d, _seg_point_dist(p, b[j], b[(j + 1) % len(b)]))
-    return float(d)
+    return min(_points_to_segments(p1, c, d), _points_to_segments(p2, a, b))
 
 
 class Quadrilateral:
