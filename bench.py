@@ -244,6 +244,27 @@ def run_reference_cuda(args, rank, world, local_rank):
     }), flush=True)
 
 
+def csrc_hash():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "manga-image-translator_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def latest_traffic_summary():
+    """Newest profiles/r*_ncu_traffic*.json written by tools/ncu_traffic.py (None when absent)."""
+    import glob
+    c = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic*.json")))
+    if not c:
+        return None, None
+    with open(c[-1]) as f:
+        return json.load(f), os.path.basename(c[-1])
+
+
 def roofline_from_profile(prof, peaks, pages_timed):
     """`roofline` object of the JSON line from the per-class profile {class: {launches, ms, flops, bytes}} that the library
     recorded with CUDA events around every launch of the timed region (`pages_timed` pages on this rank)."""
@@ -260,13 +281,14 @@ def roofline_from_profile(prof, peaks, pages_timed):
     # DRAM traffic of the dominant class from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum summed over the
     # class's kernels of one page, cold caches), per launch like `achieved`; null if that summary is not in the tree
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_v13.json")
-    if tensor_bound and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
+    tj, tname = latest_traffic_summary()
+    if tensor_bound and tj:
         per_page = top["launches"] / max(1, pages_timed)
         traffic = tj["conv_class_dram_bytes_per_page"] / max(1.0, per_page)
-        traffic_src = "profiles/r01_ncu_traffic_v13.json (ncu, one page, cold cache; includes the split pass of each conv)"
+        cur = csrc_hash()
+        traffic_src = (f"profiles/{tname} (tools/ncu_traffic.py over an ncu launch list of one page, cold cache, every kernel of the conv ops); "
+                       f"measured on csrc {tj.get('csrc_sha', '?')} at {tj.get('git_head', '?')}, "
+                       + ("same CUDA sources as this run" if tj.get("csrc_sha") == cur else f"this run's sources are {cur} (re-profile)"))
     return {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
@@ -311,7 +333,7 @@ def ffc_block_from_launches(launch_list, prof, pages_timed, peaks, H=None, W=Non
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from mit_b200 import synth
+    from mit_b200 import exchange, synth
     from mit_b200.pipeline import HotPath, ResultExchange, shard_indices
     torch.set_grad_enabled(False)
     os.environ.setdefault("MITB_PROFILE_LAUNCHES", "1")    # per-launch conv list for the LaMa FFC figure
@@ -355,6 +377,11 @@ def run_ours(args, rank, world, local_rank):
     def resident_step():
         for i, sp in enumerate(staged):
             db, dmask, ocr, out = hp.run_resident(sp)
+            if xchg is not None:                             # N > 1: the page goes into this rank's result record, device to device
+                o, nb = xchg.lay.o["page"]
+                xchg.buf[i, o:o + nb].copy_(out.reshape(-1))
+        if xchg is not None:
+            exchange.gather_records(xchg.buf, world)         # the one collective of the path: all ranks' records over NCCL / NVLink
         return out
 
     # ---------------- device-resident throughput (`value`)
@@ -379,6 +406,13 @@ def run_ours(args, rank, world, local_rank):
     launch_list = prof.pop("_launches", [])               # per-launch conv list (MITB_PROFILE_LAUNCHES), not a kernel class
     eng.lib.mitb_profile_enable(eng._h, 0)
     value = args.steps * n_pages * world / (ms_total / 1e3)
+    # the same region once more WITHOUT the per-launch event pairs of the profiler (they cost ~2 us per launch): informational
+    barrier()
+    e0.record()
+    resident_step()
+    e1.record()
+    barrier()
+    value_unprofiled = n_pages * world / (max_over_ranks(e0.elapsed_time(e1)) / 1e3)
 
     # ---------------- end-to-end through the plugin API with host buffers (`e2e`)
     def e2e_step():
@@ -450,6 +484,8 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{n_pages} pages 2048x1536 per GPU, dbnet_convnext + 48px_ctc ({LINES} lines/page, V={VOCAB}) + lama_mpe, "
                                    f"round-robin sharded over {world} GPU(s)", "pages_per_step": n_pages * world,
+                       "value_region": "resident pages, per-launch CUDA-event profiler ON (feeds `roofline`)" + (", incl. the NCCL all-gather of the result records" if world > 1 else ""),
+                       "value_without_profiler": value_unprofiled, "workers": args.workers,
                        "l2": f"inputs larger than L2 ({staged_bytes / 1e9:.1f} GB of staged pages per step)",
                        "weights": "seeded random (no checkpoints offline)"},
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

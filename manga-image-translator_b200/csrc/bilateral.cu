@@ -4,7 +4,7 @@
 // Semantics follow OpenCV's 8-bit 3-channel path (third-party, restated and checked against the installed cv2 4.13 in
 // tests): radius 8, BORDER_REFLECT_101, neighbours = offsets with sqrt(i^2+j^2) <= 8 in row-major order, spatial weight
 // float(exp(-0.5 r^2/sigma_s^2)), colour weight LUT float(exp(-0.5 k^2/sigma_c^2)) indexed by |db|+|dg|+|dr|,
-// w = sw*cw, sums accumulated with fused multiply-add in neighbour order, result = cvRound(sum / wsum).
+// w = sw*cw, sums accumulated with fused multiply-add in neighbour order, result = cvRound(sum * (1/wsum)).
 #include <math.h>
 #include "mitb_internal.h"
 
@@ -67,12 +67,15 @@ __global__ void __launch_bounds__(BTX * BTY) bilateral17_kernel(const uint8_t* i
     s0 = __fmaf_rn((float)v.x, w, s0); s1 = __fmaf_rn((float)v.y, w, s1); s2 = __fmaf_rn((float)v.z, w, s2);
     ws = __fadd_rn(ws, w);
   }
-  // cv2 divides each channel sum by wsum (IEEE division), it does not multiply by a reciprocal: with 1/wsum a handful of bytes
-  // per million land on the other side of a .5 boundary (measured against cv2 4.13: 66 of 9.4 M on a 2048x1536 page, 0 with division)
+  // OpenCV's own implementation (bilateral_filter.simd.hpp) multiplies by the reciprocal: w = 1 / wsum; b = cvRound(sum_b * w).
+  // This is bit-exact against cv2 with IPP disabled on every machine.  The stock pip wheel routes 8-bit bilateralFilter through
+  // Intel IPP, a closed-source kernel whose rounding differs from OpenCV's own in a few bytes per million AND between CPUs
+  // (measured: per-channel division on one host, something else again on the B200 box), so it cannot serve as a definition.
+  const float inv = __fdiv_rn(1.f, ws);
   uint8_t* o = out + ((size_t)y * W + x) * 3;
-  o[0] = (uint8_t)__float2int_rn(__fdiv_rn(s0, ws));
-  o[1] = (uint8_t)__float2int_rn(__fdiv_rn(s1, ws));
-  o[2] = (uint8_t)__float2int_rn(__fdiv_rn(s2, ws));
+  o[0] = (uint8_t)__float2int_rn(__fmul_rn(s0, inv));
+  o[1] = (uint8_t)__float2int_rn(__fmul_rn(s1, inv));
+  o[2] = (uint8_t)__float2int_rn(__fmul_rn(s2, inv));
 }
 
 void launch_bilateral17(const uint8_t* img, int h, int w, uint8_t* out, cudaStream_t st) {

@@ -192,7 +192,18 @@ def test_bilateral17_matches_cv2(eng):
     big = cv2.GaussianBlur(rng.integers(0, 256, (600, 811, 3), dtype=np.uint8), (0, 0), 5)
     from mit_b200 import synth
     page = synth.make_page(0)[0]                       # the 2048x1536 bench page (grey text page: all three channels equal)
-    for im in (img, smooth, big, page):
-        ref = cv2.bilateralFilter(im, 17, 80, 80)
-        out = eng.bilateral17(im).cpu().numpy()
-        assert np.array_equal(out, ref), int((out != ref).sum())          # uint8 work: bit-exact
+    use_ipp = cv2.ipp.useIPP()
+    try:
+        for im in (img, smooth, big, page):
+            out = eng.bilateral17(im).cpu().numpy()
+            # bit-exact against OpenCV's own implementation (the definition: open source, machine independent) ...
+            cv2.ipp.setUseIPP(False)
+            ref = cv2.bilateralFilter(im, 17, 80, 80)
+            assert np.array_equal(out, ref), int((out != ref).sum())
+            # ... and within 1 LSB on a few bytes per million of whatever closed-source IPP kernel this host's wheel dispatches to
+            cv2.ipp.setUseIPP(use_ipp)
+            d = np.abs(out.astype(int) - cv2.bilateralFilter(im, 17, 80, 80).astype(int))
+            print(f"bilateral {im.shape}: bytes differing from the IPP-dispatched cv2 default: {int((d != 0).sum())} of {d.size}")
+            assert d.max() <= 1 and (d != 0).mean() < 2e-5
+    finally:
+        cv2.ipp.setUseIPP(use_ipp)
