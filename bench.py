@@ -506,7 +506,7 @@ def main():
     ap.add_argument("--pages", type=int, default=PAGES_PER_GPU, help="pages per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-bar", action="store_true")
-    ap.add_argument("--workers", type=int, default=4, help="host threads of the page pipeline in the e2e leg")
+    ap.add_argument("--workers", type=int, default=8, help="host threads of the page pipeline in the e2e leg")
     ap.add_argument("--fast-e2e", action="store_true", help="one warm-up step for the e2e leg (development only)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

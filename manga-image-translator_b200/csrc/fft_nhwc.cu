@@ -37,9 +37,13 @@ struct FftNDev { int n, nst, nbt; int radix[kMaxSt]; const float2* tw; const uin
 
 #include "tc_common.cuh"
 
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex arithmetic on the packed fp32x2 pipe of sm_100 (add.f32x2 / fma.rn.f32x2): one instruction per complex add / subtract,
+// two per complex multiply - the butterflies are instruction-issue bound (ncu), so halving their FP instruction count pays
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+}
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 // multiply by -i (forward) or +i (inverse)
 __device__ __forceinline__ float2 rot90(float2 a, bool inv) { return inv ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
 
