@@ -33,7 +33,8 @@ namespace mitb {
 namespace {
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TM_EWARPS = 8;
+constexpr int TM_EWARPS = 12;               // 3 epilogue warps per scheduler: short-K layers are bound by epilogue LATENCY (2 warps left the schedulers ~70 % idle)
+constexpr int TM_EPARTS = TM_EWARPS / 4;     // column parts per TMEM lane quarter
 constexpr int TM_MMAWARP = TM_EWARPS, TM_TMAWARP = TM_EWARPS + 1;
 constexpr int TM_THREADS = (TM_EWARPS + 2) * 32;
 
@@ -245,10 +246,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
 
   if (warp < TM_EWARPS) {
     // =========================== epilogue: warp w drains TMEM lane quarter (w & 3), column half (w >> 2) ===========================
-    const int q = warp & 3, ehalf = warp >> 2;
+    const int q = warp & 3, epart = warp >> 2;       // TMEM lane quarter (must equal warp % 4), column part
     const int HoWo = p.Ho * p.Wo;
     const int nchunks = BN / 16, h0 = (nchunks + 1) / 2;
-    const int cb_lo = (ehalf == 0 ? 0 : h0) * 16, cb_hi = (ehalf == 0 ? h0 : nchunks) * 16;
+    // the row-stat layout has two column halves per N tile (shared with conv_tc.cu): parts 0 / 1 take them, part 2 idles there
+    const int ehalf = epart;
+    const int cb_lo = p.stat_max ? (epart == 0 ? 0 : epart == 1 ? h0 : nchunks) * 16 : (nchunks * epart / TM_EPARTS) * 16;
+    const int cb_hi = p.stat_max ? (epart == 0 ? h0 : nchunks) * 16 : (nchunks * (epart + 1) / TM_EPARTS) * 16;
     // row r of the tile -> output pixel (linear index into the Ho x Wo grid of image nimg), -1 when outside
     auto row_pixel = [&](int r, int nimg_t, int oy0, int ox0, int& nimg, int& oy, int& ox) -> bool {
       if (p.lin) {
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             }
           }
         }
-        if (row_ok) {
+        if (row_ok && epart < 2) {
           const size_t m = ((size_t)nimg * p.Ho + oy) * p.Wo + ox;
           const size_t o = m * p.stat_ld + (n0 / BN) * 2 + ehalf;
           p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
@@ -313,8 +317,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             rmask |= 1u << j;
           }
         }
-        // The residual / branch-sum operands of chunk cb+16 are fetched while chunk cb is transposed and stored: the loads
-        // would otherwise sit on the critical path of every 16-column step (short-K layers are epilogue bound).
+        // The residual / branch-sum operands of a chunk are requested right after its TMEM load is issued, so both latencies
+        // overlap (and the other two warps of the scheduler run meanwhile).
         float4 pa0[4], pa1[4];
         auto fetch_adds = [&](int cb, float4 (&A0)[4], float4 (&A1)[4]) {
           const int cq = n0 + cb + 4 * sub;
@@ -335,14 +339,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             }
           }
         };
-        if (p.add0 || p.add1) fetch_adds(cb_lo, pa0, pa1);
 #pragma unroll 1
         for (int cb = cb_lo; cb < cb_hi; cb += 16) {
           uint32_t raw[16];
           tmem_ld16(taddr_row + (uint32_t)cb, raw);
-          float4 na0[4], na1[4];
-          const bool more = cb + 16 < cb_hi;
-          if ((p.add0 || p.add1) && more) fetch_adds(cb + 16, na0, na1);
+          if (p.add0 || p.add1) fetch_adds(cb, pa0, pa1);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -398,10 +399,6 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             }
           }
           __syncwarp();
-          if (more && (p.add0 || p.add1)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { pa0[j] = na0[j]; pa1[j] = na1[j]; }
-          }
         }
       } else {
         // ---- planar (NCHW) or unaligned output: lane = pixel, so each channel's stores are contiguous across lanes
