@@ -113,8 +113,9 @@ class GatheredPage:
     inpainted: np.ndarray
 
 
-def unpack_page(lay: Layout, record: np.ndarray) -> GatheredPage:
-    """Inverse of pack_page on a host uint8[record_bytes] array."""
+def unpack_page(lay: Layout, record: np.ndarray, copy: bool = True) -> GatheredPage:
+    """Inverse of pack_page on a host uint8[record_bytes] array.  copy=False returns raw_mask / inpainted as views of `record`
+    (valid until the buffer is overwritten by the next exchange) instead of 12.6 MB copies per page."""
     def view(name, dtype, shape):
         o, n = lay.o[name]
         return record[o:o + n].view(dtype).reshape(shape)
@@ -133,7 +134,8 @@ def unpack_page(lay: Layout, record: np.ndarray) -> GatheredPage:
         q = Quadrilateral(lp[i].astype(np.int64), bytes(tx[i, :int(ln[i])]).decode("utf-8"), float(pr[i]))
         q.fg_r, q.fg_g, q.fg_b, q.bg_r, q.bg_g, q.bg_b = (int(v) for v in col[i])
         lines.append(q)
-    return GatheredPage(textlines, lines, view("mask", np.uint8, (lay.H, lay.W)).copy(), view("page", np.uint8, (lay.H, lay.W, 3)).copy())
+    mask, page = view("mask", np.uint8, (lay.H, lay.W)), view("page", np.uint8, (lay.H, lay.W, 3))
+    return GatheredPage(textlines, lines, mask.copy() if copy else mask, page.copy() if copy else page)
 
 
 def gather_records(local: torch.Tensor, world: int) -> torch.Tensor:
@@ -151,9 +153,11 @@ def gather_records(local: torch.Tensor, world: int) -> torch.Tensor:
     return out
 
 
-def unpack_gathered(lay: Layout, gathered: torch.Tensor, n_pages_total: int, pinned: Optional[torch.Tensor] = None) -> List[GatheredPage]:
+def unpack_gathered(lay: Layout, gathered: torch.Tensor, n_pages_total: int, pinned: Optional[torch.Tensor] = None,
+                    copy: bool = True) -> List[GatheredPage]:
     """Rank 0: device [world, pages_per_rank, record_bytes] -> pages in their original order (page i was processed by rank
-    i % world as its (i // world)-th page).  One D2H copy (into `pinned` when given)."""
+    i % world as its (i // world)-th page).  One D2H copy (into `pinned` when given); copy=False leaves the page-sized arrays as
+    views of that host buffer."""
     world = gathered.shape[0]
     if gathered.is_cuda:
         host = pinned if pinned is not None else torch.empty(gathered.shape, dtype=torch.uint8, pin_memory=True)
@@ -162,4 +166,4 @@ def unpack_gathered(lay: Layout, gathered: torch.Tensor, n_pages_total: int, pin
     else:
         host = gathered
     arr = host.numpy()
-    return [unpack_page(lay, arr[i % world, i // world]) for i in range(n_pages_total)]
+    return [unpack_page(lay, arr[i % world, i // world], copy) for i in range(n_pages_total)]

@@ -138,14 +138,15 @@ class ResultExchange:
         for i, r in enumerate(results):
             exchange.pack_page(self.lay, self.buf[i], r.textlines, r.ocr_lines, r.raw_mask, r.inpainted)
 
-    def exchange(self, world: int, rank: int, n_pages_total: int):
-        """Collective.  Returns the pages in original order on rank 0, None elsewhere."""
+    def exchange(self, world: int, rank: int, n_pages_total: int, copy: bool = False):
+        """Collective.  Returns the pages in original order on rank 0, None elsewhere.  With copy=False (default) the masks and pages
+        are views of this object's pinned host buffer, valid until the next exchange()."""
         g = exchange.gather_records(self.buf, world)
         if rank != 0:
             return None
         if g.is_cuda and (self._pinned is None or self._pinned.shape != g.shape):
             self._pinned = torch.empty(g.shape, dtype=torch.uint8, pin_memory=True)
-        return exchange.unpack_gathered(self.lay, g, n_pages_total, self._pinned)
+        return exchange.unpack_gathered(self.lay, g, n_pages_total, self._pinned, copy)
 
     @property
     def gathered_bytes(self) -> int:
