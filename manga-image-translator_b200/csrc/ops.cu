@@ -186,108 +186,6 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* in, int in
   }
 }
 
-// Cluster variant: one CTA per 128-channel chunk of an 8 x 8 pixel tile, the C/128 CTAs of a tile form a thread-block cluster and
-// exchange their LayerNorm partial sums through distributed shared memory.  Why: with all C channels in one CTA the halo tile it
-// walks is (py+6) x 14 pixels x 4C bytes = 229 KB at C = 512 - more than L1 - so every one of the 98 loads per thread went to L2
-// (12x read amplification, 0.9 TB/s).  A 128-channel chunk of a 14 x 14 halo is 100 KB: it stays in L1 and L2 sees each input ~3x.
-constexpr int DWC_PY = 8, DWC_CH = 128;
-__global__ void __launch_bounds__(32 * DWC_PY) dwconv7_ln_cluster_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs,
-                                                                         int out_coff, const float* wdw, const float* bdw, const float* lnw,
-                                                                         const float* lnb, float eps, int H, int W, int C, int ncl,
-                                                                         uint16_t* o_hi, uint16_t* o_mid) {
-  __shared__ float red[2][DWC_PY][DW_TX];
-  const unsigned rank = blockIdx.x % ncl;                 // cluster rank = channel chunk (cluster dims (ncl,1,1) tile blockIdx.x)
-  const int c = rank * DWC_CH + threadIdx.x * 4;
-  const int xt = (blockIdx.x / ncl) * DW_TX;
-  const int y = blockIdx.y * DWC_PY + threadIdx.y;
-  const int n = blockIdx.z;
-  const bool row_ok = y < H;
-  float4 acc[DW_TX];
-  const float4 bias = *reinterpret_cast<const float4*>(bdw + c);
-#pragma unroll
-  for (int i = 0; i < DW_TX; ++i) acc[i] = bias;
-  if (row_ok) {
-    for (int dy = 0; dy < 7; ++dy) {
-      const int iy = y + dy - 3;
-      if (iy < 0 || iy >= H) continue;
-      float4 wv[7];
-#pragma unroll
-      for (int dx = 0; dx < 7; ++dx) wv[dx] = __ldg(reinterpret_cast<const float4*>(wdw + (size_t)(dy * 7 + dx) * C + c));
-      const float* rowp = in + ((size_t)(n * H + iy) * W) * in_cs + in_coff + c;
-#pragma unroll
-      for (int j = 0; j < DW_TX + 6; ++j) {
-        const int ix = xt + j - 3;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(rowp + (size_t)ix * in_cs));
-#pragma unroll
-        for (int dx = 0; dx < 7; ++dx) {
-          const int i = j - dx;
-          if (i >= 0 && i < DW_TX) {
-            acc[i].x = fmaf(v.x, wv[dx].x, acc[i].x); acc[i].y = fmaf(v.y, wv[dx].y, acc[i].y);
-            acc[i].z = fmaf(v.z, wv[dx].z, acc[i].z); acc[i].w = fmaf(v.w, wv[dx].w, acc[i].w);
-          }
-        }
-      }
-    }
-  }
-  // ---- LayerNorm over all C channels: warp = one output row of this chunk; chunks combine through DSMEM in rank order
-  const int lane = threadIdx.x;
-  float mean[DW_TX], rstd[DW_TX];
-  for (int pass = 0; pass < 2; ++pass) {
-    float mine = 0.f;                                    // lane i < 8 ends up holding pixel i's total
-#pragma unroll
-    for (int i = 0; i < DW_TX; ++i) {
-      float part;
-      if (pass == 0) part = acc[i].x + acc[i].y + acc[i].z + acc[i].w;
-      else {
-        const float a = acc[i].x - mean[i], b = acc[i].y - mean[i], cc = acc[i].z - mean[i], d = acc[i].w - mean[i];
-        part = a * a + b * b + cc * cc + d * d;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == i) mine = part;
-    }
-    if (lane < DW_TX) red[pass][threadIdx.y][lane] = mine;
-    if (ncl > 1) {
-      asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-      float tot = 0.f;
-      if (lane < DW_TX) {
-        const uint32_t local = (uint32_t)__cvta_generic_to_shared(&red[pass][threadIdx.y][lane]);
-        for (unsigned r = 0; r < (unsigned)ncl; ++r) {
-          uint32_t remote; float v;
-          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
-          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-          tot += v;
-        }
-      }
-      mine = tot;
-    } else __syncwarp();
-#pragma unroll
-    for (int i = 0; i < DW_TX; ++i) {
-      const float t = __shfl_sync(0xffffffffu, mine, i);
-      if (pass == 0) mean[i] = t / C; else rstd[i] = rsqrtf(t / C + eps);
-    }
-  }
-  if (ncl > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers may still read red[]
-  if (!row_ok) return;
-  const float4 g = *reinterpret_cast<const float4*>(lnw + c), be = *reinterpret_cast<const float4*>(lnb + c);
-  float* orow = out + ((size_t)(n * H + y) * W) * out_cs + out_coff + c;
-#pragma unroll
-  for (int i = 0; i < DW_TX; ++i) {
-    const int x = xt + i;
-    if (x < W) {
-      float4 r;
-      r.x = (acc[i].x - mean[i]) * rstd[i] * g.x + be.x; r.y = (acc[i].y - mean[i]) * rstd[i] * g.y + be.y;
-      r.z = (acc[i].z - mean[i]) * rstd[i] * g.z + be.z; r.w = (acc[i].w - mean[i]) * rstd[i] * g.w + be.w;
-      if (o_hi) {
-        uint2 hh, mm; split4_bf16(r, hh, mm);
-        const size_t o = ((size_t)(n * H + y) * W + x) * C + c;
-        *reinterpret_cast<uint2*>(o_hi + o) = hh; *reinterpret_cast<uint2*>(o_mid + o) = mm;
-      } else *reinterpret_cast<float4*>(orow + (size_t)x * out_cs) = r;
-    }
-  }
-}
-
 void launch_dwconv7_ln(const View& in, const View& out, const float* wdw, const float* bdw, const float* lnw,
                        const float* lnb, float eps, cudaStream_t st, const SplitView* osv) {
   const int C = in.C;
@@ -299,21 +197,6 @@ void launch_dwconv7_ln(const View& in, const View& out, const float* wdw, const 
   MITB_CHECK(C % 128 == 0 && C <= 1024, "dwconv7_ln: C=%d must be a multiple of 128 (<=1024)", C);
   MITB_CHECK(in.cs % 4 == 0 && in.coff % 4 == 0 && out.cs % 4 == 0 && out.coff % 4 == 0, "dwconv7_ln alignment");
   ProfScope ps("dwconv7_ln", (98.0 + 8.0) * in.pixels() * C, 8.0 * in.pixels() * C + 4.0 * 51 * C, st);
-  static int use_cluster = -1;
-  if (use_cluster < 0) { const char* e = getenv("MITB_DW_NO_CLUSTER"); use_cluster = (e && atoi(e)) ? 0 : 1; }
-  if (use_cluster && C / DWC_CH <= 8) {
-    const int ncl = C / DWC_CH;
-    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(((in.W + DW_TX - 1) / DW_TX) * ncl), (unsigned)((in.H + DWC_PY - 1) / DWC_PY), (unsigned)in.N);
-    cfg.blockDim = dim3(32, DWC_PY); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = (unsigned)ncl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, dwconv7_ln_cluster_kernel, (const float*)in.p, in.cs, in.coff, out.p, out.cs, out.coff, wdw, bdw, lnw, lnb, eps,
-                               in.H, in.W, C, ncl, ohi, omid));
-    LAUNCH_END();
-    return;
-  }
   const int tx = C / 4;
   int py = 256 / tx; if (py < 1) py = 1;
   dim3 block(tx, py), grid((in.W + DW_TX - 1) / DW_TX, (in.H + py - 1) / py, in.N);
