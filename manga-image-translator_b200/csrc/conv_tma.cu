@@ -6,15 +6,16 @@
 // still needs ~2600 cycles per K block against a tensor floor of 768 (profiles/r01_tc_skeleton_experiments.txt), and a 3x3
 // conv repeats the conversion of every input element 9 times (once per tap) per N tile.
 //
-// Here the operands arrive pre-converted (bf16 hi / mid NHWC tensors written by the producing kernel's epilogue, or by one
-// memory-bound split pass) and the GEMM main loop has no producer warps at all:
-//   TMA warp one elected lane: per tap GROUP (taps of one kernel column, 64 channels) ONE activation box {64 ch, bw, bh + kh - 1}
-//            of the hi and mid tensors (zero padding = TMA out-of-bounds fill) into an A-ring slot, and per tap the weight boxes
-//            {64 k, BN} into a B-ring slot - all in the UMMA K-major SWIZZLE_128B layout, completing on mbarriers (expect_tx);
-//   MMA warp one elected lane: 12 tcgen05.mma per tap (bf16x3: Ah*Bh + Ah*Bm + Am*Bh; tap j of a group reads the group's box
-//            j*bw rows further down), tcgen05.commit -> the slot's "empty" barrier;
-//   12 epilogue warps: TMEM -> registers -> (+add0)*scale+shift -> act -> *mul1 -> +add1 -> coalesced stores (fp32 and / or the
-//            consumer's bf16 hi/mid operands) through a shared-memory transpose; double-buffered accumulator.
+// Here the conversion happens ONCE per input element in a separate memory-bound pass (split_pad_kernel: fp32 view ->
+// dense bf16 hi / mid NHWC tensors, optional BN+ReLU prologue, reflect halo materialised, planar inputs transposed), and the
+// GEMM main loop has no producer warps at all:
+//   warp 9   one thread: per K block (= 64 channels of one tap) four TMA loads - the activation box {64 ch, bw, bh} of the
+//            hi and mid tensors at the tap-shifted pixel coordinates (zero padding = TMA out-of-bounds fill) and the
+//            weight boxes {64 k, BN} - all landing in the UMMA K-major SWIZZLE_128B layout, completing on the stage's
+//            "full" mbarrier (expect_tx);
+//   warp 8   one thread: 12 tcgen05.mma per K block (bf16x3: Ah*Bh + Ah*Bm + Am*Bh), tcgen05.commit -> "empty" barrier;
+//   warps 0-7 epilogue: TMEM -> registers -> (+add0)*scale+shift -> act -> *mul1 -> +add1 -> coalesced fp32 stores through a
+//            shared-memory transpose; double-buffered accumulator, so tile i drains while tile i+1 is multiplied.
 // Operand fusion (ConvOp::in_sv / out_sv / seg2): a producer's epilogue can store its result directly as the consumer's bf16
 // hi/mid operand tensor (SplitView, optionally with a reflect halo and the consumer's BN+ReLU prologue applied), so the split
 // pass disappears; and a second K segment with its own tensor maps lets two convolutions of different inputs accumulate into one
@@ -38,17 +39,11 @@ constexpr int TM_MMAWARP = TM_EWARPS, TM_TMAWARP = TM_EWARPS + 1;
 constexpr int TM_THREADS = (TM_EWARPS + 2) * 32;
 
 struct SegParams {                                             // one K segment = one input tensor
-  CUtensorMap ta_hi, ta_mid;                                  // activations: 4-D (C, Wp, Hp, N) bf16, box {64, bw, (bh + grp - 1), 1}
-  int cblks, c0;                                              // 64-channel blocks, channel offset of the slice
-  // Taps come in groups that share ONE activation box: the `grp` taps of a group differ only in dy, so tap j of the group is the
-  // same box read `joff * bw` rows further down (a multiple of 8 rows = 1024 bytes: the UMMA descriptor just starts later).
-  // A 3x3 stride-1 conv is 3 groups of 3: each activation byte is pulled from L2 (bh + 2) / (3 bh) times as often as tap by tap.
-  int ngrp, grp, a_box_bytes, kbase;                          // kbase: first K block of this segment in the weight matrix
-  int8_t gdy[kMaxTaps], gdx[kMaxTaps];                        // per group: box origin offset in (padded) input coordinates
-  uint8_t kidx[kMaxTaps], joff[kMaxTaps];                     // per (group, j): weight tap index, row-group offset inside the box
+  CUtensorMap ta_hi, ta_mid;                                  // activations: 4-D (C, Wp, Hp, N) bf16, box {64, bw, bh, 1}
+  int ntaps, cblks, c0; int8_t tdy[kMaxTaps], tdx[kMaxTaps];  // channel offset of the slice; tap offsets in (padded) input coordinates
 };
 struct TmaParams {
-  SegParams seg[2]; int nseg, nkb, SA, SB, a_slot_bytes;      // SA / SB: ring depths of activation-group and weight-tile slots
+  SegParams seg[2]; int nseg, nkb;
   CUtensorMap tb_hi, tb_mid;                                  // weights: 2-D (K, Npad) bf16, box {64, BN}
   int N, Ho, Wo, M, lin;                                      // lin: tile = 128 consecutive rows of the flattened [M][C] matrix
   int sy, sx;                                                 // conv stride (TMA element strides of the activation box)
@@ -65,6 +60,11 @@ struct TmaParams {
 };
 
 #include "tc_common.cuh"
+
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c, int x, int y, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n) : "memory");
+}
 
 // One K block of the bf16x3 product: for each of the four 16-wide k steps Ah*Bh, Ah*Bm, Am*Bh, then tcgen05.commit on the
 // stage's "empty" barrier - issued by one elected lane of a converged warp (operands stay in uniform registers).
@@ -103,6 +103,23 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
       "}\n" ::"r"(bar) : "memory");
 }
+// expect_tx + the four operand boxes of one K block, issued by one elected lane of a converged warp
+__device__ __forceinline__ void tma_kblock(uint32_t bar, uint32_t bytes, uint32_t a_hi, uint32_t a_mid, uint32_t b_hi, uint32_t b_mid,
+                                           const CUtensorMap* ta_hi, const CUtensorMap* ta_mid, const CUtensorMap* tb_hi,
+                                           const CUtensorMap* tb_mid, int c, int x, int y, int n, int k, int n0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%6, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%7, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%8, {%14, %15}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%9, {%14, %15}], [%0];\n"
+      "}\n" ::"r"(bar), "r"(bytes), "r"(a_hi), "r"(a_mid), "r"(b_hi), "r"(b_mid), "l"(ta_hi), "l"(ta_mid), "l"(tb_hi), "l"(tb_mid),
+      "r"(c), "r"(x), "r"(y), "r"(n), "r"(k), "r"(n0) : "memory");
+}
+
 // ---- CTA-pair (cta_group::2) variants: one 256 x BN tile per pair of SMs, each CTA stages its own 128 rows of A and HALF of B
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
@@ -156,50 +173,21 @@ __device__ __forceinline__ void umma_commit_elect_pair(uint32_t bar) {
       "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], msk;\n"
       "}\n" ::"r"(bar) : "memory");
 }
-// activation group (hi, mid boxes) -> A slot; weight tile (hi, mid) -> B slot.  One elected lane of a converged warp issues.
-template <int CG>
-__device__ __forceinline__ void tma_a_group(uint32_t bar, uint32_t bytes, uint32_t a_hi, uint32_t a_mid, const CUtensorMap* ta_hi,
-                                            const CUtensorMap* ta_mid, int c, int x, int y, int n) {
-  if (CG == 2)
-    asm volatile(
-        "{\n"
-        ".reg .pred pe;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "@pe mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;\n"
-        "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4, {%6, %7, %8, %9}], [%0];\n"
-        "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%5, {%6, %7, %8, %9}], [%0];\n"
-        "}\n" ::"r"(bar), "r"(bytes), "r"(a_hi), "r"(a_mid), "l"(ta_hi), "l"(ta_mid), "r"(c), "r"(x), "r"(y), "r"(n) : "memory");
-  else
-    asm volatile(
-        "{\n"
-        ".reg .pred pe;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-        "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4, {%6, %7, %8, %9}], [%0];\n"
-        "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%5, {%6, %7, %8, %9}], [%0];\n"
-        "}\n" ::"r"(bar), "r"(bytes), "r"(a_hi), "r"(a_mid), "l"(ta_hi), "l"(ta_mid), "r"(c), "r"(x), "r"(y), "r"(n) : "memory");
-}
-template <int CG>
-__device__ __forceinline__ void tma_b_tile(uint32_t bar, uint32_t bytes, uint32_t b_hi, uint32_t b_mid, const CUtensorMap* tb_hi,
-                                           const CUtensorMap* tb_mid, int k, int n0) {
-  if (CG == 2)
-    asm volatile(
-        "{\n"
-        ".reg .pred pe;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "@pe mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;\n"
-        "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4, {%6, %7}], [%0];\n"
-        "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%5, {%6, %7}], [%0];\n"
-        "}\n" ::"r"(bar), "r"(bytes), "r"(b_hi), "r"(b_mid), "l"(tb_hi), "l"(tb_mid), "r"(k), "r"(n0) : "memory");
-  else
-    asm volatile(
-        "{\n"
-        ".reg .pred pe;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4, {%6, %7}], [%0];\n"
-        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%5, {%6, %7}], [%0];\n"
-        "}\n" ::"r"(bar), "r"(bytes), "r"(b_hi), "r"(b_mid), "l"(tb_hi), "l"(tb_mid), "r"(k), "r"(n0) : "memory");
+// expect_tx on the LEADER's full barrier (cluster address) + this CTA's four operand boxes completing on it
+__device__ __forceinline__ void tma_kblock_pair(uint32_t lead_bar, uint32_t bytes, uint32_t a_hi, uint32_t a_mid, uint32_t b_hi, uint32_t b_mid,
+                                                const CUtensorMap* ta_hi, const CUtensorMap* ta_mid, const CUtensorMap* tb_hi,
+                                                const CUtensorMap* tb_mid, int c, int x, int y, int n, int k, int n0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;\n"
+      "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%6, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%7, {%10, %11, %12, %13}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%8, {%14, %15}], [%0];\n"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%9, {%14, %15}], [%0];\n"
+      "}\n" ::"r"(lead_bar), "r"(bytes), "r"(a_hi), "r"(a_mid), "r"(b_hi), "r"(b_mid), "l"(ta_hi), "l"(ta_mid), "l"(tb_hi), "l"(tb_mid),
+      "r"(c), "r"(x), "r"(y), "r"(n), "r"(k), "r"(n0) : "memory");
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: clusters of two CTAs (one SM pair) share a 256 x BN tile through tcgen05 cta_group::2:
@@ -211,24 +199,22 @@ template <int ACT, int CG>
 __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int BN = p.BN, SA = p.SA, SB = p.SB;
-  const uint32_t b_bytes = (uint32_t)(BN / CG) * 128;                                // CG = 2: half of the weight tile per CTA
-  const uint32_t a_slot = (uint32_t)p.a_slot_bytes, a_half = a_slot >> 1, b_slot = 2 * b_bytes;
+  const int BN = p.BN, S = p.stages;
+  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)(BN / CG) * 128;         // CG = 2: half of the weight tile per CTA
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
   const uint32_t crank = CG == 2 ? cluster_rank() : 0u;
-  // shared memory: SA activation-group slots (hi | mid), SB weight-tile slots (hi | mid), barriers, TMEM slot, epilogue staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)SA * a_slot + (size_t)SB * b_slot);   // afull[SA] aempty[SA] bfull[SB] bempty[SB] tfull[2] tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
-  float* estage = reinterpret_cast<float*>(bars + 2 * SA + 2 * SB + 6);  // [TM_EWARPS][32 rows][20 floats] epilogue transpose buffer
-  const uint32_t smem_base = smem_u32(smem), bsm_base = smem_base + (uint32_t)SA * a_slot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  float* estage = reinterpret_cast<float*>(bars + 2 * S + 6);          // [TM_EWARPS][32 rows][20 floats] epilogue transpose buffer
+  const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
-  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
-  auto aempty_bar = [&](int s) { return bar_base + 8u * (SA + s); };
-  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * SA + s); };
-  auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = p.nkb;
   const int bw = 1 << p.bw_log2, bh = TC_BM >> p.bw_log2;
   const int mt = p.N * p.tiles_y * p.tiles_x, nt = p.npad / BN;
   const int total_tiles = ((mt + CG - 1) / CG) * nt;                 // CG = 2: pair tiles (two consecutive 128-row tiles)
@@ -237,8 +223,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
   const uint32_t acc_stride = (uint32_t)(p.tmem_cols >> 1);
 
   if (tid == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(afull_bar(s), CG); mbar_init(aempty_bar(s), 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), CG); mbar_init(bempty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), CG * TM_EWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -457,69 +442,54 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     // moved every operand of every tcgen05.mma through R2UR/ELECT sequences: ~350 dependent instructions per K block on this
     // single warp, i.e. ~1400 cycles against the 768-cycle tensor floor of a 128x128x64 bf16x3 block (ncu, r01).
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG * TC_BM) >> 4) << 24);
-    int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int lt = 0;
+    int s = 0; uint32_t ph = 0; int lt = 0;
     if (CG == 1 || crank == 0)
     for (int t = tile_first; t < total_tiles; t += tile_step, ++lt) {
       const int buf = lt & 1;
       mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_stride;
-      uint32_t acc = 0u;                                            // first K block of the tile overwrites the accumulator
-      for (int sg = 0; sg < p.nseg; ++sg) {
-        const SegParams& sp = p.seg[sg];
-        const int ngroups = sp.cblks * sp.ngrp;
-        int g = 0;
-        for (int i = 0; i < ngroups; ++i) {
-          mbar_wait(afull_bar(sa), pha);                            // the group's activation box (hi, mid) has landed
-          const uint32_t a_hi0 = smem_base + (uint32_t)sa * a_slot;
-          for (int j = 0; j < sp.grp; ++j) {
-            mbar_wait(bfull_bar(sb), phb);
-            tc_fence_after();
-            const uint32_t a_hi = a_hi0 + (uint32_t)sp.joff[g * sp.grp + j] * ((uint32_t)bw * 128u), a_mid = a_hi + a_half;
-            const uint32_t b_hi = bsm_base + (uint32_t)sb * b_slot, b_mid = b_hi + b_bytes;
-            if (CG == 2)
-              umma_kblock_x3_pair(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
-                                  acc, bempty_bar(sb));             // 12 pair MMAs + commit multicast -> frees the weight slot in both CTAs
-            else
-              umma_kblock_x3(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
-                             acc, bempty_bar(sb));                  // 12 MMAs + commit -> frees the weight slot when they retire
-            acc = 1u;
-            if (++sb == SB) { sb = 0; phb ^= 1u; }
-          }
-          if (CG == 2) umma_commit_elect_pair(aempty_bar(sa)); else umma_commit_elect(aempty_bar(sa));   // group done -> activation slot free
-          if (++sa == SA) { sa = 0; pha ^= 1u; }
-          if (++g == sp.ngrp) g = 0;
-        }
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+        const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+        if (CG == 2)
+          umma_kblock_x3_pair(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
+                              kb > 0 ? 1u : 0u, empty_bar(s));       // 12 pair MMAs + commit multicast -> frees the stage in both CTAs
+        else
+          umma_kblock_x3(tmem_d, make_desc_sw128(a_hi), make_desc_sw128(a_mid), make_desc_sw128(b_hi), make_desc_sw128(b_mid), idesc,
+                         kb > 0 ? 1u : 0u, empty_bar(s));            // 12 MMAs + commit -> frees the stage when they retire
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
       if (CG == 2) umma_commit_elect_pair(tfull_bar(buf)); else umma_commit_elect(tfull_bar(buf));      // accumulator complete -> epilogue(s)
     }
     __syncwarp();
   } else if (warp == TM_TMAWARP) {
     // =========================== operand loader: four TMA boxes per K block (whole warp loops, one elected lane issues) =====
-    int sa = 0, sb = 0; uint32_t pha = 1, phb = 1;
-    const uint32_t afull_lead0 = CG == 2 ? mapa_rank(afull_bar(0), 0) : afull_bar(0);
-    const uint32_t bfull_lead0 = CG == 2 ? mapa_rank(bfull_bar(0), 0) : bfull_bar(0);
-    const int nb0 = CG == 2 ? (int)crank * (BN / 2) : 0;
+    int s = 0; uint32_t ph = 1;
+    const uint32_t full_lead0 = CG == 2 ? mapa_rank(full_bar(0), 0) : full_bar(0);
     for (int t = tile_first; t < total_tiles; t += tile_step) {
       int nimg, oy0, ox0, n0;
       decode(t, nimg, oy0, ox0, n0);
+      int kb = 0;
       for (int sg = 0; sg < p.nseg; ++sg) {
         const SegParams& sp = p.seg[sg];
-        for (int cb = 0; cb < sp.cblks; ++cb) {
-          for (int g = 0; g < sp.ngrp; ++g) {
-            mbar_wait(aempty_bar(sa), pha);
-            const uint32_t a_hi = smem_base + (uint32_t)sa * a_slot;
-            tma_a_group<CG>(afull_lead0 + 8u * sa, (uint32_t)sp.a_box_bytes, a_hi, a_hi + a_half, &sp.ta_hi, &sp.ta_mid, sp.c0 + cb * TC_BK,
-                            ox0 * p.sx + sp.gdx[g], oy0 * p.sy + sp.gdy[g], nimg);
-            if (++sa == SA) { sa = 0; pha ^= 1u; }
-            for (int j = 0; j < sp.grp; ++j) {
-              mbar_wait(bempty_bar(sb), phb);
-              const uint32_t b_hi = bsm_base + (uint32_t)sb * b_slot;
-              tma_b_tile<CG>(bfull_lead0 + 8u * sb, 2 * b_bytes, b_hi, b_hi + b_bytes, &p.tb_hi, &p.tb_mid,
-                             (sp.kbase + (int)sp.kidx[g * sp.grp + j] * sp.cblks + cb) * TC_BK, n0 + nb0);
-              if (++sb == SB) { sb = 0; phb ^= 1u; }
-            }
-          }
+        int tap = 0, cb = 0;
+        const int nk = sp.ntaps * sp.cblks;
+        for (int i = 0; i < nk; ++i, ++kb) {
+          mbar_wait(empty_bar(s), ph);
+          const uint32_t a_hi = smem_base + (uint32_t)s * stage_bytes, a_mid = a_hi + a_bytes;
+          const uint32_t b_hi = a_mid + a_bytes, b_mid = b_hi + b_bytes;
+          const int x = ox0 * p.sx + sp.tdx[tap], y = oy0 * p.sy + sp.tdy[tap];
+          if (CG == 2)
+            tma_kblock_pair(full_lead0 + 8u * s, 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &sp.ta_hi, &sp.ta_mid, &p.tb_hi, &p.tb_mid,
+                            sp.c0 + cb * TC_BK, x, y, nimg, kb * TC_BK, n0 + (int)crank * (BN / 2));
+          else
+            tma_kblock(full_bar(s), 2 * a_bytes + 2 * b_bytes, a_hi, a_mid, b_hi, b_mid, &sp.ta_hi, &sp.ta_mid, &p.tb_hi, &p.tb_mid,
+                       sp.c0 + cb * TC_BK, x, y, nimg, kb * TC_BK, n0);
+          if (++cb == sp.cblks) { cb = 0; ++tap; }
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -767,35 +737,6 @@ bool conv_tma_supported(const ConvOp& op) {
   return true;
 }
 
-// Tap groups of one K segment (SegParams): taps that share dx and have consecutive dy read ONE activation box of bh + grp - 1 rows.
-// Needs stride 1, a full kh x kw tap grid and group_ok; otherwise every tap is its own group (grp = 1).
-static void build_groups(SegParams& sg, const int8_t* tdy, const int8_t* tdx, int ntaps, int pt, int pl, bool group_ok, int bw, int bh, int* grp_out) {
-  int kw = 1; while (kw < ntaps && tdy[kw] == tdy[0]) ++kw;
-  const int kh = ntaps / kw;
-  bool grid = group_ok && kh > 1 && kh * kw == ntaps && tdy[kw < ntaps ? kw : 0] != tdy[0];
-  const int step = grid ? (tdy[kw] > tdy[0] ? 1 : -1) : 0;
-  for (int t = 0; t < ntaps && grid; ++t) grid = tdy[t] == tdy[0] + step * (t / kw) && tdx[t] == tdx[t % kw];
-  if (grid) {
-    sg.ngrp = kw; sg.grp = kh;
-    const int dy_min = step > 0 ? tdy[0] : tdy[(kh - 1) * kw];
-    for (int g = 0; g < kw; ++g) {
-      sg.gdy[g] = (int8_t)(dy_min + pt); sg.gdx[g] = (int8_t)(tdx[g] + pl);
-      for (int j = 0; j < kh; ++j) { sg.kidx[g * kh + j] = (uint8_t)(j * kw + g); sg.joff[g * kh + j] = (uint8_t)(tdy[j * kw + g] - dy_min); }
-    }
-  } else {
-    sg.ngrp = ntaps; sg.grp = 1;
-    for (int t = 0; t < ntaps; ++t) { sg.gdy[t] = (int8_t)(tdy[t] + pt); sg.gdx[t] = (int8_t)(tdx[t] + pl); sg.kidx[t] = (uint8_t)t; sg.joff[t] = 0; }
-  }
-  sg.a_box_bytes = 2 * (bh + sg.grp - 1) * bw * 128;
-  *grp_out = sg.grp;
-}
-
-static int tap_group_env() {         // MITB_TAPGROUP=0: every tap loads its own activation box (round-1 behaviour)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MITB_TAPGROUP"); v = e ? atoi(e) : 1; }
-  return v;
-}
-
 static bool g_stem_map_failed = false;       // the driver refused the overlapping-stride map once: keep the gather kernel for stems
 
 bool conv_stem8_supported(const ConvOp& op) {
@@ -888,42 +829,26 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
   memset(&p, 0, sizeof(p));
   const bool two = op.seg2.sv.valid();
   p.nseg = two ? 2 : 1;
-  p.seg[0].cblks = cblks; p.seg[0].c0 = sv_coff; p.seg[0].kbase = 0;
+  p.seg[0].ntaps = stem ? op.w8_kh : op.ntaps; p.seg[0].cblks = cblks; p.seg[0].c0 = sv_coff;
+  if (stem) for (int t = 0; t < op.w8_kh; ++t) { p.seg[0].tdy[t] = (int8_t)(op.tdy[t * op.w8_kw] + sv.pt); p.seg[0].tdx[t] = (int8_t)(op.tdx[0] + sv.pl); }
+  else for (int t = 0; t < op.ntaps; ++t) { p.seg[0].tdy[t] = (int8_t)(op.tdy[t] + sv.pt); p.seg[0].tdx[t] = (int8_t)(op.tdx[t] + sv.pl); }
   p.N = N; p.Ho = op.Ho; p.Wo = op.Wo; p.M = N * op.Ho * op.Wo; p.sy = op.sy; p.sx = op.sx;
   const bool lin = !stem && !two && op.ntaps == 1 && op.Ho == H && op.Wo == W && op.sy == 1 && op.sx == 1 && op.tdy[0] == 0 && op.tdx[0] == 0 &&
                    sv.Hp == H && sv.Wp == W;
   p.lin = lin ? 1 : 0;                                              // 1x1: flattened [pixels][C] matrix
-  // ---- tap grouping: which segments can share activation boxes between taps of one column (see SegParams)
-  const bool group_ok = tap_group_env() != 0 && !stem && op.sy == 1 && op.sx == 1;
-  int kh0 = 1, kh1 = 1;                                            // group sizes if grouping is possible (kernel heights of the tap grids)
-  { SegParams tmp; memset(&tmp, 0, sizeof(tmp)); build_groups(tmp, op.tdy, op.tdx, stem ? 1 : op.ntaps, 0, 0, group_ok, 8, 1, &kh0); }
-  if (two) { SegParams tmp; memset(&tmp, 0, sizeof(tmp)); build_groups(tmp, op.seg2.tdy, op.seg2.tdx, op.seg2.ntaps, 0, 0, group_ok, 8, 1, &kh1); }
-  const int khm = kh0 > kh1 ? kh0 : kh1;
   int bw, bh;
   if (lin) { bw = 128; bh = 1; p.tiles_x = (p.M + 127) / 128; p.tiles_y = 1; p.N = 1; }
   else {
-    // tile shape: minimise (padded tiles) x (operand bytes per 64-channel block): taller tiles re-use more of a group's box
-    // ((bh + kh - 1) rows serve kh taps), wider ones waste less at ragged right edges; the box must fit its slot (<= 192 rows)
-    double best = -1; bw = 128;
+    long best = -1; bw = 128;
     for (int cand = 128; cand >= 8; cand >>= 1) {
       const int ch = 128 / cand;
-      const double tiles = (double)((op.Wo + cand - 1) / cand) * (double)((op.Ho + ch - 1) / ch);
-      const double a_rows = khm > 1 && (ch + khm - 1) * cand <= 192 ? (double)(ch + khm - 1) * cand / khm : 128.0;   // rows loaded per tap
-      const double cost = tiles * (a_rows * 256.0 + 128.0 * 256.0);       // activation + (a typical 128-wide) weight tile bytes per tap
+      const long cost = (long)((op.Wo + cand - 1) / cand) * cand * (long)((op.Ho + ch - 1) / ch) * ch;
       if (best < 0 || cost < best) { best = cost; bw = cand; }
     }
     bh = 128 / bw;
     p.tiles_x = (op.Wo + bw - 1) / bw; p.tiles_y = (op.Ho + bh - 1) / bh;
   }
   p.bw_log2 = 0; while ((1 << p.bw_log2) < bw) ++p.bw_log2;
-  const bool do_group = group_ok && !lin && (bh + khm - 1) * bw <= 192;      // slot budget: 192 rows x 128 B x (hi, mid) = 48 KB
-  int g0 = 1, g1 = 1;
-  if (stem) {
-    SegParams& sg = p.seg[0];
-    sg.ngrp = op.w8_kh; sg.grp = 1; sg.a_box_bytes = 2 * bh * bw * 128;
-    for (int t = 0; t < op.w8_kh; ++t) { sg.gdy[t] = (int8_t)(op.tdy[t * op.w8_kw] + sv.pt); sg.gdx[t] = (int8_t)(op.tdx[0] + sv.pl); sg.kidx[t] = (uint8_t)t; sg.joff[t] = 0; }
-  } else build_groups(p.seg[0], op.tdy, op.tdx, op.ntaps, sv.pt, sv.pl, do_group, bw, bh, &g0);
-  const int bh0 = bh + g0 - 1;                                               // box heights of the two segments' activation maps
   if (stem) {
     if (!make_stem_tmap(&p.seg[0].ta_hi, sv.hi, N, sv.Hp, sv.Wp, bw, bh) || !make_stem_tmap(&p.seg[0].ta_mid, sv.mid, N, sv.Hp, sv.Wp, bw, bh)) {
       g_stem_map_failed = true;                                        // fall back for good: conv_stem8_supported() is false from now on
@@ -931,7 +856,7 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
       return;
     }
   } else if (lin) { make_act_tmap(&p.seg[0].ta_hi, sv.hi, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); make_act_tmap(&p.seg[0].ta_mid, sv.mid, 1, 1, N * sv.Hp * sv.Wp, sv.C, bw, bh, 1, 1); }
-  else { make_act_tmap(&p.seg[0].ta_hi, sv.hi, N, sv.Hp, sv.Wp, sv.C, bw, bh0, op.sx, op.sy); make_act_tmap(&p.seg[0].ta_mid, sv.mid, N, sv.Hp, sv.Wp, sv.C, bw, bh0, op.sx, op.sy); }
+  else { make_act_tmap(&p.seg[0].ta_hi, sv.hi, N, sv.Hp, sv.Wp, sv.C, bw, bh, op.sx, op.sy); make_act_tmap(&p.seg[0].ta_mid, sv.mid, N, sv.Hp, sv.Wp, sv.C, bw, bh, op.sx, op.sy); }
   int kdim = (stem ? op.w8_kh : op.ntaps) * cblks * TC_BK;
   if (two) {
     const ConvOp::Seg2& s2 = op.seg2;
@@ -944,10 +869,10 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
       conv_halo(s2.tdy, s2.tdx, s2.ntaps, PAD_REFLECT, s2.sv.H, s2.sv.W, op.Ho, op.Wo, 1, 1, qt, qb, ql, qr);
       MITB_CHECK(qt == 0 && qb == 0 && ql == 0 && qr == 0, "tma conv: zero padding needs a halo-free seg2");
     }
-    p.seg[1].cblks = s2.C / TC_BK; p.seg[1].c0 = s2.coff; p.seg[1].kbase = kdim / TC_BK;
-    build_groups(p.seg[1], s2.tdy, s2.tdx, s2.ntaps, s2.sv.pt, s2.sv.pl, do_group, bw, bh, &g1);
-    make_act_tmap(&p.seg[1].ta_hi, s2.sv.hi, N, s2.sv.Hp, s2.sv.Wp, s2.sv.C, bw, bh + g1 - 1, 1, 1);
-    make_act_tmap(&p.seg[1].ta_mid, s2.sv.mid, N, s2.sv.Hp, s2.sv.Wp, s2.sv.C, bw, bh + g1 - 1, 1, 1);
+    p.seg[1].ntaps = s2.ntaps; p.seg[1].cblks = s2.C / TC_BK; p.seg[1].c0 = s2.coff;
+    for (int t = 0; t < s2.ntaps; ++t) { p.seg[1].tdy[t] = (int8_t)(s2.tdy[t] + s2.sv.pt); p.seg[1].tdx[t] = (int8_t)(s2.tdx[t] + s2.sv.pl); }
+    make_act_tmap(&p.seg[1].ta_hi, s2.sv.hi, N, s2.sv.Hp, s2.sv.Wp, s2.sv.C, bw, bh, 1, 1);
+    make_act_tmap(&p.seg[1].ta_mid, s2.sv.mid, N, s2.sv.Hp, s2.sv.Wp, s2.sv.C, bw, bh, 1, 1);
     kdim += s2.ntaps * s2.C;
     MITB_CHECK(op.tc_kpad == kdim, "tma conv: merged weight has K %d, segments need %d", op.tc_kpad, kdim);
   }
@@ -990,23 +915,12 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;
-  // ---- shared-memory rings: SA activation-group slots, SB weight-tile slots
-  const int gmax = g0 > g1 ? g0 : g1;
-  const size_t a_slot = 2 * (size_t)(bh + gmax - 1) * bw * 128, b_slot = 2 * (size_t)(p.BN / cg) * 128;
+  const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)(p.BN / cg) * 128;
   const size_t epi_bytes = (size_t)TM_EWARPS * 32 * 20 * sizeof(float);
-  const size_t budget = 227 * 1024 - 1024 - 512 - epi_bytes;
-  int SA, SB;
-  if (gmax == 1) {                                                           // one box per tap: equally deep rings (= the old stages)
-    int st_ = (int)(budget / (a_slot + b_slot)); if (st_ > 6) st_ = 6;
-    SA = SB = st_;
-  } else {
-    SA = 2;
-    SB = (int)((budget - SA * a_slot) / b_slot); if (SB > 6) SB = 6;
-    if (SB >= 5 && budget >= 3 * a_slot + (size_t)(SB - 1) * b_slot) { SA = 3; SB = (int)((budget - SA * a_slot) / b_slot); if (SB > 6) SB = 6; }
-  }
-  MITB_CHECK(SA >= 2 && SB >= 2, "tma conv: tile does not fit shared memory (SA %d SB %d)", SA, SB);
-  p.SA = SA; p.SB = SB; p.a_slot_bytes = (int)a_slot;
-  const size_t smem = SA * a_slot + SB * b_slot + (size_t)(2 * SA + 2 * SB + 6) * 8 + epi_bytes + 1024;
+  int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes); if (stages > 6) stages = 6;
+  MITB_CHECK(stages >= 2, "tma conv: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + (2 * stages + 6) * 8 + epi_bytes + 1024;
   const long total_tiles = ((mtiles + cg - 1) / cg) * (p.npad / p.BN);
   const long units = num_sms / cg;
   const int grid = (int)(total_tiles < units ? total_tiles : units) * cg;
