@@ -26,6 +26,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <cuda_bf16.h>
+#include <type_traits>
 #include "mitb_internal.h"
 
 namespace mitb {
@@ -57,6 +58,7 @@ struct TmaParams {
   // split output (ConvOp::out_sv): bf16 hi / mid at [((n*os_Hp + y + os_pt)*os_Wp + x + os_pl)*os_pitch + os_coff + c] (null: none)
   uint16_t* os_hi; uint16_t* os_mid; int os_pitch, os_coff, os_Hp, os_Wp, os_pt, os_pl;
   const float* os_scale; const float* os_shift; int os_relu;  // consumer prologue applied before splitting
+  int fast;                                                   // NHWC, 16-byte aligned rows / constants, Cout % 4 == 0: the packed epilogue
 };
 
 #include "tc_common.cuh"
@@ -298,6 +300,96 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
           const size_t m = ((size_t)nimg * p.Ho + oy) * p.Wo + ox;
           const size_t o = m * p.stat_ld + (n0 / BN) * 2 + ehalf;
           p.stat_max[o] = bm; p.stat_sum[o] = bs; p.stat_idx[o] = bi;
+        }
+      } else if (p.fast) {
+        // ---- the common case (NHWC output, every per-channel constant and row 16-byte aligned, Cout % 4 == 0), written for
+        // instruction count: short-K layers (ConvNeXt fc1, the spectral 1x1 convs, the decoders) are bound by the epilogue's issue
+        // slots, not by the tensor pipe.  Arithmetic on the packed fp32x2 pipe, per-channel constants as one 16-byte load each,
+        // no per-element bounds checks, and the TMEM load of the next chunk in flight while this one is processed.  The 16-column
+        // chunks of a tile rotate over the TM_EPARTS warps of a lane quarter from tile to tile, so that chunk counts that do
+        // not divide by TM_EPARTS (BN = 128: 3 + 3 + 2) balance over consecutive tiles (the accumulator is double buffered).
+        const uint32_t st_w = smem_u32(estage + (size_t)warp * 32 * 20) + (uint32_t)lane * 80u;              // this lane's row of the staging tile
+        const int sub = lane & 3, rsel = lane >> 2;              // this thread: columns 4*sub..+3 of rows rsel + 8j
+        const uint32_t st_r = smem_u32(estage + (size_t)warp * 32 * 20) + (uint32_t)rsel * 80u + (uint32_t)sub * 16u;
+        // element offsets of this thread's four rows in the output / split output / residual tensors (host checked: < 2^31 elements)
+        uint32_t eo[4], so[4], ao[4], rmask = 0;
+        const float* addp = p.add0 ? p.add0 + p.add0_coff : p.add1 ? p.add1 + p.add1_coff : nullptr;
+        const int add_cs = p.add0 ? p.add0_cs : p.add1_cs;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int nimg, oy, ox;
+          eo[j] = 0; so[j] = 0; ao[j] = 0;
+          if (row_pixel(q * 32 + rsel + 8 * j, nimg_t, oy0, ox0, nimg, oy, ox)) {
+            const uint32_t opix = (uint32_t)((nimg * p.oH + oy * p.oy_mul + p.oy_add) * p.oW + ox * p.ox_mul + p.ox_add);
+            eo[j] = opix * (uint32_t)p.out_cs + (uint32_t)p.out_coff;
+            ao[j] = opix * (uint32_t)add_cs;
+            so[j] = (uint32_t)((nimg * p.os_Hp + oy + p.os_pt) * p.os_Wp + ox + p.os_pl) * (uint32_t)p.os_pitch + (uint32_t)p.os_coff;
+            rmask |= 1u << j;
+          }
+        }
+        const bool extra = p.add0 || p.add1 || p.mul1;           // residual / layer-scale operands: only long-K layers have them
+        int nch = (p.Cout - n0 + 15) >> 4; if (nch > nchunks) nch = nchunks;      // chunks wholly past Cout are never touched
+        int c = (epart + TM_EPARTS - lt % TM_EPARTS) % TM_EPARTS;
+        uint32_t raw[16];
+        if (c < nch) tmem_ld16(taddr_row + (uint32_t)(c * 16), raw);
+#pragma unroll 1
+        for (; c < nch; c += TM_EPARTS) {
+          const int cq = n0 + c * 16 + 4 * sub;
+          const bool colok = cq < p.Cout;                       // Cout % 4 == 0: a thread's four columns are in or out together
+          float4 A[4];                                           // residual / branch-sum rows (at most one of add0 / add1 on this path)
+          if (addp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              A[j] = (colok && ((rmask >> j) & 1u)) ? *reinterpret_cast<const float4*>(addp + (ao[j] + (uint32_t)cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (colok) {
+            if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + cq));
+            if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + cq));
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts128(st_w + 16u * i, raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
+          __syncwarp();
+          if (c + TM_EPARTS < nch) tmem_ld16(taddr_row + (uint32_t)((c + TM_EPARTS) * 16), raw);      // next chunk: latency hidden behind the math
+          if (colok) {
+            auto body = [&](auto extra_tag) {
+              constexpr bool EXTRA = decltype(extra_tag)::value;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (!((rmask >> j) & 1u)) continue;
+                const float4 a = lds128(st_r + (uint32_t)j * 640u);
+                float2 v0 = make_float2(a.x, a.y), v1 = make_float2(a.z, a.w);
+                if (EXTRA && p.add0) { v0 = __fadd2_rn(v0, make_float2(A[j].x, A[j].y)); v1 = __fadd2_rn(v1, make_float2(A[j].z, A[j].w)); }
+                v0 = __ffma2_rn(v0, make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                v1 = __ffma2_rn(v1, make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                v0 = act_t2<ACT>(v0, p.act); v1 = act_t2<ACT>(v1, p.act);
+                if (EXTRA) {
+                  if (p.mul1) {                     // (layer scale: re-read per row from L1 - these long-K layers have the slack, the registers do not)
+                    const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mul1 + cq));
+                    v0 = __fmul2_rn(v0, make_float2(mu.x, mu.y)); v1 = __fmul2_rn(v1, make_float2(mu.z, mu.w));
+                  }
+                  if (p.add1) { v0 = __fadd2_rn(v0, make_float2(A[j].x, A[j].y)); v1 = __fadd2_rn(v1, make_float2(A[j].z, A[j].w)); }
+                }
+                if (p.out) *reinterpret_cast<float4*>(p.out + (eo[j] + (uint32_t)cq)) = make_float4(v0.x, v0.y, v1.x, v1.y);
+                if (p.os_hi) {                       // producer -> consumer fusion: store the consumer's bf16 hi / mid operands directly
+                  if (p.os_scale) {
+                    const float4 osc = __ldg(reinterpret_cast<const float4*>(p.os_scale + cq)), osh = __ldg(reinterpret_cast<const float4*>(p.os_shift + cq));
+                    v0 = __ffma2_rn(v0, make_float2(osc.x, osc.y), make_float2(osh.x, osh.y));
+                    v1 = __ffma2_rn(v1, make_float2(osc.z, osc.w), make_float2(osh.z, osh.w));
+                    if (p.os_relu) { v0 = make_float2(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f)); v1 = make_float2(fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f)); }
+                  }
+                  uint2 hh, mm;
+                  split4p(v0, v1, hh, mm);
+                  const uint32_t o = so[j] + (uint32_t)cq;
+                  *reinterpret_cast<uint2*>(p.os_hi + o) = hh;
+                  *reinterpret_cast<uint2*>(p.os_mid + o) = mm;
+                }
+              }
+            };
+            if (extra) body(std::true_type{}); else body(std::false_type{});
+          }
+          __syncwarp();
         }
       } else if (!p.out_planar && ((p.out_cs | p.out_coff) & 3) == 0 &&
                  (!p.add0 || (!p.add0_planar && ((p.add0_cs | p.add0_coff) & 3) == 0)) &&
@@ -912,6 +1004,20 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
     p.os_scale = op.os_scale; p.os_shift = op.os_shift; p.os_relu = op.os_relu;
     if (!op.out.p) { p.oH = op.Ho; p.oW = op.Wo; }
   } else MITB_CHECK(op.out.p || op.stat_max, "tma conv: no output");
+  {
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    p.fast = !op.stat_max && !op.out.planar && op.out.C % 4 == 0 && ((op.out.cs | op.out.coff) & 3) == 0 && al16(op.out.p) &&
+             (!op.add0.p || (!op.add0.planar && ((op.add0.cs | op.add0.coff) & 3) == 0 && al16(op.add0.p))) &&
+             (!op.add1.p || (!op.add1.planar && ((op.add1.cs | op.add1.coff) & 3) == 0 && al16(op.add1.p))) && !(op.add0.p && op.add1.p) &&
+             (size_t)op.out.N * p.oH * p.oW * (size_t)(op.out.p ? op.out.cs : 1) < ((size_t)1 << 31) &&
+             (!op.add0.p || (size_t)op.out.N * p.oH * p.oW * (size_t)op.add0.cs < ((size_t)1 << 31)) &&
+             (!op.add1.p || (size_t)op.out.N * p.oH * p.oW * (size_t)op.add1.cs < ((size_t)1 << 31)) &&
+             (!p.os_hi || (size_t)op.out_sv.N * op.out_sv.Hp * op.out_sv.Wp * (size_t)op.out_sv.C < ((size_t)1 << 31)) && al16(op.scale) && al16(op.shift) && al16(op.mul1) && al16(op.os_scale) && al16(op.os_shift) &&
+             (!p.os_hi || (((uintptr_t)p.os_hi | (uintptr_t)p.os_mid) & 7) == 0);
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("MITB_SLOW_EPILOGUE"); env = (e && atoi(e)) ? 1 : 0; }
+    if (env) p.fast = 0;
+  }
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;

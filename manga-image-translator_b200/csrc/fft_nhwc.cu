@@ -7,7 +7,7 @@
 //     one TMA box per CTA (cp.async.bulk.tensor, mbarrier completion) where the tile shape allows;
 //   * one warp performs 32 independent FFTs in lock step, lane = channel: all butterfly indices and twiddles are
 //     warp-uniform (no divergence, no bank conflicts, twiddle reads broadcast), the transform runs IN PLACE in shared
-//     memory (decimation in frequency, mixed radix {4,2,3,5}); the digit-reversed result order is undone for free when the
+//     memory (decimation in frequency, mixed radix {16,12,4,2,3,5}; 16 = 4x4 and 12 = 4x3 fused in registers); the digit-reversed result order is undone for free when the
 //     rows are written back (each frequency is its own 256-byte segment).
 // Real-input trick: two CHANNELS are packed into one complex sequence (z = x_c0 + i x_c1 is just a float2 load of an NHWC
 // pixel), separated after the row transform; the inverse packs two Hermitian spectra the same way.
@@ -54,6 +54,26 @@ __device__ __forceinline__ float2 rot90(float2 a, bool inv) { return inv ? make_
 template <bool INV>
 __device__ __forceinline__ float2 twc(const float2* tw, int i) { float2 w = tw[i]; if (INV) w.y = -w.y; return w; }
 
+// 4- and 3-point DFTs in registers, natural order in and out (forward: exp(-2 pi i jq / r); INV: conjugate)
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 t0 = caddf(a0, a2), t1 = csubf(a0, a2), t2 = caddf(a1, a3), t3 = rot90(csubf(a1, a3), INV);
+  a0 = caddf(t0, t2); a1 = caddf(t1, t3); a2 = csubf(t0, t2); a3 = csubf(t1, t3);
+}
+template <bool INV>
+__device__ __forceinline__ void dft3(float2& a0, float2& a1, float2& a2) {
+  const float2 t1 = caddf(a1, a2);
+  const float2 t2 = __ffma2_rn(t1, make_float2(-0.5f, -0.5f), a0);
+  const float2 t3 = __fmul2_rn(csubf(a1, a2), make_float2(0.86602540378443864676f, 0.86602540378443864676f));
+  // forward: y1 = t2 - i t3, y2 = t2 + i t3 ; inverse: swapped
+  const float2 y1 = make_float2(t2.x + t3.y, t2.y - t3.x), y2 = make_float2(t2.x - t3.y, t2.y + t3.x);
+  a0 = caddf(a0, t1);
+  a1 = INV ? y2 : y1; a2 = INV ? y1 : y2;
+}
+// multiply by the constant twiddle exp(-2 pi i e / N) = (c, -s) (INV: conjugate)
+template <bool INV>
+__device__ __forceinline__ float2 cmulk(float2 a, float c, float s) { return cmulf(a, make_float2(c, INV ? s : -s)); }
+
 template <bool INV>
 __device__ __forceinline__ void fft_dif(float2* X, const float2* tw, const uint32_t* bt, const FftNDev& pl, int lane, int warp) {
   int L = pl.n;
@@ -62,7 +82,56 @@ __device__ __forceinline__ void fft_dif(float2* X, const float2* tw, const uint3
     const int m = L / r;                 // length of the sub-sequences this stage produces
     const int nb = pl.n / r;
     const uint32_t sm = (uint32_t)m * FV;
-    if (r == 4) {
+    if (r == 16) {
+      // two radix-4 steps fused in registers: j = j1 + 4 j2, q = 4 q1 + q2, w16^(jq) = w4^(j1 q1) w16^(j1 q2) w4^(j2 q2).
+      // Halves the shared-memory round trips, table lookups and barriers of two radix-4 stages (the kernels are issue bound).
+      const float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, H = 0.70710678118654752440f;
+      for (int b = warp; b < nb; b += FW) {
+        const uint32_t e = bt[b];
+        float2* x = X + (e & 0xffffu) * FV + lane;
+        const int kt = (int)(e >> 16);
+        float2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = x[j * sm];
+#pragma unroll
+        for (int j1 = 0; j1 < 4; ++j1) dft4<INV>(a[j1], a[j1 + 4], a[j1 + 8], a[j1 + 12]);        // b[j1][q2] -> a[j1 + 4 q2]
+        a[5] = cmulk<INV>(a[5], C1, S1);  a[6] = cmulk<INV>(a[6], H, H);     a[7] = cmulk<INV>(a[7], S1, C1);      // w16^1, ^2, ^3
+        a[9] = cmulk<INV>(a[9], H, H);    a[10] = rot90(a[10], INV);         a[11] = cmulk<INV>(a[11], -H, H);     // w16^2, ^4, ^6
+        a[13] = cmulk<INV>(a[13], S1, C1); a[14] = cmulk<INV>(a[14], -H, H); a[15] = cmulk<INV>(a[15], -C1, -S1);  // w16^3, ^6, ^9
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) dft4<INV>(a[4 * q2], a[4 * q2 + 1], a[4 * q2 + 2], a[4 * q2 + 3]);     // y[4 q1 + q2] -> a[4 q2 + q1]
+        if (kt) {
+#pragma unroll
+          for (int q = 1; q < 16; ++q) a[4 * (q & 3) + (q >> 2)] = cmulf(a[4 * (q & 3) + (q >> 2)], twc<INV>(tw, q * kt));
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q * sm] = a[4 * (q & 3) + (q >> 2)];
+      }
+    } else if (r == 12) {
+      // radix 4 x radix 3 fused in registers: j = j1 + 3 j2, q = 4 q1 + q2, w12^(jq) = w3^(j1 q1) w12^(j1 q2) w4^(j2 q2)
+      const float C1 = 0.86602540378443864676f;
+      for (int b = warp; b < nb; b += FW) {
+        const uint32_t e = bt[b];
+        float2* x = X + (e & 0xffffu) * FV + lane;
+        const int kt = (int)(e >> 16);
+        float2 a[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) a[j] = x[j * sm];
+#pragma unroll
+        for (int j1 = 0; j1 < 3; ++j1) dft4<INV>(a[j1], a[j1 + 3], a[j1 + 6], a[j1 + 9]);           // b[j1][q2] -> a[j1 + 3 q2]
+        a[4] = cmulk<INV>(a[4], C1, 0.5f);   a[5] = cmulk<INV>(a[5], 0.5f, C1);                         // q2 = 1: w12^1, w12^2
+        a[7] = cmulk<INV>(a[7], 0.5f, C1);   a[8] = cmulk<INV>(a[8], -0.5f, C1);                        // q2 = 2: w12^2, w12^4
+        a[10] = rot90(a[10], INV);           a[11] = make_float2(-a[11].x, -a[11].y);                   // q2 = 3: w12^3 = -i, w12^6 = -1
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) dft3<INV>(a[3 * q2], a[3 * q2 + 1], a[3 * q2 + 2]);           // y[4 q1 + q2] -> a[3 q2 + q1]
+        if (kt) {
+#pragma unroll
+          for (int q = 1; q < 12; ++q) a[3 * (q & 3) + (q >> 2)] = cmulf(a[3 * (q & 3) + (q >> 2)], twc<INV>(tw, q * kt));
+        }
+#pragma unroll
+        for (int q = 0; q < 12; ++q) x[q * sm] = a[3 * (q & 3) + (q >> 2)];
+      }
+    } else if (r == 4) {
       for (int b = warp; b < nb; b += FW) {
         const uint32_t e = bt[b];
         float2* x = X + (e & 0xffffu) * FV + lane;
@@ -280,6 +349,8 @@ std::map<std::pair<int, int>, PlanN*> g_plans;
 bool factor(int n, int* radix, int* nst) {
   int r = n, k = 0;
   auto push = [&](int f) { if (k < kMaxSt) radix[k] = f; ++k; };
+  while (r % 16 == 0) { push(16); r /= 16; }              // fused stages first: (4 x 4) and (4 x 3) in registers
+  if (r % 12 == 0) { push(12); r /= 12; }
   while (r % 4 == 0) { push(4); r /= 4; }
   while (r % 2 == 0) { push(2); r /= 2; }
   while (r % 3 == 0) { push(3); r /= 3; }
