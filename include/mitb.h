@@ -136,6 +136,20 @@ int mitb_op_mpe_tables(mitb_ctx* ctx, const uint8_t* small, int n, int32_t* rel_
 /* cv2.bilateralFilter(img, 17, 80, 80) on a uint8 HWC3 device image (detector pre-filter, dbnet_convnext.py:549). */
 int mitb_op_bilateral17(mitb_ctx* ctx, const uint8_t* img, int h, int w, uint8_t* out, void* stream);
 
+/* Text-line crops on the device: for each of the n lines of an OCR chunk,
+ * cv2.warpPerspective(page[y1:y2, x1:x2], M, (w, h)) [+ cv2.rotate(ROTATE_90_COUNTERCLOCKWISE) for vertical lines] of
+ * Quadrilateral.get_transformed_region (utils/generic.py:445-481), written into the zero-padded chunk canvas
+ * uint8 [n, canvas_h, canvas_w, 3] of Model48pxCTCOCR._infer (ocr/model_48px_ctc.py:86-92).  Bit-exact with OpenCV (INTER_LINEAR,
+ * BORDER_CONSTANT 0).  page: uint8 [h, w, 3] on the device.  lines: device double [n][16] = { Minv[9] (inverse of the homography the
+ * host solved with cv2.findHomography, row major), x1, y1, crop_w, crop_h, out_w, out_h (before the rotation), rot (0 / 1) }. */
+int mitb_op_warp_lines_u8(mitb_ctx* ctx, const uint8_t* page, int h, int w, const double* lines, int n, uint8_t* canvas, int canvas_h,
+                          int canvas_w, void* stream);
+/* Greedy CTC collapse of decode_ctc_top1 (ocr/model_48px_ctc.py:466-478, row O8): per line keep step t iff argmax[t] != 0 (blank) and
+ * argmax[t] != argmax[t-1]; counts int32 [n]; the kept steps, their character ids, log-probabilities and colours are compacted to the
+ * front of steps / chars int32 [n,t], logprob_out [n,t], colors_out [n,t,6] (the last two may be NULL). */
+int mitb_op_ctc_collapse(mitb_ctx* ctx, const int32_t* argmax, const float* logprob, const float* colors, int n, int t, int32_t* counts,
+                         int32_t* steps, int32_t* chars, float* logprob_out, float* colors_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

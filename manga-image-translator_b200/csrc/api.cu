@@ -355,4 +355,22 @@ int mitb_op_bilateral17(mitb_ctx* ctx, const uint8_t* img, int h, int w, uint8_t
   API_END(ctx)
 }
 
+int mitb_op_warp_lines_u8(mitb_ctx* ctx, const uint8_t* page, int h, int w, const double* lines, int n, uint8_t* canvas, int canvas_h,
+                          int canvas_w, void* stream) {
+  API_BEGIN(ctx)
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;
+  launch_warp_lines(page, h, w, lines, n, canvas, canvas_h, canvas_w, (cudaStream_t)stream);
+  g_launch_counter = nullptr;
+  API_END(ctx)
+}
+
+int mitb_op_ctc_collapse(mitb_ctx* ctx, const int32_t* argmax, const float* logprob, const float* colors, int n, int t, int32_t* counts,
+                         int32_t* steps, int32_t* chars, float* logprob_out, float* colors_out, void* stream) {
+  API_BEGIN(ctx)
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;
+  launch_ctc_collapse(argmax, logprob, colors, n, t, counts, steps, chars, logprob_out, colors_out, (cudaStream_t)stream);
+  g_launch_counter = nullptr;
+  API_END(ctx)
+}
+
 }  // extern "C"

@@ -24,6 +24,7 @@
 // box; 1x1 convs use the flattened [pixels][C] matrix (bw = 128, bh = 1).  Persistent CTAs, one per SM.
 #include <cuda.h>
 #include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <cuda_bf16.h>
 #include <type_traits>
@@ -738,7 +739,26 @@ void make_w_tmap(CUtensorMap* m, const uint16_t* base, int kdim, int rows, int b
 // N tile width: minimise waves x tile time.  Tile time per K block = max(tensor floor 6*bn cycles, operand bytes over the
 // SM's share of L2 bandwidth ~42 B/clk); candidates split Cout into j equal tiles rounded up to 16.
 // cg = 2: tiles are 256-row pair tiles on sms/2 SM pairs, each CTA stages half of the weight tile.
-int choose_bn(int Cout, long mtiles, int nkb, int sms, int cg, double* cost_out) {
+// Epilogue term: the accumulator is double buffered, so a tile costs max(main loop, epilogue) once the pipeline is full; the
+// epilogue drains 128 x bn elements at `epi` cycles per column (measured instruction counts of the packed epilogue: ~26 per
+// element with GELU + operand split, ~12 without, over 4 schedulers at ~0.7 issue efficiency).  MITB_CM="mode,epi_gelu,epi,fix"
+// overrides the constants (tools/cost_model_sweep.py).
+struct CostModel { int mode; double epi_gelu, epi, fix; };
+const CostModel& cost_model() {
+  static CostModel cm = {0, 40.0, 40.0, 600.0};
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (const char* e = getenv("MITB_CM")) {
+      int mode = 0; double a = 0, b = 0, c = 0;
+      if (sscanf(e, "%d,%lf,%lf,%lf", &mode, &a, &b, &c) == 4) cm = {mode, a, b, c};
+    }
+  }
+  return cm;
+}
+
+int choose_bn(int Cout, long mtiles, int nkb, int sms, int cg, bool gelu, double* cost_out) {
+  const CostModel& cm = cost_model();
   double best = 1e30; int best_bn = 16;
   const long units = sms / cg, mt = (mtiles + cg - 1) / cg;
   for (int j = 1; j <= 16; ++j) {
@@ -748,7 +768,8 @@ int choose_bn(int Cout, long mtiles, int nkb, int sms, int cg, double* cost_out)
     const long nt = (Cout + bn - 1) / bn;
     const long waves = (mt * nt + units - 1) / units;
     const double mma = 6.0 * bn, l2 = (32768.0 + 256.0 * bn / cg) / 42.0;
-    const double tile = nkb * (mma > l2 ? mma : l2) + 40.0 * bn + 600.0;
+    const double main_loop = nkb * (mma > l2 ? mma : l2), epi = (gelu ? cm.epi_gelu : cm.epi) * bn;
+    const double tile = (cm.mode == 1 ? (main_loop > epi ? main_loop : epi) : main_loop + epi) + cm.fix;
     const double cost = waves * tile;
     if (cost < best * 0.999) { best = cost; best_bn = bn; }
   }
@@ -975,8 +996,8 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
   if (op.stat_max) p.BN = op.tc_bn;
   else {
     double c1 = 0, c2 = 0;
-    const int bn1 = choose_bn(op.out.C, mtiles, p.nkb, num_sms, 1, &c1);
-    const int bn2 = choose_bn(op.out.C, mtiles, p.nkb, num_sms, 2, &c2);
+    const int bn1 = choose_bn(op.out.C, mtiles, p.nkb, num_sms, 1, op.act == ACT_GELU, &c1);
+    const int bn2 = choose_bn(op.out.C, mtiles, p.nkb, num_sms, 2, op.act == ACT_GELU, &c2);
     const int mode = pair_mode_env();
     // CTA pairs (cta_group::2) when the per-SM L2 budget, not the tensor pipe, bounds the tile and there are enough pair tiles
     if (mtiles >= 2 && num_sms % 2 == 0 && (mode >= 2 || (mode == 1 && c2 < 0.97 * c1))) { cg = 2; p.BN = bn2; } else p.BN = bn1;

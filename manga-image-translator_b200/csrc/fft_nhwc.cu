@@ -265,7 +265,7 @@ __device__ __forceinline__ void store_pair(const FftKParams& p, size_t pix, int 
   if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---- forward rows: S [N*h rows][w][C] real -> T [N*h][w2][C] complex.  CTA = (row, chunk of 32 channel PAIRS)
-__global__ void __launch_bounds__(FT) rfft_rows_nhwc_kernel(const __grid_constant__ FftKParams p) {
+__global__ void __launch_bounds__(FT, 3) rfft_rows_nhwc_kernel(const __grid_constant__ FftKParams p) {
   FFT_SMEM_CARVE(p.pl.n)
   const int row = blockIdx.x, chunk = blockIdx.y;
   const int pair = chunk * FV + lane;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(FT) rfft_rows_nhwc_kernel(const __grid_constan
 // ---- columns: complex FFT over h.  forward: T -> spectrum * scale (split and/or fp32 [..][2C]); inverse: F fp32 [..][2C] -> T
 // CTA = (n * w2 + kx, chunk of 32 complex channels)
 template <bool INV>
-__global__ void __launch_bounds__(FT) fft_cols_nhwc_kernel(const __grid_constant__ FftKParams p) {
+__global__ void __launch_bounds__(FT, 3) fft_cols_nhwc_kernel(const __grid_constant__ FftKParams p) {
   FFT_SMEM_CARVE(p.pl.n)
   const int n = blockIdx.x / p.w2, kx = blockIdx.x - n * p.w2, chunk = blockIdx.y;
   const int ch = chunk * FV + lane;                     // complex channel
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(FT) fft_cols_nhwc_kernel(const __grid_constant
 }
 
 // ---- inverse rows: T [N*h][w2][C] complex (+ residual) -> U [N*h][w][C] real.  CTA = (row, chunk of 32 channel pairs)
-__global__ void __launch_bounds__(FT) irfft_rows_nhwc_kernel(const __grid_constant__ FftKParams p) {
+__global__ void __launch_bounds__(FT, 3) irfft_rows_nhwc_kernel(const __grid_constant__ FftKParams p) {
   FFT_SMEM_CARVE(p.pl.n)
   const int row = blockIdx.x, chunk = blockIdx.y;
   const int pair = chunk * FV + lane;

@@ -149,6 +149,11 @@ void launch_lama_pack_input(const float* img, const float* mask, int N, int H, i
 void launch_lama_blend(const View& pred, const float* img, const float* mask, float* out, cudaStream_t st);
 void launch_lama_pack_u8(const uint8_t* img, const uint8_t* mask, int H, int W, const View& dst, float* maskf, cudaStream_t st);
 void launch_lama_blend_u8(const View& pred, const uint8_t* img, const uint8_t* mask, uint8_t* out, int composite, cudaStream_t st);
+// warp.cu: perspective crops of text lines into the OCR chunk canvas (cv2.warpPerspective + rotate, bit-exact) and greedy CTC collapse
+void launch_warp_lines(const uint8_t* page, int H, int W, const double* lines /*[n][16]*/, int n, uint8_t* canvas, int canvas_h, int canvas_w,
+                       cudaStream_t st);
+void launch_ctc_collapse(const int* argmax, const float* logprob, const float* colors, int n, int T, int* counts, int* steps, int* chars,
+                         float* lp_out, float* col_out, cudaStream_t st);
 void launch_mpe_tables(const uint8_t* small /*[n,256,256] INTER_AREA-reduced mask*/, int n, int* rel_pos, int* direct, cudaStream_t st);
 void launch_mpe_add(const View& x, const int* rel_pos, const int* direct, int th, int tw, const float* mask,
                     const float* table, const float* dirw, float a5, float a6, cudaStream_t st);

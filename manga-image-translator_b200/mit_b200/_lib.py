@@ -60,6 +60,8 @@ SIGNATURES = {
     "mitb_op_attention": (I, [P, P, P, I, I, I, I, P, P]),
     "mitb_op_mpe_tables": (I, [P, P, I, P, P, P]),
     "mitb_op_bilateral17": (I, [P, P, I, I, P, P]),
+    "mitb_op_warp_lines_u8": (I, [P, P, I, I, P, I, P, I, I, P]),
+    "mitb_op_ctc_collapse": (I, [P, P, P, P, I, I, P, P, P, P, P, P]),
 }
 
 

@@ -364,6 +364,35 @@ class Engine:
         self._call(self.lib.mitb_op_bilateral17, _ptr(img), h, w, _ptr(out), self._stream())
         return out
 
+    def warp_lines(self, page: torch.Tensor, records: np.ndarray, canvas_w: int, canvas_h: int = 48) -> torch.Tensor:
+        """Perspective crops of the text lines of one OCR chunk straight into the chunk canvas (row O3 on the device).
+        page: uint8 [H,W,3] CUDA tensor; records: float64 [n,16] from host.geometry.warp_record; returns uint8 [n,canvas_h,canvas_w,3]."""
+        assert page.is_cuda and page.dtype == torch.uint8 and page.dim() == 3 and page.shape[2] == 3 and page.is_contiguous()
+        if isinstance(records, torch.Tensor) and records.is_cuda:
+            rec = records.contiguous()
+            assert rec.dtype == torch.float64
+        else:
+            rec = self.h2d(np.ascontiguousarray(records, dtype=np.float64))
+        assert rec.dim() == 2 and rec.shape[1] == 16
+        n = int(rec.shape[0])
+        canvas = torch.empty((n, canvas_h, canvas_w, 3), dtype=torch.uint8, device=self.device)
+        self._call(self.lib.mitb_op_warp_lines_u8, _ptr(page), int(page.shape[0]), int(page.shape[1]), _ptr(rec), n, _ptr(canvas), canvas_h,
+                   canvas_w, self._stream())
+        return canvas
+
+    def ctc_collapse(self, idx: torch.Tensor, logprob: torch.Tensor, colors: torch.Tensor):
+        """Greedy CTC collapse on the device (row O8): returns (counts [n], steps [n,T], chars [n,T], logprob [n,T], colors [n,T,6]) with
+        the kept steps compacted to the front of each row; entries past counts[i] are unspecified."""
+        n, T = idx.shape
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        steps = torch.empty((n, T), dtype=torch.int32, device=self.device)
+        chars = torch.empty((n, T), dtype=torch.int32, device=self.device)
+        lp = torch.empty((n, T), dtype=torch.float32, device=self.device)
+        col = torch.empty((n, T, 6), dtype=torch.float32, device=self.device)
+        self._call(self.lib.mitb_op_ctc_collapse, _ptr(idx.contiguous()), _ptr(logprob.contiguous()), _ptr(colors.contiguous()), n, T,
+                   _ptr(counts), _ptr(steps), _ptr(chars), _ptr(lp), _ptr(col), self._stream())
+        return counts, steps, chars, lp, col
+
 
 _engines = {}
 

@@ -224,26 +224,47 @@ class Quadrilateral:
     def get_transformed_region(self, img, direction, textheight) -> np.ndarray:
         """Perspective crop to a `textheight`-tall strip (generic.py:445-481): crop the AABB, homography from the 4 corners
         (cv2.findHomography RANSAC 5.0), warpPerspective; vertical lines are rotated 90 degrees counter-clockwise."""
-        v_vec, h_vec = self._axes()
-        ratio = np.linalg.norm(v_vec) / np.linalg.norm(h_vec)
-        src = self.pts.astype(np.int64).copy()
-        im_h, im_w = img.shape[:2]
-        x1, y1 = np.clip(src[:, 0].min(), 0, im_w), np.clip(src[:, 1].min(), 0, im_h)
-        x2, y2 = np.clip(src[:, 0].max(), 0, im_w), np.clip(src[:, 1].max(), 0, im_h)
-        crop = img[y1:y2, x1:x2]
-        src[:, 0] -= x1
-        src[:, 1] -= y1
-        self.assigned_direction = direction
-        if direction == "h":
-            h, w = max(int(textheight), 2), max(int(round(textheight / ratio)), 2)
-        else:
-            w, h = max(int(textheight), 2), max(int(round(textheight * ratio)), 2)
-        dst = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], dtype=np.float32)
-        M, _ = cv2.findHomography(src, dst, cv2.RANSAC, 5.0)
-        region = cv2.warpPerspective(crop, M, (w, h))
+        (x1, y1, x2, y2), M, (w, h) = warp_setup(self, img.shape[0], img.shape[1], direction, textheight)
+        region = cv2.warpPerspective(img[y1:y2, x1:x2], M, (w, h))
         if direction == "v":
             region = cv2.rotate(region, cv2.ROTATE_90_COUNTERCLOCKWISE)
         return region
+
+
+def warp_setup(q, im_h: int, im_w: int, direction: str, textheight):
+    """Host half of Quadrilateral.get_transformed_region (generic.py:445-468): the clipped AABB of the quad, the homography onto
+    the (w, h) strip and that size.  `q` is any object with `.structure` and `.pts` (ours or the reference's Quadrilateral)."""
+    l1a, l1b, l2a, l2b = [np.asarray(a).astype(np.float32) for a in q.structure]
+    ratio = np.linalg.norm(l1b - l1a) / np.linalg.norm(l2b - l2a)
+    src = q.pts.astype(np.int64).copy()
+    x1, y1 = np.clip(src[:, 0].min(), 0, im_w), np.clip(src[:, 1].min(), 0, im_h)
+    x2, y2 = np.clip(src[:, 0].max(), 0, im_w), np.clip(src[:, 1].max(), 0, im_h)
+    src[:, 0] -= x1
+    src[:, 1] -= y1
+    q.assigned_direction = direction
+    if direction == "h":
+        h, w = max(int(textheight), 2), max(int(round(textheight / ratio)), 2)
+    else:
+        w, h = max(int(textheight), 2), max(int(round(textheight * ratio)), 2)
+    dst = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], dtype=np.float32)
+    M, _ = cv2.findHomography(src, dst, cv2.RANSAC, 5.0)
+    return (int(x1), int(y1), int(x2), int(y2)), M, (w, h)
+
+
+def warp_record(q, im_h: int, im_w: int, direction: str, textheight=48):
+    """One line record of `mitb_op_warp_lines_u8` (include/mitb.h): float64[16] = inverse homography (cv2.invert, the very call
+    cv2.warpPerspective makes on M), crop origin and size, strip size before the rotation, rotation flag; plus the width of the
+    strip as it lands in the OCR canvas.  A degenerate quad (empty crop, or no homography) yields an all-zero strip, where the
+    reference would raise inside cv2."""
+    (x1, y1, x2, y2), M, (w, h) = warp_setup(q, im_h, im_w, direction, textheight)
+    rec = np.zeros(16, dtype=np.float64)
+    rot = 1 if direction == "v" else 0
+    if M is not None and x2 > x1 and y2 > y1:
+        rec[:9] = cv2.invert(np.asarray(M, dtype=np.float64))[1].reshape(-1)
+        rec[9:16] = (x1, y1, x2 - x1, y2 - y1, w, h, rot)
+    else:
+        rec[13:16] = (w, h, rot)
+    return rec, (h if rot else w)
 
 
 def can_merge_region(a: Quadrilateral, b: Quadrilateral, ratio=1.9, discard_connection_gap=2, char_gap_tolerance=0.6,

@@ -20,6 +20,7 @@ from . import exchange, plugins, synth
 from .compat import InpainterConfig, OcrConfig, chunks
 from .engine import get_engine
 from .host import mpe
+from .host.geometry import warp_record
 
 
 @dataclass
@@ -33,7 +34,7 @@ class PageResult:
 @dataclass
 class StagedPage:
     page_u8: torch.Tensor                   # [H,W,3] uint8 on device
-    ocr_chunks: List[torch.Tensor]          # uint8 [n,48,wp,3] on device
+    ocr_chunks: list                        # per chunk of <= 16 lines: (float64 [n,16] warp records on the device, canvas width)
     mask_u8: torch.Tensor                   # [H,W] uint8 on device
     rel_pos: Optional[torch.Tensor]
     direct: Optional[torch.Tensor]
@@ -91,21 +92,21 @@ class HotPath:
     def stage(self, page: np.ndarray, quads, mask: np.ndarray) -> StagedPage:
         eng = self.engine
         dev = eng.device
-        regions = [q.get_transformed_region(page, q.direction, 48) for q in quads]
-        perm = sorted(range(len(regions)), key=lambda i: regions[i].shape[1])
+        # OCR lines: only the 4-point homographies are host work; the crops themselves are cut out of the resident page by
+        # mitb_op_warp_lines_u8 inside run_resident (one launch per chunk of 16 lines, sorted by width like the reference)
+        recs = [warp_record(q, page.shape[0], page.shape[1], q.direction, 48) for q in quads]
+        perm = sorted(range(len(recs)), key=lambda i: recs[i][1])
         chunks_dev = []
         for indices in chunks(perm, 16):
-            widths = [regions[i].shape[1] for i in indices]
-            canvas = np.zeros((len(indices), 48, max(widths) + 7 + 128, 3), np.uint8)
-            for i, idx in enumerate(indices):
-                canvas[i, :, :widths[i]] = regions[idx]
-            chunks_dev.append(torch.from_numpy(canvas).to(dev))
+            widths = [recs[i][1] for i in indices]
+            rec = np.stack([recs[i][0] for i in indices])
+            chunks_dev.append((torch.from_numpy(rec).to(dev), max(widths) + 7 + 128))
         rel = direct = None
         if self.use_mpe:
             r, d = mpe.mpe_tables_256(((mask.astype(np.float32) / 255.0) >= 0.5).astype(np.float32))
             rel, direct = torch.from_numpy(r[None]).to(dev), torch.from_numpy(d[None]).to(dev)
         sp = StagedPage(torch.from_numpy(page).to(dev), chunks_dev, torch.from_numpy(mask).to(dev), rel, direct)
-        sp.bytes = sum(t.numel() * t.element_size() for t in [sp.page_u8, sp.mask_u8] + chunks_dev +
+        sp.bytes = sum(t.numel() * t.element_size() for t in [sp.page_u8, sp.mask_u8] + [c[0] for c in chunks_dev] +
                        ([rel, direct] if rel is not None else []))
         return sp
 
@@ -113,7 +114,10 @@ class HotPath:
         eng = self.engine
         filt = eng.bilateral17(sp.page_u8)
         db, dmask = eng.dbnet_forward(filt[None])
-        ocr = [eng.ocr_forward(c) for c in sp.ocr_chunks]
+        ocr = []
+        for rec, wp in sp.ocr_chunks:
+            pred, logprob, colors = eng.ocr_forward(eng.warp_lines(sp.page_u8, rec, wp))
+            ocr.append(eng.ctc_collapse(pred, logprob, colors))
         out = eng.lama_infer_u8(sp.page_u8, sp.mask_u8, sp.rel_pos, sp.direct, composite=True)
         return db, dmask, ocr, out
 

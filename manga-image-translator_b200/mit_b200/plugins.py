@@ -28,6 +28,7 @@ from .compat import InpainterConfig, OcrConfig, OfflineDetector, OfflineInpainte
 from .engine import Engine, get_engine, trace
 from ._lib import MitbError
 from .host import det_post, mpe, rearrange
+from .host.geometry import warp_record
 
 
 def _require_cuda(device: str) -> str:
@@ -168,42 +169,61 @@ class Model48pxCTCOCR(_InjectableWeights, OfflineOCR):
         threshold = 0.5 if getattr(config, "prob", None) is None else config.prob
         with trace("host:ocr_direction"):
             quadrilaterals = list(self._generate_text_direction(textlines))
-        with trace("host:ocr_crops"):
-            region_imgs = [q.get_transformed_region(image, d, text_height) for q, d in quadrilaterals]
+        # Crops: by default on the device: the host solves the 4-point homographies, one kernel per chunk warps the
+        # lines out of the resident page straight into the chunk canvas (bit-exact with cv2.warpPerspective + rotate).  The bubble
+        # filter needs the crops on the host, so it keeps the reference's own sequence (MITB_HOST_CROPS=1 forces that path too).
+        host_crops = ((1 <= ignore_bubble <= 50) or os.environ.get("MITB_HOST_CROPS", "0") == "1" or image.dtype != np.uint8 or image.ndim != 3
+                      or image.shape[2] != 3 or not all(isinstance(q, Quadrilateral) for q, _ in quadrilaterals))
+        eng = self.engine
+        if host_crops:
+            with trace("host:ocr_crops"):
+                region_imgs = [q.get_transformed_region(image, d, text_height) for q, d in quadrilaterals]
+            line_w = [r.shape[1] for r in region_imgs]
+        else:
+            with trace("host:ocr_homography"):
+                recs = [warp_record(q, image.shape[0], image.shape[1], d, text_height) for q, d in quadrilaterals]
+            line_w = [w for _, w in recs]
+            rec_arr = np.stack([r for r, _ in recs]) if recs else np.zeros((0, 16), dtype=np.float64)
+            page_dev = eng.h2d(np.ascontiguousarray(image)) if recs else None
         out_regions = []
-        perm = range(len(region_imgs))
+        perm = range(len(line_w))
         is_quadrilaterals = False
         if len(quadrilaterals) > 0 and isinstance(quadrilaterals[0][0], Quadrilateral):
             is_quadrilaterals = True
-            perm = sorted(range(len(region_imgs)), key=lambda x: region_imgs[x].shape[1])
+            perm = sorted(range(len(line_w)), key=lambda x: line_w[x])
         if 1 <= ignore_bubble <= 50:
             from .host.bubble import is_ignore
         for indices in chunks(perm, max_chunk_size):
             N = len(indices)
-            widths = [region_imgs[i].shape[1] for i in indices]
+            widths = [line_w[i] for i in indices]
             max_width = (4 * (max(widths) + 7) // 4) + 128
-            region = np.zeros((N, text_height, max_width, 3), dtype=np.uint8)
-            for i, idx in enumerate(indices):
-                if 1 <= ignore_bubble <= 50 and is_ignore(region_imgs[idx], ignore_bubble):
+            if host_crops:
+                region = np.zeros((N, text_height, max_width, 3), dtype=np.uint8)
+                for i, idx in enumerate(indices):
+                    if 1 <= ignore_bubble <= 50 and is_ignore(region_imgs[idx], ignore_bubble):
+                        continue
+                    region[i, :, :widths[i], :] = region_imgs[idx]
+                region_dev = eng.h2d(region)
+            else:
+                region_dev = eng.warp_lines(page_dev, rec_arr[list(indices)], max_width, text_height)
+            # (x-127.5)/127.5 normalisation, network, log-softmax/argmax, colour clamp and the greedy CTC collapse all run on the device
+            pred, logprob, colors = eng.ocr_forward(region_dev)
+            counts, _, kept_ch, kept_lp, kept_col = eng.ctc_collapse(pred, logprob, colors)
+            counts, kept_ch, kept_lp, kept_col = eng.d2h(counts), eng.d2h(kept_ch), eng.d2h(kept_lp), eng.d2h(kept_col)
+            for i in range(N):
+                cnt = int(counts[i])
+                if cnt == 0:
                     continue
-                region[i, :, :widths[i], :] = region_imgs[idx]
-            # (x-127.5)/127.5 normalisation, network, log-softmax/argmax and colour clamp all run on the device
-            eng = self.engine
-            pred, logprob, colors = eng.ocr_forward(eng.h2d(region))
-            pred, logprob, colors = eng.d2h(pred), eng.d2h(logprob), eng.d2h(colors)
-            for i, steps in enumerate(ctc_collapse(pred)):
-                if len(steps) == 0:
-                    continue
-                chars = [self.dictionary[c] for c in pred[i, steps]]
+                chars = [self.dictionary[c] for c in kept_ch[i, :cnt]]
                 chars = [" " if ch == "<SP>" else ch for ch in chars]
-                prob = np.exp(np.mean(logprob[i, steps].astype(np.float64)))          # mean of python floats == float64 mean
+                prob = np.exp(np.mean(kept_lp[i, :cnt].astype(np.float64)))           # mean of python floats == float64 mean
                 if prob < threshold:
                     continue
                 txt = "".join(chars)
-                sel = [s for s, ch in zip(steps, chars) if ch != " "]
+                sel = [k for k, ch in enumerate(chars) if ch != " "]
                 cols = [0] * 6
                 if sel:
-                    ints = (colors[i, sel].astype(np.float64) * 255).astype(np.int64)   # int(float(v) * 255) per element
+                    ints = (kept_col[i, sel].astype(np.float64) * 255).astype(np.int64)  # int(float(v) * 255) per element
                     cols = [int(ints[:, k].sum() / len(sel)) for k in range(6)]
                 fr, fg, fb, br, bg, bb = cols
                 self.logger.info(f"prob: {prob} {txt} fg: ({fr}, {fg}, {fb}) bg: ({br}, {bg}, {bb})")

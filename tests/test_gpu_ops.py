@@ -215,3 +215,54 @@ def test_bilateral17_matches_cv2(eng):
             assert d.max() <= 1 and (d != 0).mean() < 2e-5
     finally:
         cv2.ipp.setUseIPP(use_ipp)
+
+
+@pytest.mark.gpu
+def test_warp_lines_matches_cv2(eng):
+    """mitb_op_warp_lines_u8 (row O3 on the device) against cv2.warpPerspective + cv2.rotate as Quadrilateral.get_transformed_region
+    calls them (utils/generic.py:445-481): bit-exact, incl. vertical lines, quads clipped by the page border and the zero padding."""
+    from mit_b200.host import geometry
+    from test_host import _random_line_quads
+    rng = np.random.default_rng(5)
+    H, W = 1100, 800
+    page = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    page_dev = torch.from_numpy(page).to(eng.device)
+    quads = [geometry.Quadrilateral(p, "", 1.0) for p in _random_line_quads(rng, H, W, 48)]
+    recs, regions = [], []
+    for i, q in enumerate(quads):
+        d = "h" if i % 2 else "v"
+        rec, cw = geometry.warp_record(q, H, W, d, 48)
+        if not rec[11] or not rec[12]:
+            continue
+        recs.append(rec)
+        regions.append(q.get_transformed_region(page, d, 48))
+    assert len(recs) >= 40
+    for lo in range(0, len(recs), 16):
+        chunk = recs[lo:lo + 16]
+        wp = max(r.shape[1] for r in regions[lo:lo + 16]) + 135
+        canvas = eng.warp_lines(page_dev, np.stack(chunk), wp).cpu().numpy()
+        assert canvas.shape == (len(chunk), 48, wp, 3)
+        for k, reg in enumerate(regions[lo:lo + 16]):
+            assert np.array_equal(canvas[k, :, :reg.shape[1]], reg), f"line {lo + k}: {(canvas[k, :, :reg.shape[1]] != reg).sum()} bytes differ"
+            assert not canvas[k, :, reg.shape[1]:].any()
+
+
+@pytest.mark.gpu
+def test_ctc_collapse_device(eng):
+    """mitb_op_ctc_collapse (row O8) against the host collapse that is itself pinned to the reference's decode_ctc_top1."""
+    from mit_b200.plugins import ctc_collapse
+    rng = np.random.default_rng(2)
+    n, T = 16, 173
+    idx = rng.integers(0, 4, (n, T)).astype(np.int32)           # few symbols: many blanks and repeats
+    idx[3] = 0
+    idx[4] = 2
+    lp = rng.standard_normal((n, T)).astype(np.float32)
+    col = rng.random((n, T, 6)).astype(np.float32)
+    dev = eng.device
+    counts, steps, chars, klp, kcol = [t.cpu().numpy() for t in eng.ctc_collapse(torch.from_numpy(idx).to(dev), torch.from_numpy(lp).to(dev),
+                                                                                torch.from_numpy(col).to(dev))]
+    for i, st in enumerate(ctc_collapse(idx)):
+        st = np.asarray(st, dtype=np.int64)
+        assert counts[i] == len(st)
+        assert np.array_equal(steps[i, :len(st)], st) and np.array_equal(chars[i, :len(st)], idx[i, st])
+        assert np.array_equal(klp[i, :len(st)], lp[i, st]) and np.array_equal(kcol[i, :len(st)], col[i, st])

@@ -466,3 +466,46 @@ def test_detect_variants_and_bubble_filter_standalone():
     mixed = white.copy(); mixed[:, :60] = 5
     colour = white.copy(); colour[10:30, 10:60] = (250, 20, 20)
     assert not bubble.is_ignore(white, 10) and bubble.is_ignore(mixed, 10) and bubble.is_ignore(colour, 10) and not bubble.is_ignore(mixed, 0)
+
+
+def _random_line_quads(rng, H, W, n):
+    """Rotated rectangles with integer corners, some hanging over the page border, some vertical."""
+    quads = []
+    for t in range(n):
+        cx, cy = rng.uniform(0, W), rng.uniform(0, H)
+        ww, hh = rng.uniform(40, 500), rng.uniform(20, 80)
+        if t % 3 == 0:
+            ww, hh = hh, ww
+        ang = rng.uniform(-0.35, 0.35) if t % 4 else 0.0
+        c, s = np.cos(ang), np.sin(ang)
+        pts = np.array([[-ww / 2, -hh / 2], [ww / 2, -hh / 2], [ww / 2, hh / 2], [-ww / 2, hh / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]
+        quads.append(pts.astype(np.int64))
+    return quads
+
+
+def test_warp_oracle_equals_cv2():
+    """Pins oracle/warp_ref.py (the restatement of OpenCV's warpPerspective the CUDA kernel is checked against) on the installed cv2:
+    bit-exact on random line quads, both strip orientations, incl. quads clipped by the page border."""
+    from oracle import warp_ref
+    rng = np.random.default_rng(11)
+    page = rng.integers(0, 256, (700, 900, 3), dtype=np.uint8)
+    n_px = 0
+    for pts in _random_line_quads(rng, 700, 900, 40):
+        q = geometry.Quadrilateral(pts, "", 1.0)
+        for d in ("h", "v"):
+            (x1, y1, x2, y2), M, (w, h) = geometry.warp_setup(q, 700, 900, d, 48)
+            if M is None or x2 <= x1 or y2 <= y1:
+                continue
+            crop = page[y1:y2, x1:x2]
+            ref = cv2.warpPerspective(crop, M, (w, h))
+            assert np.array_equal(warp_ref.warp_perspective(crop, M, w, h), ref)
+            # ... and the line-record form (what the kernel consumes) reproduces get_transformed_region incl. the rotation
+            rec, cw = geometry.warp_record(q, 700, 900, d, 48)
+            region = q.get_transformed_region(page, d, 48)
+            assert cw == region.shape[1] and region.shape[0] == 48
+            line = warp_ref.warp_line_record(page, rec, cw + 135)
+            assert np.array_equal(line[:, :cw], region) and not line[:, cw:].any()
+            n_px += region.size
+    assert n_px > 10 ** 6
+    tab = warp_ref.bilinear_itab()
+    assert tab[0].tolist() == [32767, 0, 0, 1] and (tab.sum(1) == 32768).all()
