@@ -150,6 +150,37 @@ int mitb_op_warp_lines_u8(mitb_ctx* ctx, const uint8_t* page, int h, int w, cons
 int mitb_op_ctc_collapse(mitb_ctx* ctx, const int32_t* argmax, const float* logprob, const float* colors, int n, int t, int32_t* counts,
                          int32_t* steps, int32_t* chars, float* logprob_out, float* colors_out, void* stream);
 
+/* ---- mask refinement (manga_translator/mask_refinement/__init__.py:9-31, text_mask_utils.py:64-190) ---- */
+/* cv2.resize(src, (dw, dh), interpolation=INTER_LINEAR) for uint8 [sh,sw,channels] (channels 1 or 3), bit-exact; binarize != 0
+ * additionally maps every non-zero result to 255 (`mask[mask > 0] = 255`, __init__.py:18,28). */
+int mitb_op_resize_linear_u8(mitb_ctx* ctx, const uint8_t* src, int sh, int sw, int channels, uint8_t* dst, int dh, int dw, int binarize, void* stream);
+/* cv2.rectangle(mask, (x, y), (x + w, y + h), 0, 1) for n rectangles (rects int32 [n][4] = x, y, w, h; text_mask_utils.py:99-100). */
+int mitb_op_cut_rects(mitb_ctx* ctx, uint8_t* mask, int h, int w, const int32_t* rects, int n, void* stream);
+/* cv2.connectedComponentsWithStats(mask) (8-connectivity): labels int32 [h*w] = component id in [0, ncomp) or -1 for background (ids are
+ * in no particular order - the reference's use of them is order independent), stats int32 [cap][5] = {x0, y0, x1, y1, area},
+ * ncomp int32 [1] (components beyond `cap` get label -1; the caller checks ncomp <= cap).  scratch: int32 [2*h*w]. */
+int mitb_op_cc_label(mitb_ctx* ctx, const uint8_t* mask, int h, int w, int32_t* labels, int32_t* stats, int32_t* ncomp, int cap, int32_t* scratch,
+                     void* stream);
+/* owner_map[i] = owner[labels[i]] (text line owning the pixel's component, -1: none): all textline_ccs of complete_mask in one map. */
+int mitb_op_owner_map(mitb_ctx* ctx, const int32_t* labels, const int32_t* owner, int n, int32_t* owner_map, void* stream);
+/* refine_mask (text_mask_utils.py:71-94) for all text lines of a page at once: DenseCRF2D with unary_from_softmax of the line's
+ * component mask, addPairwiseGaussian(sxy_g, w_g), addPairwiseBilateral(sxy_b, srgb, w_b) (DIAG_KERNEL, NO_NORMALIZATION), `iters`
+ * mean-field iterations, argmax.  lines2 / lines5: int32 [nlines][8] = {x, y, w, h (region in the working image), first pixel of the
+ * region's segment, first slot and capacity (power of two, >= 2 (d+1) w h) of its hash-table segment, 0} for the d = 2 and d = 5
+ * lattices; img uint8 [h,w,3] (the bilateral-filtered working image); refined uint8 [npix] (255: text).  err int32 [1]: non-zero if a
+ * lattice key left the packed range or a table overflowed.  work: device scratch of mitb_op_crf_workspace bytes. */
+int mitb_op_crf_workspace(long long npix, long long nslots2, long long nslots5, unsigned long long* bytes);
+int mitb_op_dense_crf(mitb_ctx* ctx, const int32_t* lines2, const int32_t* lines5, int nlines, const uint8_t* img, const int32_t* owner_map, int img_w,
+                      int max_pix, int max_cap2, int max_cap5, long long npix, long long nslots2, long long nslots5, int iters, float sxy_g,
+                      float w_g, float sxy_b, float srgb, float w_b, float u_on, void* work, uint8_t* refined, int32_t* err, void* stream);
+/* Per line: cc = refined inside rect1, (owner_map == line) elsewhere; cv2.dilate(cc[rect2], ellipse) OR-ed into final_mask
+ * (text_mask_utils.py:183-186).  lines int32 [nlines][12] = {x1,y1,w1,h1, x2,y2,w2,h2, first pixel of the refined segment, offset of
+ * the line's structuring element in `se`, its size, 0}. */
+int mitb_op_dilate_lines(mitb_ctx* ctx, const int32_t* lines, int nlines, int max_pix2, const int32_t* owner_map, const uint8_t* refined,
+                         const uint8_t* se, int img_w, uint8_t* final_mask, void* stream);
+/* cv2.dilate(src, se) for a uint8 image and a ksize x ksize structuring element (anchor at the centre). */
+int mitb_op_dilate_se(mitb_ctx* ctx, const uint8_t* src, int h, int w, const uint8_t* se, int ksize, uint8_t* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

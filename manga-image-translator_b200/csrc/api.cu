@@ -373,4 +373,44 @@ int mitb_op_ctc_collapse(mitb_ctx* ctx, const int32_t* argmax, const float* logp
   API_END(ctx)
 }
 
+#define MITB_OP(body)                                             \
+  API_BEGIN(ctx)                                                  \
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;          \
+  body;                                                           \
+  g_launch_counter = nullptr;                                     \
+  API_END(ctx)
+
+int mitb_op_resize_linear_u8(mitb_ctx* ctx, const uint8_t* src, int sh, int sw, int channels, uint8_t* dst, int dh, int dw, int binarize, void* stream) {
+  MITB_OP(launch_resize_linear_u8(src, sh, sw, channels, dst, dh, dw, binarize, (cudaStream_t)stream))
+}
+int mitb_op_cut_rects(mitb_ctx* ctx, uint8_t* mask, int h, int w, const int32_t* rects, int n, void* stream) {
+  MITB_OP(launch_cut_rects(mask, h, w, rects, n, (cudaStream_t)stream))
+}
+int mitb_op_cc_label(mitb_ctx* ctx, const uint8_t* mask, int h, int w, int32_t* labels, int32_t* stats, int32_t* ncomp, int cap, int32_t* scratch,
+                     void* stream) {
+  MITB_OP(launch_cc_label(mask, h, w, labels, stats, ncomp, cap, scratch, (cudaStream_t)stream))
+}
+int mitb_op_owner_map(mitb_ctx* ctx, const int32_t* labels, const int32_t* owner, int n, int32_t* owner_map, void* stream) {
+  MITB_OP(launch_owner_map(labels, owner, n, owner_map, (cudaStream_t)stream))
+}
+int mitb_op_crf_workspace(long long npix, long long nslots2, long long nslots5, unsigned long long* bytes) {
+  if (!bytes) return 1;
+  *bytes = (unsigned long long)crf_workspace_bytes((long)npix, (long)nslots2, (long)nslots5);
+  return 0;
+}
+int mitb_op_dense_crf(mitb_ctx* ctx, const int32_t* lines2, const int32_t* lines5, int nlines, const uint8_t* img, const int32_t* owner_map, int img_w,
+                      int max_pix, int max_cap2, int max_cap5, long long npix, long long nslots2, long long nslots5, int iters, float sxy_g,
+                      float w_g, float sxy_b, float srgb, float w_b, float u_on, void* work, uint8_t* refined, int32_t* err, void* stream) {
+  MITB_OP(launch_crf(lines2, lines5, nlines, img, owner_map, img_w, max_pix, max_cap2, max_cap5, (long)npix, (long)nslots2, (long)nslots5, iters,
+                     sxy_g, w_g, sxy_b, srgb, w_b, u_on, work, refined, err, (cudaStream_t)stream))
+}
+int mitb_op_dilate_lines(mitb_ctx* ctx, const int32_t* lines, int nlines, int max_pix2, const int32_t* owner_map, const uint8_t* refined,
+                         const uint8_t* se, int img_w, uint8_t* final_mask, void* stream) {
+  MITB_OP(launch_dilate_lines(lines, nlines, max_pix2, owner_map, refined, se, img_w, final_mask, (cudaStream_t)stream))
+}
+int mitb_op_dilate_se(mitb_ctx* ctx, const uint8_t* src, int h, int w, const uint8_t* se, int ksize, uint8_t* dst, void* stream) {
+  MITB_OP(launch_dilate_se(src, h, w, se, ksize, dst, (cudaStream_t)stream))
+}
+#undef MITB_OP
+
 }  // extern "C"

@@ -149,6 +149,19 @@ void launch_lama_pack_input(const float* img, const float* mask, int N, int H, i
 void launch_lama_blend(const View& pred, const float* img, const float* mask, float* out, cudaStream_t st);
 void launch_lama_pack_u8(const uint8_t* img, const uint8_t* mask, int H, int W, const View& dst, float* maskf, cudaStream_t st);
 void launch_lama_blend_u8(const View& pred, const uint8_t* img, const uint8_t* mask, uint8_t* out, int composite, cudaStream_t st);
+// maskrefine.cu: mask refinement: cv2-exact uint8 bilinear resize, rectangle cuts, connected components with stats,
+// the batched DenseCRF of refine_mask, per-line ellipse dilation
+void launch_resize_linear_u8(const uint8_t* src, int sh, int sw, int cn, uint8_t* dst, int dh, int dw, int binarize, cudaStream_t st);
+void launch_cut_rects(uint8_t* mask, int h, int w, const int* rects, int n, cudaStream_t st);
+void launch_cc_label(const uint8_t* mask, int h, int w, int* labels, int* stats, int* ncomp, int cap, int* scratch, cudaStream_t st);
+void launch_owner_map(const int* labels, const int* owner, int n, int* omap, cudaStream_t st);
+size_t crf_workspace_bytes(long npix, long nslots2, long nslots5);
+void launch_crf(const int* lines2, const int* lines5, int nlines, const uint8_t* img, const int* omap, int img_w, int max_pix, int max_cap2, int max_cap5,
+                long npix, long nslots2, long nslots5, int iters, float sxy_g, float w_g, float sxy_b, float srgb, float w_b, float u_on, void* work,
+                uint8_t* refined, int* err, cudaStream_t st);
+void launch_dilate_lines(const int* lines, int nlines, int max_pix2, const int* omap, const uint8_t* refined, const uint8_t* se, int img_w,
+                         uint8_t* final_mask, cudaStream_t st);
+void launch_dilate_se(const uint8_t* src, int h, int w, const uint8_t* se, int ksize, uint8_t* dst, cudaStream_t st);
 // warp.cu: perspective crops of text lines into the OCR chunk canvas (cv2.warpPerspective + rotate, bit-exact) and greedy CTC collapse
 void launch_warp_lines(const uint8_t* page, int H, int W, const double* lines /*[n][16]*/, int n, uint8_t* canvas, int canvas_h, int canvas_w,
                        cudaStream_t st);

@@ -92,96 +92,131 @@ void launch_layernorm(const View& in, const View& out, const float* w, const flo
 // output pixels of one row; the C/4 threads with the same threadIdx.y jointly normalise those 8 pixels.
 constexpr int DW_TX = 8;
 
-__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* in, int in_cs, int in_coff, float* out, int out_cs,
-                                                         int out_coff, const float* wdw, const float* bdw, const float* lnw,
-                                                         const float* lnb, float eps, int N, int H, int W, int C, uint16_t* o_hi,
-                                                         uint16_t* o_mid) {
+// ncu (r02, C = 512): the first version of this kernel was bound by instruction issue, not by memory - 31 M warp instructions
+// for 9.6 M warp-FMAs: 64-bit address arithmetic and a bounds predicate per input pixel, scalar FMAs.  This version keeps the same
+// tiling (same summation order per output: bias, then taps in (dy, dx) order) but runs the taps on the packed fp32x2 pipe (two
+// channels per instruction), addresses the input with 32-bit element offsets from one base pointer, and takes a predicate-free
+// path for tiles that do not touch the left / right image border (CTA-uniform).
+__device__ __forceinline__ void dw_taps(float2 (&acc)[DW_TX][2], const float4 v, const float2 (&wv)[7][2], int j) {
+  const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+#pragma unroll
+  for (int dx = 0; dx < 7; ++dx) {
+    const int i = j - dx;                    // output pixel fed by input pixel j through tap dx (resolved at compile time)
+    if (i >= 0 && i < DW_TX) {
+      acc[i][0] = __ffma2_rn(lo, wv[dx][0], acc[i][0]);
+      acc[i][1] = __ffma2_rn(hi, wv[dx][1], acc[i][1]);
+    }
+  }
+}
+
+template <int WROW>                  // warps per pixel row = C / 128
+__global__ void __launch_bounds__(256, 2) dwconv7_ln_kernel(const float* __restrict__ in, int in_cs, int in_coff, float* __restrict__ out,
+                                                            int out_cs, int out_coff, const float* __restrict__ wdw,
+                                                            const float* __restrict__ bdw, const float* __restrict__ lnw,
+                                                            const float* __restrict__ lnb, float eps, int N, int H, int W, int C,
+                                                            uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_mid) {
   extern __shared__ float red[];                 // [PY][nwarps_per_row][DW_TX]
   const int c = threadIdx.x * 4;
   const int xt = blockIdx.x * DW_TX;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int n = blockIdx.z;
   const bool row_ok = y < H;
-  float4 acc[DW_TX];
-  const float4 bias = *reinterpret_cast<const float4*>(bdw + c);
+  float2 acc[DW_TX][2];
+  {
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(bdw + c));
 #pragma unroll
-  for (int i = 0; i < DW_TX; ++i) acc[i] = bias;
+    for (int i = 0; i < DW_TX; ++i) { acc[i][0] = make_float2(bias.x, bias.y); acc[i][1] = make_float2(bias.z, bias.w); }
+  }
   if (row_ok) {
+    const bool interior = xt >= 3 && xt + DW_TX + 3 <= W;      // CTA-uniform: no input pixel of this tile is left / right of the image
+    const unsigned ucs = (unsigned)in_cs;
     for (int dy = 0; dy < 7; ++dy) {
       const int iy = y + dy - 3;
       if (iy < 0 || iy >= H) continue;
-      float4 wv[7];
+      float2 wv[7][2];
 #pragma unroll
-      for (int dx = 0; dx < 7; ++dx) wv[dx] = __ldg(reinterpret_cast<const float4*>(wdw + (size_t)(dy * 7 + dx) * C + c));
-      const float* rowp = in + ((size_t)(n * H + iy) * W) * in_cs + in_coff + c;
+      for (int dx = 0; dx < 7; ++dx) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wdw + (unsigned)(dy * 7 + dx) * (unsigned)C + (unsigned)c));
+        wv[dx][0] = make_float2(w4.x, w4.y); wv[dx][1] = make_float2(w4.z, w4.w);
+      }
+      if (interior) {
+        const float* rowp = in + ((unsigned)((n * H + iy) * W + xt - 3) * ucs + (unsigned)(in_coff + c));       // host checked: < 2^31 elements
 #pragma unroll
-      for (int j = 0; j < DW_TX + 6; ++j) {
-        const int ix = xt + j - 3;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(rowp + (size_t)ix * in_cs));
+        for (int j = 0; j < DW_TX + 6; ++j) dw_taps(acc, __ldg(reinterpret_cast<const float4*>(rowp + (unsigned)j * ucs)), wv, j);
+      } else {
+        const float* rowp = in + ((unsigned)((n * H + iy) * W) * ucs + (unsigned)(in_coff + c));
 #pragma unroll
-        for (int dx = 0; dx < 7; ++dx) {
-          const int i = j - dx;                  // output pixel fed by this input through tap dx
-          if (i >= 0 && i < DW_TX) {
-            acc[i].x = fmaf(v.x, wv[dx].x, acc[i].x); acc[i].y = fmaf(v.y, wv[dx].y, acc[i].y);
-            acc[i].z = fmaf(v.z, wv[dx].z, acc[i].z); acc[i].w = fmaf(v.w, wv[dx].w, acc[i].w);
-          }
+        for (int j = 0; j < DW_TX + 6; ++j) {
+          const int ix = xt + j - 3;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(rowp + (unsigned)ix * ucs));
+          dw_taps(acc, v, wv, j);
         }
       }
     }
   }
-  // ---- LayerNorm over C across the threadIdx.x dimension (two-pass)
+  // ---- LayerNorm over C across the threadIdx.x dimension (two-pass: mean, then centred variance).  The eight per-pixel partial
+  // sums of a warp are reduced together by a transposed butterfly (9 shuffles instead of 40): after the xor-16/8/4 steps each lane
+  // holds ONE pixel's partial (pixel = lane bits 4,3,2), two more steps finish it; lanes with (lane & 3) == 0 publish it.
   const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
-  const int wrow = blockDim.x >> 5 ? blockDim.x >> 5 : 1;      // warps per pixel row (C/128), >=1
   const int warp_in_row = threadIdx.x >> 5;
-  float* myred = red + (size_t)threadIdx.y * wrow * DW_TX;
+  float* myred = red + (size_t)threadIdx.y * WROW * DW_TX;
   float mean[DW_TX], rstd[DW_TX];
   for (int pass = 0; pass < 2; ++pass) {
     float part[DW_TX];
 #pragma unroll
     for (int i = 0; i < DW_TX; ++i) {
-      if (pass == 0) part[i] = acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+      if (pass == 0) part[i] = (acc[i][0].x + acc[i][0].y) + (acc[i][1].x + acc[i][1].y);
       else {
-        float a = acc[i].x - mean[i], b = acc[i].y - mean[i], cc = acc[i].z - mean[i], d = acc[i].w - mean[i];
-        part[i] = a * a + b * b + cc * cc + d * d;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
-    }
-    if (blockDim.x >= 32) {
-      __syncthreads();
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < DW_TX; ++i) myred[warp_in_row * DW_TX + i] = part[i];
-      }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < DW_TX; ++i) {
-        float t = 0.f;
-        for (int wv = 0; wv < wrow; ++wv) t += myred[wv * DW_TX + i];
-        part[i] = t;
+        const float a = acc[i][0].x - mean[i], b = acc[i][0].y - mean[i], cc = acc[i][1].x - mean[i], d = acc[i][1].y - mean[i];
+        part[i] = (a * a + b * b) + (cc * cc + d * d);
       }
     }
+    {
+      const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float keep = u16 ? part[i + 4] : part[i], give = u16 ? part[i] : part[i + 4];
+        part[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float keep = u8 ? part[i + 2] : part[i], give = u8 ? part[i] : part[i + 2];
+        part[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+      }
+      {
+        const float keep = u4 ? part[1] : part[0], give = u4 ? part[0] : part[1];
+        part[0] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+      }
+      part[0] += __shfl_xor_sync(0xffffffffu, part[0], 2);
+      part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+    }
+    __syncthreads();                                           // (pass 1: everyone has read the pass-0 totals)
+    if ((lane & 3) == 0) myred[warp_in_row * DW_TX + (lane >> 2)] = part[0];      // pixel index = (bit4, bit3, bit2) = lane >> 2
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < DW_TX; ++i) {
-      if (pass == 0) mean[i] = part[i] / C; else rstd[i] = rsqrtf(part[i] / C + eps);
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < WROW; ++wv) t += myred[wv * DW_TX + i];
+      if (pass == 0) mean[i] = t / C; else rstd[i] = rsqrtf(t / C + eps);
     }
   }
   if (!row_ok) return;
-  const float4 g = *reinterpret_cast<const float4*>(lnw + c), be = *reinterpret_cast<const float4*>(lnb + c);
-  float* orow = out + ((size_t)(n * H + y) * W) * out_cs + out_coff + c;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(lnw + c)), be = __ldg(reinterpret_cast<const float4*>(lnb + c));
+  const unsigned opix0 = (unsigned)((n * H + y) * W);
 #pragma unroll
   for (int i = 0; i < DW_TX; ++i) {
     const int x = xt + i;
     if (x < W) {
       float4 r;
-      r.x = (acc[i].x - mean[i]) * rstd[i] * g.x + be.x; r.y = (acc[i].y - mean[i]) * rstd[i] * g.y + be.y;
-      r.z = (acc[i].z - mean[i]) * rstd[i] * g.z + be.z; r.w = (acc[i].w - mean[i]) * rstd[i] * g.w + be.w;
+      r.x = (acc[i][0].x - mean[i]) * rstd[i] * g.x + be.x; r.y = (acc[i][0].y - mean[i]) * rstd[i] * g.y + be.y;
+      r.z = (acc[i][1].x - mean[i]) * rstd[i] * g.z + be.z; r.w = (acc[i][1].y - mean[i]) * rstd[i] * g.w + be.w;
       if (o_hi) {                       // the only consumer is the fc1 GEMM: store its bf16 hi / mid operands, dense [pixel][C]
         uint2 hh, mm; split4_bf16(r, hh, mm);
-        const size_t o = ((size_t)(n * H + y) * W + x) * C + c;
+        const unsigned o = (opix0 + (unsigned)x) * (unsigned)C + (unsigned)c;
         *reinterpret_cast<uint2*>(o_hi + o) = hh; *reinterpret_cast<uint2*>(o_mid + o) = mm;
-      } else *reinterpret_cast<float4*>(orow + (size_t)x * out_cs) = r;
+      } else *reinterpret_cast<float4*>(out + ((opix0 + (unsigned)x) * (unsigned)out_cs + (unsigned)(out_coff + c))) = r;
     }
   }
 }
@@ -196,13 +231,23 @@ void launch_dwconv7_ln(const View& in, const View& out, const float* wdw, const 
   }
   MITB_CHECK(C % 128 == 0 && C <= 1024, "dwconv7_ln: C=%d must be a multiple of 128 (<=1024)", C);
   MITB_CHECK(in.cs % 4 == 0 && in.coff % 4 == 0 && out.cs % 4 == 0 && out.coff % 4 == 0, "dwconv7_ln alignment");
+  MITB_CHECK((size_t)in.pixels() * (size_t)(in.cs > out.cs ? in.cs : out.cs) < ((size_t)1 << 31) && (size_t)in.pixels() * C < ((size_t)1 << 31),
+             "dwconv7_ln: tensor too large for 32-bit element offsets");
   ProfScope ps("dwconv7_ln", (98.0 + 8.0) * in.pixels() * C, 8.0 * in.pixels() * C + 4.0 * 51 * C, st);
   const int tx = C / 4;
   int py = 256 / tx; if (py < 1) py = 1;
   dim3 block(tx, py), grid((in.W + DW_TX - 1) / DW_TX, (in.H + py - 1) / py, in.N);
   const size_t smem = (size_t)py * (tx / 32) * DW_TX * sizeof(float);
-  dwconv7_ln_kernel<<<grid, block, smem, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, wdw, bdw, lnw, lnb, eps,
-                                               in.N, in.H, in.W, C, ohi, omid);
+#define DW_CASE(R) dwconv7_ln_kernel<R><<<grid, block, smem, st>>>(in.p, in.cs, in.coff, out.p, out.cs, out.coff, wdw, bdw, lnw, lnb, eps, \
+                                                                   in.N, in.H, in.W, C, ohi, omid)
+  switch (tx / 32) {
+    case 1: DW_CASE(1); break;
+    case 2: DW_CASE(2); break;
+    case 4: DW_CASE(4); break;
+    case 8: DW_CASE(8); break;
+    default: MITB_CHECK(false, "dwconv7_ln: C=%d (supported: 128, 256, 512, 1024)", C);
+  }
+#undef DW_CASE
   LAUNCH_END();
 }
 

@@ -23,7 +23,7 @@ class MitbError(RuntimeError):
 _lib = None
 
 # name -> (restype, argtypes); mirrors include/mitb.h one to one (checked by tests/test_host.py::test_abi_header_and_library_agree)
-P, I, F = C.c_void_p, C.c_int, C.c_float
+P, I, F, LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "mitb_create": (I, [I, C.POINTER(P)]),
     "mitb_destroy": (None, [P]),
@@ -62,6 +62,14 @@ SIGNATURES = {
     "mitb_op_bilateral17": (I, [P, P, I, I, P, P]),
     "mitb_op_warp_lines_u8": (I, [P, P, I, I, P, I, P, I, I, P]),
     "mitb_op_ctc_collapse": (I, [P, P, P, P, I, I, P, P, P, P, P, P]),
+    "mitb_op_resize_linear_u8": (I, [P, P, I, I, I, P, I, I, I, P]),
+    "mitb_op_cut_rects": (I, [P, P, I, I, P, I, P]),
+    "mitb_op_cc_label": (I, [P, P, I, I, P, P, P, I, P, P]),
+    "mitb_op_owner_map": (I, [P, P, P, I, P, P]),
+    "mitb_op_crf_workspace": (I, [LL, LL, LL, C.POINTER(C.c_ulonglong)]),
+    "mitb_op_dense_crf": (I, [P, P, P, I, P, P, I, I, I, I, LL, LL, LL, I, F, F, F, F, F, F, P, P, P, P]),
+    "mitb_op_dilate_lines": (I, [P, P, I, I, P, P, P, I, P, P]),
+    "mitb_op_dilate_se": (I, [P, P, I, I, P, I, P, P]),
 }
 
 
