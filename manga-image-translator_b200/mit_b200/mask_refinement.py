@@ -176,14 +176,16 @@ class MaskRefiner:
         polys = [np.asarray(q.pts, dtype=np.float64) for q in lines]
         fonts = [float(q.font_size) for q in lines]
         boxes = np.array([[q.aabb.x, q.aabb.y, q.aabb.w, q.aabb.h] for q in lines], dtype=np.float64).astype(np.int32)   # BBox.xywh: int32 truncation
-        eng._call(lib.mitb_op_cut_rects, _ptr(mask_d), h, w, _ptr(self._dev(boxes)), len(boxes), eng._stream())
+        boxes_d = self._dev(boxes)                      # (device temporaries stay referenced until their launch is enqueued)
+        eng._call(lib.mitb_op_cut_rects, _ptr(mask_d), h, w, _ptr(boxes_d), len(boxes), eng._stream())
         labels, stats = self.components(mask_d)
         owner = assign_components(stats, polys, fonts, keep_threshold)
         if not (owner >= 0).any():
             return np.zeros(raw_image_hw, np.uint8)
         n = h * w
         omap = torch.empty((n,), dtype=torch.int32, device=img_d.device)
-        eng._call(lib.mitb_op_owner_map, _ptr(labels), _ptr(self._dev(owner)), n, _ptr(omap), eng._stream())
+        owner_d = self._dev(owner)
+        eng._call(lib.mitb_op_owner_map, _ptr(labels), _ptr(owner_d), n, _ptr(omap), eng._stream())
         # per line: union rectangle of its components -> CRF region (rect1) and dilation region (rect2)
         crf2, crf5, dil, ses, se_off = [], [], [], [], {}
         pix0 = slot2 = slot5 = 0
@@ -222,14 +224,15 @@ class MaskRefiner:
         refined = torch.empty((pix0,), dtype=torch.uint8, device=img_d.device)
         err = torch.zeros((1,), dtype=torch.int32, device=img_d.device)
         omap_hw = omap
-        eng._call(lib.mitb_op_dense_crf, _ptr(self._dev(a2)), _ptr(self._dev(a5)), nl, _ptr(filt), _ptr(omap_hw), w, int((a2[:, 2] * a2[:, 3]).max()),
+        a2_d, a5_d, ad_d, se_d, se3_d = self._dev(a2), self._dev(a5), self._dev(ad), self._dev(np.concatenate(ses)), self._dev(self._ellipse(kernel_size))
+        eng._call(lib.mitb_op_dense_crf, _ptr(a2_d), _ptr(a5_d), nl, _ptr(filt), _ptr(omap_hw), w, int((a2[:, 2] * a2[:, 3]).max()),
                   int(a2[:, 6].max()), int(a5[:, 6].max()), pix0, slot2, slot5, CRF_ITERS, SXY_G, W_G, SXY_B, SRGB, W_B, U_ON, _ptr(work), _ptr(refined),
                   _ptr(err), eng._stream())
         final = torch.zeros((h, w), dtype=torch.uint8, device=img_d.device)
-        eng._call(lib.mitb_op_dilate_lines, _ptr(self._dev(ad)), nl, int((ad[:, 6] * ad[:, 7]).max()), _ptr(omap_hw), _ptr(refined),
-                  _ptr(self._dev(np.concatenate(ses))), w, _ptr(final), eng._stream())
+        eng._call(lib.mitb_op_dilate_lines, _ptr(ad_d), nl, int((ad[:, 6] * ad[:, 7]).max()), _ptr(omap_hw), _ptr(refined), _ptr(se_d), w, _ptr(final),
+                  eng._stream())
         final2 = torch.empty_like(final)
-        eng._call(lib.mitb_op_dilate_se, _ptr(final), h, w, _ptr(self._dev(self._ellipse(kernel_size))), kernel_size, _ptr(final2), eng._stream())
+        eng._call(lib.mitb_op_dilate_se, _ptr(final), h, w, _ptr(se3_d), kernel_size, _ptr(final2), eng._stream())
         out = self.resize(final2, W, H, binarize=True)
         code = int(eng.d2h(err)[0])
         if code:
