@@ -83,34 +83,51 @@ def _point_distance(poly: np.ndarray, px: float, py: float) -> float:
 
 def assign_components(stats: np.ndarray, polys: List[np.ndarray], font_sizes: List[float], keep_threshold: float = 1e-2) -> np.ndarray:
     """complete_mask's decision per component (text_mask_utils.py:110-160): stats int [n][5] = x0, y0, x1, y1 (inclusive), area ->
-    owner line per component (-1: dropped).  Lines whose bounding box misses the component's rectangle overlap it by exactly 0, so
-    only the intersecting ones are clipped; distances are evaluated only when no line overlaps enough."""
+    owner line per component (-1: dropped).  Vectorised over (component, line) pairs: a component rectangle that lies inside a
+    (convex) line quad overlaps it by exactly its own area, a rectangle that misses the quad's bounding box by exactly 0; only
+    the partially overlapping pairs are clipped (Sutherland-Hodgman), and distances are evaluated only for components that no
+    line overlaps enough - a few per page."""
     M = len(polys)
     owner = np.full(len(stats), -1, np.int32)
     if M == 0 or len(stats) == 0:
         return owner
+    st = np.asarray(stats, dtype=np.int64)
+    big = np.nonzero(st[:, 4] > 9)[0]
+    if len(big) == 0:
+        return owner
+    x0, y0 = st[big, 0].astype(np.float64), st[big, 1].astype(np.float64)
+    w1, h1 = (st[big, 2] - st[big, 0] + 1).astype(np.float64), (st[big, 3] - st[big, 1] + 1).astype(np.float64)
+    x1, y1, area1 = x0 + w1, y0 + h1, st[big, 4].astype(np.float64)      # cc_pts = (x, y) .. (x + w, y + h) in the reference
+    P = np.stack(polys).astype(np.float64)                                  # [M,4,2]
     areas = np.array([_poly_area(p) for p in polys])
-    pmin = np.array([p.min(0) for p in polys])
-    pmax = np.array([p.max(0) for p in polys])
-    for k, (x0, y0, x1i, y1i, area1) in enumerate(stats.tolist()):
-        if area1 <= 9:
-            continue
-        w1, h1 = x1i - x0 + 1, y1i - y0 + 1
-        x1, y1 = x0 + w1, y0 + h1                                    # cc_pts = (x1, y1) .. (x1 + w1, y1 + h1) in the reference's names
-        ratio = np.zeros(M, np.float32)
-        for t in np.nonzero((pmin[:, 0] < x1) & (pmax[:, 0] > x0) & (pmin[:, 1] < y1) & (pmax[:, 1] > y0))[0]:
-            ratio[t] = _overlap_area(polys[t], x0, y0, x1, y1) / min(area1, areas[t])
-        avg = int(np.argmax(ratio))
-        if area1 >= areas[avg]:
-            continue
-        if ratio[avg] <= keep_threshold:
-            cx, cy = x0 + w1 / 2.0, y0 + h1 / 2.0
-            dist = np.array([_point_distance(p, cx, cy) for p in polys], dtype=np.float32)
-            avg = int(np.argmin(dist))
-            unit = max(min([font_sizes[avg], w1, h1]), 10)
-            if dist[avg] >= 0.5 * unit:
-                continue
-        owner[k] = avg
+    pmin, pmax = P.min(1), P.max(1)
+    touch = (pmin[None, :, 0] < x1[:, None]) & (pmax[None, :, 0] > x0[:, None]) & (pmin[None, :, 1] < y1[:, None]) & (pmax[None, :, 1] > y0[:, None])
+    E = np.roll(P, -1, axis=1) - P                                          # [M,4 edges,2]
+    En = np.roll(E, -1, axis=1)
+    turn = E[:, :, 0] * En[:, :, 1] - E[:, :, 1] * En[:, :, 0]
+    convex = (turn >= 0).all(1) | (turn <= 0).all(1)
+    kk, tt = np.nonzero(touch)                                              # the (component, line) pairs whose boxes intersect
+    corners = np.stack([np.stack([x0, y0], 1), np.stack([x1, y0], 1), np.stack([x1, y1], 1), np.stack([x0, y1], 1)], 1)[kk]     # [p,4,2]
+    rel = corners[:, :, None, :] - P[tt][:, None, :, :]                     # [p,4 corners,4 edges,2]
+    cross = E[tt][:, None, :, 0] * rel[..., 1] - E[tt][:, None, :, 1] * rel[..., 0]
+    inside = ((cross >= 0).all(axis=(1, 2)) | (cross <= 0).all(axis=(1, 2))) & convex[tt]      # every corner on the inner side of every edge
+    ratio = np.zeros((len(big), M), np.float32)
+    denom = np.minimum(area1[:, None], areas[None, :])
+    ratio[kk[inside], tt[inside]] = ((w1 * h1)[kk[inside]] / denom[kk[inside], tt[inside]])
+    for k, t in zip(kk[~inside], tt[~inside]):
+        ratio[k, t] = _overlap_area(polys[t], x0[k], y0[k], x1[k], y1[k]) / denom[k, t]
+    avg = ratio.argmax(1)
+    keep = area1 < areas[avg]
+    weak = keep & (ratio[np.arange(len(big)), avg] <= keep_threshold)
+    for k in np.nonzero(weak)[0]:
+        cx, cy = x0[k] + w1[k] / 2.0, y0[k] + h1[k] / 2.0
+        dist = np.array([_point_distance(p, cx, cy) for p in polys], dtype=np.float32)
+        a = int(np.argmin(dist))
+        unit = max(min([font_sizes[a], w1[k], h1[k]]), 10)
+        if dist[a] >= 0.5 * unit:
+            keep[k] = False
+        avg[k] = a
+    owner[big[keep]] = avg[keep]
     return owner
 
 

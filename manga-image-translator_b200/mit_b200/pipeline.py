@@ -78,6 +78,23 @@ class HotPath:
             out = asyncio.run(self.inp.infer(page, mask, InpainterConfig(), self.inpainting_size))
         return PageResult(textlines, raw_mask, lines, out)
 
+    def process_page_chain(self, page: np.ndarray, ocr_prob: float = 0.0, dilation_offset: int = 20, kernel_size: int = 3):
+        """The reference's own stage order for one page, every stage on the GPU path (manga_translator.py:431-600): detect ->
+        OCR of the DETECTED lines -> text-line merge (host) -> mask refinement (8f N1) -> inpaint with the REFINED
+        mask.  Returns (text regions, refined mask uint8 [H,W], inpainted page uint8 [H,W,3]).  `process_page` above is the
+        benchmark workload instead (fixed synthetic quads and mask, detector output not fed forward)."""
+        from . import mask_refinement
+        from .host import textline_merge
+        textlines, raw_mask, _ = asyncio.run(self.det.infer(page, self.detect_size, 0.5, 0.7, 2.3))
+        lines = asyncio.run(self.ocr.infer(page, textlines, OcrConfig(prob=ocr_prob))) if textlines else []
+        regions = textline_merge.dispatch(lines, page.shape[1], page.shape[0]) if lines else []
+        if not regions:
+            return [], np.zeros(page.shape[:2], np.uint8), page.copy()
+        mask = asyncio.run(mask_refinement.dispatch(regions, page, raw_mask, "fit_text", dilation_offset, 0, False, kernel_size,
+                                                    device=str(self.engine.device)))
+        out = asyncio.run(self.inp.infer(page, mask, InpainterConfig(), self.inpainting_size))
+        return regions, mask, out
+
     def process_pages(self, items, workers: int = 4, keep_on_device: bool = False) -> List[PageResult]:
         """A batch of (page, quads, mask) through the same three ``infer`` calls per page, with `workers` host threads so one
         page's host work (H2D/D2H, contours, crops, CTC collapse) overlaps other pages' kernels.  GPU submissions are

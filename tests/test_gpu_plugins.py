@@ -111,3 +111,42 @@ def test_inpainter_plugin_matches_cpu_reference_path(large):
     assert np.array_equal(page, page0) and np.array_equal(mask, mask0)   # inputs are borrowed, never mutated
     run(inp.unload())
     cls.set_state_dict(None)
+
+
+def test_full_chain_detect_ocr_merge_refine_inpaint():
+    """HotPath.process_page_chain: the reference's stage order with every stage on the GPU path.  The stages have their own parity tests;
+    this one checks the glue: the refined mask equals the oracle's mask refinement of the same detector / OCR outputs, and the page
+    is inpainted under exactly that mask."""
+    import cv2
+    from mit_b200.host import geometry, textline_merge
+    from mit_b200.pipeline import HotPath
+    from oracle import cases, mask_refine_ref
+    sd = {k: v.clone() for k, v in weights.dbnet_weights().items()}
+    sd["conv_db.binarize.4.bias"] -= 1.0
+    dictionary = weights.synthetic_dictionary(cases.OCR_VOCAB_SMALL)
+    hp = HotPath("cuda:0", sd, weights.ocr_weights(cases.OCR_VOCAB_SMALL), dictionary, weights.lama_weights(9), weights.mpe_weights(),
+                 detect_size=512, inpainting_size=512)
+    try:
+        page = synth.make_page(5, 512, 384, 6)[0]
+        regions, mask, out = hp.process_page_chain(page)
+        assert len(regions) > 0 and mask.shape == page.shape[:2] and mask.dtype == np.uint8 and out.shape == page.shape
+        # replay: same detector / OCR calls, then the CPU restatement of the reference's mask refinement
+        textlines, raw_mask, _ = run(hp.det.infer(page, 512, 0.5, 0.7, 2.3))
+        lines = run(hp.ocr.infer(page, textlines, OcrConfig(prob=0.0)))
+        regs = textline_merge.dispatch(lines, page.shape[1], page.shape[0])
+        assert [r.line_indices for r in regs] == [r.line_indices for r in regions]
+        ipp = cv2.ipp.useIPP()
+        cv2.ipp.setUseIPP(False)
+        try:
+            want = mask_refine_ref.dispatch(regs, page, raw_mask.copy(), geometry.Quadrilateral, dilation_offset=20, kernel_size=3)
+        finally:
+            cv2.ipp.setUseIPP(ipp)
+        inter, union = ((mask > 0) & (want > 0)).sum(), ((mask > 0) | (want > 0)).sum()
+        print(f"chain: {len(textlines)} lines detected, {len(lines)} read, {len(regions)} regions, refined mask covers {100.0 * (mask > 0).mean():.1f} %, "
+              f"IoU vs oracle {inter / max(1, union):.6f}")
+        assert union > 0 and inter / union >= 0.999
+        again = run(hp.inp.infer(page, mask, InpainterConfig(), 512))
+        assert np.array_equal(again, out)
+        assert (out[mask == 0] == page[mask == 0]).all()                 # pixels outside the mask are the original page
+    finally:
+        hp.close()
