@@ -415,7 +415,96 @@ __global__ void attention_kernel(const float* qk, const float* v, float* out, in
   }
 }
 
+// head_dim = 40 (the OCR encoder, model_48px_ctc.py:432): same decomposition, restructured for instruction count - the generic kernel
+// above spends two shared-memory loads per FMA.  K / V rows are padded to 44 floats so that a row is ten aligned LDS.128 (conflict
+// free per quarter warp), q lives in registers, the dot products and the P.V accumulation run on the packed fp32x2 pipe, and P.V is
+// split over the keys (each lane accumulates its own keys into 40 registers, the 32 partial vectors are summed through shared memory).
+constexpr int AT_HD = 40, AT_LD = 44;
+__global__ void __launch_bounds__(256) attention40_kernel(const float* __restrict__ qk, const float* __restrict__ v, float* __restrict__ out, int T,
+                                                          int heads, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int D = heads * AT_HD;
+  const int n = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Ks = sm; float* Vs = Ks + (size_t)T * AT_LD;
+  float* Ps = Vs + (size_t)T * AT_LD;                       // [nw][T]
+  float* Ob = Ps + (((size_t)nw * T + 3) & ~(size_t)3);     // [nw][32][AT_LD] partial outputs
+  for (int i = threadIdx.x; i < T * (AT_HD / 4); i += blockDim.x) {
+    const int t = i / (AT_HD / 4), d4 = i % (AT_HD / 4);
+    *reinterpret_cast<float4*>(Ks + t * AT_LD + 4 * d4) = __ldg(reinterpret_cast<const float4*>(qk + ((size_t)n * T + t) * 2 * D + D + h * AT_HD) + d4);
+    *reinterpret_cast<float4*>(Vs + t * AT_LD + 4 * d4) = __ldg(reinterpret_cast<const float4*>(v + ((size_t)n * T + t) * D + h * AT_HD) + d4);
+  }
+  __syncthreads();
+  float* P = Ps + (size_t)warp * T;
+  float* O = Ob + (size_t)warp * 32 * AT_LD;
+  for (int t = blockIdx.y * nw + warp; t < T; t += nw * gridDim.y) {
+    float2 q[AT_HD / 2];
+    {
+      const float4* qp = reinterpret_cast<const float4*>(qk + ((size_t)n * T + t) * 2 * D + h * AT_HD);
+#pragma unroll
+      for (int i = 0; i < AT_HD / 4; ++i) { const float4 a = __ldg(qp + i); q[2 * i] = make_float2(a.x, a.y); q[2 * i + 1] = make_float2(a.z, a.w); }
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + j * AT_LD);
+      float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < AT_HD / 4; ++i) {
+        const float4 a = kr[i];
+        s2 = __ffma2_rn(q[2 * i], make_float2(a.x, a.y), s2);
+        s2 = __ffma2_rn(q[2 * i + 1], make_float2(a.z, a.w), s2);
+      }
+      const float s = (s2.x + s2.y) * scale;
+      P[j] = s; mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    float2 acc[AT_HD / 2];
+#pragma unroll
+    for (int i = 0; i < AT_HD / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int j = lane; j < T; j += 32) {                       // this lane's keys: it wrote P[j] itself, no exchange needed yet
+      const float e = expf(P[j] - mx);
+      sum += e;
+      const float4* vr = reinterpret_cast<const float4*>(Vs + j * AT_LD);
+#pragma unroll
+      for (int i = 0; i < AT_HD / 4; ++i) {
+        const float4 a = vr[i];
+        acc[2 * i] = __ffma2_rn(make_float2(e, e), make_float2(a.x, a.y), acc[2 * i]);
+        acc[2 * i + 1] = __ffma2_rn(make_float2(e, e), make_float2(a.z, a.w), acc[2 * i + 1]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+    for (int i = 0; i < AT_HD / 4; ++i)
+      *reinterpret_cast<float4*>(O + lane * AT_LD + 4 * i) = make_float4(acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int d = lane; d < AT_HD; d += 32) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) a += O[l * AT_LD + d];
+      out[((size_t)n * T + t) * D + h * AT_HD + d] = a * inv;
+    }
+    __syncwarp();
+  }
+}
+
 void launch_attention(const float* qk, const float* v, float* out, int N, int T, int heads, int hd, cudaStream_t st) {
+  if (hd == AT_HD && (((uintptr_t)qk | (uintptr_t)v) & 15) == 0) {
+    const int threads = 256, nw = threads / 32;
+    const size_t smem = ((size_t)2 * T * AT_LD + (((size_t)nw * T + 3) & ~(size_t)3) + (size_t)nw * 32 * AT_LD) * sizeof(float);
+    if (smem <= 200 * 1024) {
+      static PerDeviceOnce attr40;
+      if (attr40.first()) CUDA_OK(cudaFuncSetAttribute(attention40_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ProfScope ps("attention", 4.0 * N * heads * (double)T * T * hd, 16.0 * N * T * heads * hd, st);
+      int rb = (T + 31) / 32; if (rb > 6) rb = 6; if (rb < 1) rb = 1;
+      attention40_kernel<<<dim3(N * heads, rb), threads, smem, st>>>(qk, v, out, T, heads, 1.0f / sqrtf((float)hd));
+      LAUNCH_END();
+      return;
+    }
+  }
   const int threads = 256;
   const size_t smem = ((size_t)2 * T * (hd + 1) + (size_t)(threads / 32) * T + (size_t)(threads / 32) * hd) * sizeof(float);
   MITB_CHECK(smem <= 200 * 1024, "attention: sequence too long (T=%d)", T);

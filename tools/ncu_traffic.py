@@ -23,7 +23,8 @@ CLASSES = (  # first match wins; conv_tc = every kernel a dense conv op launches
     ("fft", ("rfft_rows", "irfft_rows", "fft_cols")),
     ("dwconv7_ln", ("dwconv7_ln_kernel",)),
     ("layernorm", ("layernorm_kernel",)),
-    ("attention", ("attention_kernel",)),
+    ("attention", ("attention_kernel", "attention40_kernel")),
+    ("ocr_crops_ctc", ("warp_lines_kernel", "ctc_collapse_kernel")),
     ("bilateral", ("bilateral17_kernel",)),
     ("convT4_c1", ("convT4_c1_kernel",)),
 )
