@@ -326,6 +326,27 @@ class _FakeEngine:
         self.calls.append(("ocr", region.shape))
         return pred, logprob, colors
 
+    def warp_lines(self, page, records, canvas_w, canvas_h=48):
+        """Host stand-in for mitb_op_warp_lines_u8: the numpy restatement of the kernel's arithmetic."""
+        import numpy as np
+        from oracle import warp_ref
+        self.calls.append(("warp", len(records), canvas_w))
+        return np.stack([warp_ref.warp_line_record(np.asarray(page), r, canvas_w, canvas_h) for r in np.asarray(records)])
+
+    def ctc_collapse(self, pred, logprob, colors):
+        """Host stand-in for mitb_op_ctc_collapse (kept steps compacted to the front of each row)."""
+        import numpy as np
+        from mit_b200 import plugins
+        n, T = pred.shape
+        counts = np.zeros(n, np.int32)
+        steps, chars = np.zeros((n, T), np.int32), np.zeros((n, T), np.int32)
+        lp, col = np.zeros((n, T), np.float32), np.zeros((n, T, 6), np.float32)
+        for i, st in enumerate(plugins.ctc_collapse(pred)):
+            k = len(st)
+            counts[i] = k
+            steps[i, :k], chars[i, :k], lp[i, :k], col[i, :k] = st, pred[i, st], logprob[i, st], colors[i, st]
+        return counts, steps, chars, lp, col
+
     def mpe_tables_256(self, small):
         import numpy as np
         assert small.shape == (256, 256) and small.dtype == np.uint8
@@ -357,6 +378,15 @@ def test_plugin_host_logic_with_a_fake_engine():
     steps = plugins.ctc_collapse(pred)[0]
     want_prob = np.exp(np.mean([float(v) for v in logprob[0, steps]]))
     assert any(abs(q.prob - want_prob) < 1e-12 for q in out)
+    assert ocr.engine.calls[0][0] == "warp"                                          # default path: crops cut on the "device"
+    # ... and the reference's own host sequence (cv2 crops) produces the same chunk canvas, hence the same lines
+    os.environ["MITB_HOST_CROPS"] = "1"
+    try:
+        ocr.engine = _FakeEngine()
+        out2 = asyncio.run(ocr._infer(page, synth.make_quads(boxes), OcrConfig(), False))
+    finally:
+        del os.environ["MITB_HOST_CROPS"]
+    assert all(c[0] != "warp" for c in ocr.engine.calls) and [(q.text, q.prob) for q in out2] == [(q.text, q.prob) for q in out]
 
     inp = plugins.LamaMPEInpainter.__new__(plugins.LamaMPEInpainter)
     plugins.LamaMPEInpainter.__init__(inp)
