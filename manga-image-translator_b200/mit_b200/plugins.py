@@ -313,8 +313,10 @@ class LamaLargeInpainter(LamaMPEInpainter):
 
 
 # ----------------------------------------------------------------------------------------------- registration
-def register():
-    """Replace the reference registry entries with the B200 plugins (needs the real manga_translator package)."""
+def register(mask_refinement: bool = False):
+    """Replace the reference registry entries with the B200 plugins (needs the real manga_translator package).  With
+    `mask_refinement=True` also rebind `manga_translator.manga_translator.dispatch_mask_refinement` (manga_translator.py:34, called at
+    :1356-1358) to the GPU stage of `mit_b200.mask_refinement` - same signature."""
     if not compat.HAVE_REFERENCE:
         raise MitbError("register() needs an importable manga_translator package; see INTEGRATION.md")
     from manga_translator import detection, inpainting, ocr  # type: ignore
@@ -327,3 +329,7 @@ def register():
     ocr.ocr_cache.pop(Ocr.ocr48px_ctc, None)
     inpainting.inpainter_cache.pop(Inpainter.lama_mpe, None)
     inpainting.inpainter_cache.pop(Inpainter.lama_large, None)
+    if mask_refinement:
+        import manga_translator.manga_translator as mt  # type: ignore
+        from . import mask_refinement as mr
+        mt.dispatch_mask_refinement = mr.dispatch

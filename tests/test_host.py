@@ -453,6 +453,17 @@ def test_register_swaps_the_reference_registries(monkeypatch):
         obj = cls()
         with pytest.raises(Exception):
             asyncio.run(obj.infer())                                   # infer before load raises (inference.py:349-350)
+    # mask refinement is a module-level import in the orchestrator (manga_translator.py:34): register(mask_refinement=True) rebinds it
+    orch = types.ModuleType("manga_translator.manga_translator")
+    orch.dispatch_mask_refinement = Old
+    root.manga_translator = orch
+    monkeypatch.setitem(sys.modules, "manga_translator.manga_translator", orch)
+    plugins.register(mask_refinement=True)
+    from mit_b200 import mask_refinement
+    assert orch.dispatch_mask_refinement is mask_refinement.dispatch
+    import inspect
+    assert list(inspect.signature(mask_refinement.dispatch).parameters)[:8] == ["text_regions", "raw_image", "raw_mask", "method", "dilation_offset",
+                                                                                "ignore_bubble", "verbose", "kernel_size"]      # __init__.py:9
     monkeypatch.setattr(compat, "HAVE_REFERENCE", False)
     from mit_b200 import MitbError
     with pytest.raises(MitbError):
