@@ -259,11 +259,20 @@ def csrc_hash():
 def latest_traffic_summary():
     """Newest profiles/r*_ncu_traffic*.json written by tools/ncu_traffic.py (None when absent)."""
     import glob
-    c = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic*.json")))
+    import re
+    c = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic*.json")),
+               key=lambda p: [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(p))])      # natural order: v13 after v5
     if not c:
         return None, None
-    with open(c[-1]) as f:
-        return json.load(f), os.path.basename(c[-1])
+    sha = csrc_hash()
+    docs = []
+    for path in c:
+        with open(path) as f:
+            docs.append((json.load(f), os.path.basename(path)))
+    for doc, name in reversed(docs):                      # the summary measured on exactly these CUDA sources, if there is one
+        if doc.get("csrc_sha") == sha:
+            return doc, name
+    return docs[-1]
 
 
 def roofline_from_profile(prof, peaks, pages_timed):
