@@ -375,6 +375,37 @@ def mask_refine_figure(pages, n_pages):
                         "of pydensecrf's C++ DenseCRF - slower than the real library, a scale reference only"}
 
 
+def c4_figure(hp, n_pages):
+    """lama_large (18 FFC blocks, no MPE) on synthetic 2560x1920 pages: the inpainter's device section (uint8 page + mask in HBM ->
+    inpainted uint8 page), CUDA events, one warm-up page.  The lama_mpe weights of the main workload are unloaded first."""
+    import asyncio
+    from mit_b200 import synth
+    from oracle import weights
+    eng = hp.engine
+    asyncio_run = asyncio.run
+    asyncio_run(hp.inp.unload())
+    eng.load_lama(weights.lama_weights(18))
+    try:
+        staged = []
+        for i in range(n_pages + 1):
+            page, _, mask = synth.make_page(100 + i, 2560, 1920, LINES)
+            staged.append((torch.from_numpy(page).to(eng.device), torch.from_numpy(mask).to(eng.device)))
+        eng.lama_infer_u8(staged[0][0], staged[0][1], None, None, composite=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for pg, mk in staged[1:]:
+            eng.lama_infer_u8(pg, mk, None, None, composite=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_pages
+    finally:
+        eng.unload_lama()
+        asyncio_run(hp.inp.load(hp.device))
+    return {"ms_per_page": ms, "pages_per_s": 1e3 / ms, "pages": n_pages, "what": "lama_large (18 blocks) at 2560x1920, device resident, "
+            "uint8 in / uint8 out incl. pack, blend and composite; bottleneck 320x240x512, FFT 320x240"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from mit_b200 import exchange, synth
@@ -531,6 +562,16 @@ def run_ours(args, rank, world, local_rank):
             log(f"[bench] mask refinement figure unavailable: {ex!r}")
             refine = {"unavailable": repr(ex)}
 
+    # ---------------- BASELINE configs[3] (C4): lama_large at --inpainting-size 2560 on 2560x1920 pages (FFT 320x240), one GPU's share,
+    # device resident like `value`; parity at this size: tests/test_gpu_fullsize.py::test_lama_large_2560x1920
+    c4 = None
+    if rank == 0 and world == 1 and not args.no_c4:
+        try:
+            c4 = c4_figure(hp, 3)
+        except Exception as ex:
+            log(f"[bench] C4 figure unavailable: {ex!r}")
+            c4 = {"unavailable": repr(ex)}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -546,7 +587,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "lama_ffc": lama_ffc, "cpu_baseline": cpu, "gpu_bar": bar,
-            "mask_refinement": refine,
+            "mask_refinement": refine, "c4_lama_large_2560": c4,
         }), flush=True)
     hp.close()
     if world > 1:
@@ -563,6 +604,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-bar", action="store_true")
     ap.add_argument("--no-mask-refine", action="store_true", help="skip the mask-refinement (SURVEY 8f N1) figure")
+    ap.add_argument("--no-c4", action="store_true", help="skip the lama_large @ 2560 (BASELINE configs[3]) figure")
     ap.add_argument("--workers", type=int, default=8, help="host threads of the page pipeline in the e2e leg")
     ap.add_argument("--fast-e2e", action="store_true", help="one warm-up step for the e2e leg (development only)")
     args = ap.parse_args()

@@ -50,6 +50,10 @@ int mitb_set_tensor_cores(int on);
  * channel-vectorised FFT; sizes whose bottleneck h/8, w/8 are {2,3,5}-smooth) when the page is large enough that no layer
  * needs split-K (default), 2 = fused path whenever it is capable (tests). */
 int mitb_set_ffc_mode(int mode);
+/* Process-wide: LaMa's decoder (three transposed convs + the 7x7 output conv) computes only the tiles from which a hole pixel of
+ * the final blend `pred*mask + (1-mask)*img` (inpainting_lama_mpe.py:726) is reachable; every used pixel is bit-identical to the dense
+ * computation (on by default; 0 = dense, also MITB_DENSE_TAIL=1). */
+int mitb_set_sparse_decoder(int on);
 
 /* Per-launch CUDA-event timing aggregated per kernel class (for bench.py's roofline block). report() synchronises the
  * recorded events, clears them and returns a JSON object {"class": {"launches","ms","flops","bytes"}, ...} valid until

@@ -71,6 +71,7 @@ size_t mitb_workspace_bytes(const mitb_ctx* ctx) { return ctx ? ctx->c.ws.cap : 
 
 int mitb_set_tensor_cores(int on) { conv_tc_set_enabled(on != 0); return 0; }
 int mitb_set_ffc_mode(int mode) { lama_set_ffc_mode(mode); return 0; }
+int mitb_set_sparse_decoder(int on) { lama_set_sparse_decoder(on); return 0; }
 
 int mitb_profile_enable(mitb_ctx* ctx, int on) {
   API_BEGIN(ctx)

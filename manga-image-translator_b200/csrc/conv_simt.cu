@@ -465,8 +465,20 @@ void launch_conv(const ConvOp& op, cudaStream_t st) {
   const double flops = 2.0 * p.M * (double)p.K * Cout;
   const double bytes = 4.0 * ((double)op.in.pixels() * op.in.C + (op.seg2.sv.valid() ? (double)op.in.pixels() * op.seg2.C : 0.0) + (double)p.K * Cout +
                               (double)p.M * Cout * ((op.stat_max ? 0 : 1) + (op.add0.p ? 1 : 0) + (op.add1.p ? 1 : 0)));
-  if (conv_thin_supported(op)) { ProfScope ps("conv7_thin", flops, bytes, st, p.M, p.K, Cout); launch_conv_thin(op, st); return; }
-  if (conv_tc_supported(op)) { ProfScope ps(op.stat_max ? "conv_tc_rowstat" : "conv_tc", flops, bytes, st, p.M, p.K, Cout); launch_conv_tc(op, st); return; }
+  if (conv_thin_supported(op)) {
+    // with an output-sparsity hint the executed work depends on the mask (device data): no flop figure is claimed for that class
+    const bool sparse = op.tile_mask || op.tile_mask_u8;
+    ProfScope ps(sparse ? "conv7_thin_sparse" : "conv7_thin", sparse ? 0.0 : flops, sparse ? 0.0 : bytes, st, p.M, p.K, Cout);
+    launch_conv_thin(op, st);
+    return;
+  }
+  if (conv_tc_supported(op)) {
+    // output-sparse launches (ConvOp::need_px): executed work depends on device data, so they form their own class without a flop claim
+    const bool sparse = op.need_px && !op.stat_max;
+    ProfScope ps(op.stat_max ? "conv_tc_rowstat" : sparse ? "conv_tc_sparse" : "conv_tc", sparse ? 0.0 : flops, sparse ? 0.0 : bytes, st, p.M, p.K, Cout);
+    launch_conv_tc(op, st);
+    return;
+  }
   ProfScope ps(op.stat_max ? "conv_simt_rowstat" : (Cout <= 4 && !op.in.planar && op.ldw == 4) ? "conv_fewout" : "conv_simt", flops, bytes, st);
   if (op.stat_max) {
     MITB_CHECK(!op.in.planar, "row-stat epilogue expects NHWC input");

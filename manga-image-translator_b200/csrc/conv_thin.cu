@@ -21,6 +21,8 @@ struct ThinParams {
   const float* w;                                // [tap][Cin][4] (K-major fp32, ldw = 4)
   float* out; int out_cs, out_coff, Cout, out_planar;
   const float* shift; int act, pad;
+  const float* tile_mask;                        // see ConvOp::tile_mask
+  const uint8_t* tile_mask_u8;
 };
 
 __device__ __forceinline__ float act_thin(float v, int act) {
@@ -39,6 +41,39 @@ __global__ void __launch_bounds__(256, 2) conv7_thin_kernel(const ThinParams p) 
   const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH, n = blockIdx.z;
   const int tid = threadIdx.x;
   const int lx = (tid & 15) * 4, ly = tid >> 4;          // this thread's 4 output pixels: (ty0+ly, tx0+lx .. +3)
+  bool warp_active = true;
+  if (p.tile_mask || p.tile_mask_u8) {
+    // Output sparsity: LaMa's result is pred*mask + (1-mask)*img (inpainting_lama_mpe.py:726), so prediction pixels where the mask is 0
+    // are never used.  A tile without a single hole pixel stores zeros (finite, so that pred*0 stays 0) and skips its 12.8 MFLOP.
+    int any = 0;
+    const int oy_ = ty0 + ly;
+    if (oy_ < p.H) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ox_ = tx0 + lx + i;
+        if (ox_ >= p.W) continue;
+        const size_t mi = ((size_t)n * p.H + oy_) * p.W + ox_;
+        if (p.tile_mask ? p.tile_mask[mi] != 0.f : p.tile_mask_u8[mi] >= 128) any = 1;
+      }
+    }
+    warp_active = __any_sync(0xffffffffu, any) != 0;    // a warp = 2 rows x 64 pixels of the tile: skip its FMAs (not its staging) when hole free
+    if (!__syncthreads_or(any)) {
+      if (oy_ < p.H) {
+        const size_t plane_ = (size_t)p.H * p.W;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ox_ = tx0 + lx + i;
+          if (ox_ >= p.W) continue;
+          const size_t pix_ = (size_t)oy_ * p.W + ox_;
+          for (int j = 0; j < p.Cout; ++j) {
+            if (p.out_planar) p.out[((size_t)n * p.out_cs + p.out_coff + j) * plane_ + pix_] = 0.f;
+            else p.out[((size_t)n * plane_ + pix_) * p.out_cs + p.out_coff + j] = 0.f;
+          }
+        }
+      }
+      return;
+    }
+  }
   float2 acc[4][2];                                      // [pixel][output-channel pair]: the taps run on the packed fp32x2 pipe
 #pragma unroll
   for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
@@ -69,6 +104,7 @@ __global__ void __launch_bounds__(256, 2) conv7_thin_kernel(const ThinParams p) 
     }
     __syncthreads();
     // ---- accumulate
+    if (warp_active)
 #pragma unroll 1
     for (int c = 0; c < CCH; ++c) {
 #pragma unroll
@@ -104,6 +140,10 @@ __global__ void __launch_bounds__(256, 2) conv7_thin_kernel(const ThinParams p) 
       const float a = j == 0 ? acc[i][0].x : j == 1 ? acc[i][0].y : j == 2 ? acc[i][1].x : acc[i][1].y;
       float v = a + (p.shift ? p.shift[j] : 0.f);
       v = act_thin(v, p.act);
+      if (p.tile_mask || p.tile_mask_u8) {               // pixels the blend does not use: a finite constant
+        const size_t mi = ((size_t)n * p.H + oy) * p.W + ox;
+        if (!(p.tile_mask ? p.tile_mask[mi] != 0.f : p.tile_mask_u8[mi] >= 128)) v = 0.f;
+      }
       if (p.out_planar) p.out[((size_t)n * p.out_cs + p.out_coff + j) * plane + pix] = v;
       else p.out[((size_t)n * plane + pix) * p.out_cs + p.out_coff + j] = v;
     }
@@ -126,7 +166,7 @@ void launch_conv_thin(const ConvOp& op, cudaStream_t st) {
   ThinParams p;
   p.in = op.in.p; p.N = op.in.N; p.H = op.in.H; p.W = op.in.W; p.in_cs = op.in.cs; p.in_coff = op.in.coff; p.Cin = op.in.C;
   p.w = op.w; p.out = op.out.p; p.out_cs = op.out.cs; p.out_coff = op.out.coff; p.Cout = op.out.C; p.out_planar = op.out.planar;
-  p.shift = op.shift; p.act = op.act; p.pad = op.pad;
+  p.shift = op.shift; p.act = op.act; p.pad = op.pad; p.tile_mask = op.tile_mask; p.tile_mask_u8 = op.tile_mask_u8;
   const size_t smem = (size_t)(CCH * SH * SW + CCH * KS * KS * 4) * sizeof(float);
   static PerDeviceOnce attr;
   if (attr.first()) CUDA_OK(cudaFuncSetAttribute(conv7_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

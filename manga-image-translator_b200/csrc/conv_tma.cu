@@ -60,6 +60,7 @@ struct TmaParams {
   uint16_t* os_hi; uint16_t* os_mid; int os_pitch, os_coff, os_Hp, os_Wp, os_pt, os_pl;
   const float* os_scale; const float* os_shift; int os_relu;  // consumer prologue applied before splitting
   int fast;                                                   // NHWC, 16-byte aligned rows / constants, Cout % 4 == 0: the packed epilogue
+  const uint8_t* tile_need;                                   // per 128-row M tile: 0 = skip (ConvOp::need_px reduced over the tile), null: all
 };
 
 #include "tc_common.cuh"
@@ -247,6 +248,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     oy0 = ty * bh; ox0 = tx * bw;
   };
 
+  // output sparsity: every role walks the same tile sequence and skips the same tiles (a pair tile is needed if either half is)
+  auto needed = [&](int t) -> bool {
+    if (!p.tile_need) return true;
+    const int mpair = t / nt;
+    if (CG == 2) return (p.tile_need[2 * mpair] | (2 * mpair + 1 < mt ? p.tile_need[2 * mpair + 1] : (uint8_t)0)) != 0;
+    return p.tile_need[mpair] != 0;
+  };
+
   if (warp < TM_EWARPS) {
     // =========================== epilogue: warp w drains TMEM lane quarter (w & 3), column half (w >> 2) ===========================
     const int q = warp & 3, epart = warp >> 2;       // TMEM lane quarter (must equal warp % 4), column part
@@ -270,7 +279,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     };
     int lt = 0;
     const uint32_t tempty_lead0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : tempty_bar(0);   // the MMA issuer (leader) owns "accumulator drained"
-    for (int t = tile_first; t < total_tiles; t += tile_step, ++lt) {
+    for (int t = tile_first; t < total_tiles; t += tile_step) {
+      if (!needed(t)) continue;
       int nimg_t, oy0, ox0, n0;
       decode(t, nimg_t, oy0, ox0, n0);
       const int buf = lt & 1;
@@ -527,6 +537,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
       if (lane == 0) {                                     // accumulator drained -> the MMA warp may overwrite it
         if (CG == 2) mbar_arrive_cluster(tempty_lead0 + 8u * buf); else mbar_arrive(tempty_bar(buf));
       }
+      ++lt;
     }
   } else if (warp == TM_MMAWARP) {
     // =========================== MMA issuer ===========================
@@ -537,7 +548,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG * TC_BM) >> 4) << 24);
     int s = 0; uint32_t ph = 0; int lt = 0;
     if (CG == 1 || crank == 0)
-    for (int t = tile_first; t < total_tiles; t += tile_step, ++lt) {
+    for (int t = tile_first; t < total_tiles; t += tile_step) {
+      if (!needed(t)) continue;
       const int buf = lt & 1;
       mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
       tc_fence_after();
@@ -556,6 +568,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         if (++s == S) { s = 0; ph ^= 1u; }
       }
       if (CG == 2) umma_commit_elect_pair(tfull_bar(buf)); else umma_commit_elect(tfull_bar(buf));      // accumulator complete -> epilogue(s)
+      ++lt;
     }
     __syncwarp();
   } else if (warp == TM_TMAWARP) {
@@ -563,6 +576,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     int s = 0; uint32_t ph = 1;
     const uint32_t full_lead0 = CG == 2 ? mapa_rank(full_bar(0), 0) : full_bar(0);
     for (int t = tile_first; t < total_tiles; t += tile_step) {
+      if (!needed(t)) continue;
       int nimg, oy0, ox0, n0;
       decode(t, nimg, oy0, ox0, n0);
       int kb = 0;
@@ -682,6 +696,26 @@ __global__ void __launch_bounds__(256) split_stem8_kernel(const float* in, int N
     *reinterpret_cast<uint4*>(hi + (size_t)i * 8) = make_uint4(h.x, h.y, 0u, 0u);
     *reinterpret_cast<uint4*>(mid + (size_t)i * 8) = make_uint4(m.x, m.y, 0u, 0u);
   }
+}
+
+// ConvOp::need_px (uint8 over the logical output grid) -> one flag per 128-row M tile, same tile geometry as the conv kernel
+__global__ void __launch_bounds__(128) tile_need_kernel(const uint8_t* need_px, int N, int Ho, int Wo, int M, int lin, int bw_log2, int tiles_x,
+                                                        int tiles_y, uint8_t* tile_need) {
+  const int mtile = blockIdx.x, r = threadIdx.x;
+  int v = 0;
+  if (lin) {
+    const int m = mtile * 128 + r;
+    if (m < M) v = need_px[m];
+  } else {
+    const int per_img = tiles_y * tiles_x;
+    const int nimg = mtile / per_img, rr = mtile - nimg * per_img;
+    const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
+    const int bw = 1 << bw_log2, bh = 128 >> bw_log2;
+    const int oy = ty * bh + (r >> bw_log2), ox = tx * bw + (r & (bw - 1));
+    if (nimg < N && oy < Ho && ox < Wo) v = need_px[((size_t)nimg * Ho + oy) * Wo + ox];
+  }
+  const int any = __syncthreads_or(v);
+  if (r == 0) tile_need[mtile] = (uint8_t)(any != 0);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -956,7 +990,9 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
     for (int cand = 128; cand >= 8; cand >>= 1) {
       const int ch = 128 / cand;
       const long cost = (long)((op.Wo + cand - 1) / cand) * cand * (long)((op.Ho + ch - 1) / ch) * ch;
-      if (best < 0 || cost < best) { best = cost; bw = cand; }
+      // output-sparse launches: among equally tight tilings prefer the compact 16 x 8 patch - a 128 x 1 strip crosses several text
+      // boxes per row and is almost never skippable (measured: no gain with strips)
+      if (best < 0 || cost < best || (op.need_px && cost == best && cand >= 16)) { best = cost; bw = cand; }
     }
     bh = 128 / bw;
     p.tiles_x = (op.Wo + bw - 1) / bw; p.tiles_y = (op.Ho + bh - 1) / bh;
@@ -1040,6 +1076,14 @@ static void tma_launch(const ConvOp& op, cudaStream_t st, bool stem) {
     if (env) p.fast = 0;
   }
   MITB_CHECK(!op.stat_max || op.stat_ld == 2 * (op.tc_npad / op.tc_bn), "tma conv: stat_ld must equal conv_stat_blocks(op)");
+  if (op.need_px && !op.stat_max) {
+    // reduce the pixel-level hint to this launch's tile grid (one tiny launch; the scratch is per device and stream ordered)
+    static DeviceScratch g_need;
+    uint8_t* tn = static_cast<uint8_t*>(g_need.get((size_t)mtiles + 16));
+    tile_need_kernel<<<(unsigned)mtiles, 128, 0, st>>>(op.need_px, N, op.Ho, op.Wo, N * op.Ho * op.Wo, p.lin, p.bw_log2, p.tiles_x, p.tiles_y, tn);
+    count_launch();
+    p.tile_need = tn;
+  }
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = 2 * cols;
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)(p.BN / cg) * 128;

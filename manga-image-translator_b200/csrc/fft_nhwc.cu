@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(FT, 3) rfft_rows_nhwc_kernel(const __grid_cons
   __syncthreads();
   fft_dif<false>(X, tw, bt, p.pl, lane, warp);
   float2* dst = reinterpret_cast<float2*>(p.out_f) + (size_t)row * p.w2 * p.C;
+#pragma unroll 4
   for (int k = warp; k < p.w2; k += FW) {
     const int kc = k ? p.w - k : 0;
     const float2 z = X[(size_t)rev[k] * FV + lane], zc = X[(size_t)rev[kc] * FV + lane];
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(FT, 3) fft_cols_nhwc_kernel(const __grid_const
              p.in + pix0 * p.in_cs + p.in_coff + chunk * 2 * FV, (long)p.w2 * p.in_cs, ok, lane, warp);
   __syncthreads();
   fft_dif<INV>(X, tw, bt, p.pl, lane, warp);
+#pragma unroll 4
   for (int ky = warp; ky < p.h; ky += FW) {
     float2 z = X[(size_t)rev[ky] * FV + lane];
     if (!ok) continue;
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(FT, 3) irfft_rows_nhwc_kernel(const __grid_con
   const bool ok = 2 * pair < p.C;
   load_tables(p.pl, tw, rev, bt);
   const float2* src = reinterpret_cast<const float2*>(p.in) + (size_t)row * p.w2 * p.C;
+#pragma unroll 4                                       // several rows' loads in flight per warp (ncu: this kernel waited on one load at a time)
   for (int k = warp; k < p.w2; k += FW) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)k * p.C + 2 * pair));
@@ -331,6 +334,7 @@ __global__ void __launch_bounds__(FT, 3) irfft_rows_nhwc_kernel(const __grid_con
   }
   __syncthreads();
   fft_dif<true>(X, tw, bt, p.pl, lane, warp);
+#pragma unroll 4
   for (int x = warp; x < p.w; x += FW) {
     float2 z = X[(size_t)rev[x] * FV + lane];
     if (!ok) continue;

@@ -171,6 +171,12 @@ static FfcFastOps ffc_fast_ops(const FfcLayer& l, const SplitView& Xs, const Spl
 
 static int g_ffc_mode = 1;             // 0: generic planar path only, 1: fused path when no layer needs split-K, 2: fused whenever capable
 void lama_set_ffc_mode(int mode) { g_ffc_mode = mode; }
+static int g_sparse_decoder = -1;      // -1: environment default (on unless MITB_DENSE_TAIL=1)
+void lama_set_sparse_decoder(int on) { g_sparse_decoder = on ? 1 : 0; }
+static bool lama_sparse_decoder() {
+  if (g_sparse_decoder < 0) { const char* ev = getenv("MITB_DENSE_TAIL"); g_sparse_decoder = (ev && atoi(ev)) ? 0 : 1; }
+  return g_sparse_decoder != 0;
+}
 
 static bool ffc_fast_ok(const LamaModel& m, int n, int h, int w) {
   if (g_ffc_mode == 0 || !fft_nhwc_supported(h, w, 192) || h < 4 || w < 4) return false;
@@ -252,12 +258,33 @@ void lama_run(Ctx& ctx, LamaModel& m, const float* img, const float* mask, const
       View t = X; X = Z; Z = t;
     }
     // upsampling: 3 x [ConvTranspose2d(3,s2,p1,op1) + BN + ReLU], then ReflectionPad(3) + Conv7x7 + sigmoid
+    // Output sparsity of the decoder: the result is pred*mask + (1-mask)*img (inpainting_lama_mpe.py:726), so prediction pixels outside
+    // the hole are never used.  Walking the receptive fields back from the hole gives, per upsampling stage, the pixels that can reach a
+    // hole pixel: the 7x7 conv reads u3 within 3 px of a hole pixel; a stride-2 transposed conv's phases produce the 2x2 block of a
+    // grid pixel from its 1-neighbourhood.  Tiles without such a pixel are skipped (left unwritten) - every used output is computed from
+    // computed inputs, bit-identically to the dense path (MITB_DENSE_TAIL=1 disables the hints; one image per call only).
+    const bool sp = lama_sparse_decoder() && n == 1 && h % 8 == 0 && w % 8 == 0;
+    uint8_t *need_u3 = nullptr, *g2 = nullptr, *need_u2 = nullptr, *g1 = nullptr, *need_u1 = nullptr, *g0 = nullptr;
+    if (sp) {
+      need_u3 = (uint8_t*)ws.alloc((size_t)h * w);
+      g2 = (uint8_t*)ws.alloc((size_t)h * w / 4); need_u2 = (uint8_t*)ws.alloc((size_t)h * w / 4);
+      g1 = (uint8_t*)ws.alloc((size_t)h * w / 16); need_u1 = (uint8_t*)ws.alloc((size_t)h * w / 16);
+      g0 = (uint8_t*)ws.alloc((size_t)h * w / 64);
+      if (!e.dry) {
+        launch_need_from_mask(u8 ? nullptr : mask, u8 ? u8->mask : nullptr, h, w, 3, need_u3, st);
+        launch_need_pool2(need_u3, h, w, g2, need_u2, st);
+        launch_need_pool2(need_u2, h / 2, w / 2, g1, need_u1, st);
+        launch_need_pool2(need_u1, h / 4, w / 4, g0, nullptr, st);
+      }
+    }
     View u1 = ws.view(n, h / 4, w / 4, 256), u2 = ws.view(n, h / 2, w / 2, 128), u3 = ws.view(n, h, w, 64);
-    e.convT2(m.up[0].ph, X, u1, [](ConvOp& op) { op.act = ACT_RELU; });
-    e.convT2(m.up[1].ph, u1, u2, [](ConvOp& op) { op.act = ACT_RELU; });
-    e.convT2(m.up[2].ph, u2, u3, [](ConvOp& op) { op.act = ACT_RELU; });
+    e.convT2(m.up[0].ph, X, u1, [&](ConvOp& op) { op.act = ACT_RELU; op.need_px = g0; });
+    e.convT2(m.up[1].ph, u1, u2, [&](ConvOp& op) { op.act = ACT_RELU; op.need_px = g1; });
+    e.convT2(m.up[2].ph, u2, u3, [&](ConvOp& op) { op.act = ACT_RELU; op.need_px = g2; });
     View pred = ws.view(n, h, w, 3, true);
-    { ConvOp op = Exec::op_from(m.outc, u3, pred, 1, PAD_REFLECT); op.act = ACT_SIGMOID; e.conv(op); }
+    { ConvOp op = Exec::op_from(m.outc, u3, pred, 1, PAD_REFLECT); op.act = ACT_SIGMOID;
+      if (sp) { if (u8) op.tile_mask_u8 = u8->mask; else op.tile_mask = mask; }      // (maskf's arena slot was released above)
+      e.conv(op); }
     if (!e.dry) {
       if (u8) launch_lama_blend_u8(pred, u8->img, u8->mask, u8->out, u8->composite, st);
       else launch_lama_blend(pred, img, mask, out, st);

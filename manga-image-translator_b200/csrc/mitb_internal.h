@@ -88,6 +88,13 @@ struct ConvOp {
   const float* in_scale = nullptr; const float* in_shift = nullptr; int in_relu = 0;
   // epilogue: v = acc (+add0) ; v = v*scale[c]+shift[c] ; v = act(v) ; v *= mul1[c] ; v += add1
   View add0, add1;                    // same pixel grid as out; p==nullptr when unused
+  // Optional output-sparsity hint (conv7_thin only): planar fp32 [N][Ho][Wo]; a CTA tile whose entries are all zero writes zeros
+  // instead of computing - for a conv whose only consumer multiplies / selects by this very mask (LaMa's final blend).
+  const float* tile_mask = nullptr;
+  const uint8_t* tile_mask_u8 = nullptr;   // the same hint from a uint8 mask: "non-zero" means >= 128 (mask / 255 >= 0.5)
+  // Output-sparsity hint for the TMA conv kernel: uint8 [N][Ho][Wo] over this launch's LOGICAL output grid; output tiles without a
+  // non-zero entry are skipped (left unwritten).  The caller guarantees that nothing it still needs depends on skipped pixels.
+  const uint8_t* need_px = nullptr;
   const float* scale = nullptr; const float* shift = nullptr; const float* mul1 = nullptr;
   int act = ACT_NONE;
   // tensor-core copies of the weights (conv_tc.cu): bf16 hi/mid [tc_npad][tc_kpad], K-major; null -> SIMT path only
@@ -162,6 +169,9 @@ void launch_crf(const int* lines2, const int* lines5, int nlines, const uint8_t*
 void launch_dilate_lines(const int* lines, int nlines, int max_pix2, const int* omap, const uint8_t* refined, const uint8_t* se, int img_w,
                          uint8_t* final_mask, cudaStream_t st);
 void launch_dilate_se(const uint8_t* src, int h, int w, const uint8_t* se, int ksize, uint8_t* dst, cudaStream_t st);
+// ops.cu: need maps of LaMa's decoder (which pixels of each upsampling stage can reach a hole pixel of the final blend)
+void launch_need_from_mask(const float* mask_f, const uint8_t* mask_u8, int H, int W, int radius, uint8_t* need, cudaStream_t st);
+void launch_need_pool2(const uint8_t* src, int H, int W, uint8_t* pooled /*[H/2][W/2]*/, uint8_t* dilated /*[H/2][W/2], radius 1, may be null*/, cudaStream_t st);
 // warp.cu: perspective crops of text lines into the OCR chunk canvas (cv2.warpPerspective + rotate, bit-exact) and greedy CTC collapse
 void launch_warp_lines(const uint8_t* page, int H, int W, const double* lines /*[n][16]*/, int n, uint8_t* canvas, int canvas_h, int canvas_w,
                        cudaStream_t st);
@@ -248,6 +258,7 @@ void ocr_run(Ctx&, OcrModel&, const float* x_nchw, const uint8_t* x_u8, int n, i
 int ocr_vocab(const OcrModel&);
 LamaModel* lama_build(Ctx&, const Weights&);
 void lama_free(LamaModel*);
+void lama_set_sparse_decoder(int on);   // output-sparse LaMa decoder (skip tiles the final blend cannot see); default on
 void lama_set_ffc_mode(int mode);     // 0 generic planar FFC path, 1 fused NHWC path when no layer needs split-K (default), 2 fused whenever capable
 struct LamaU8Io { const uint8_t* img = nullptr; const uint8_t* mask = nullptr; uint8_t* out = nullptr; int composite = 0; };
 void lama_run(Ctx&, LamaModel&, const float* img, const float* mask, const int* rel_pos, const int* direct, int th,

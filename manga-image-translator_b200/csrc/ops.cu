@@ -539,6 +539,50 @@ void launch_lama_pack_input(const float* img, const float* mask, int N, int H, i
   LAUNCH_END();
 }
 
+// Need maps for the output-sparse LaMa decoder.  need_from_mask: 1 where a hole pixel (mask != 0 / uint8 mask >= 128) lies within
+// `radius` (Chebyshev) - the pixels of the last feature map that the final 7x7 conv reads for a hole pixel.  need_pool2: OR over 2x2
+// blocks (the logical grid of a stride-2 transposed conv's phases), and that map dilated by 1 (the inputs those phases read).
+__global__ void need_from_mask_kernel(const float* mask_f, const uint8_t* mask_u8, int H, int W, int radius, uint8_t* need) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  int any = 0;
+  for (int dy = -radius; dy <= radius && !any; ++dy) {
+    const int yy = y + dy; if (yy < 0 || yy >= H) continue;
+    for (int dx = -radius; dx <= radius; ++dx) {
+      const int xx = x + dx; if (xx < 0 || xx >= W) continue;
+      const size_t i = (size_t)yy * W + xx;
+      if (mask_f ? mask_f[i] != 0.f : mask_u8[i] >= 128) { any = 1; break; }
+    }
+  }
+  need[(size_t)y * W + x] = (uint8_t)any;
+}
+__global__ void need_pool2_kernel(const uint8_t* src, int H, int W, uint8_t* pooled) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, h2 = H / 2, w2 = W / 2;
+  if (x >= w2 || y >= h2) return;
+  const uint8_t* r0 = src + (size_t)(2 * y) * W + 2 * x;
+  pooled[(size_t)y * w2 + x] = (uint8_t)((r0[0] | r0[1] | r0[W] | r0[W + 1]) != 0);
+}
+__global__ void need_dilate1_kernel(const uint8_t* src, int H, int W, uint8_t* dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  int any = 0;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy; if (yy < 0 || yy >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) { const int xx = x + dx; if (xx >= 0 && xx < W) any |= src[(size_t)yy * W + xx]; }
+  }
+  dst[(size_t)y * W + x] = (uint8_t)(any != 0);
+}
+void launch_need_from_mask(const float* mask_f, const uint8_t* mask_u8, int H, int W, int radius, uint8_t* need, cudaStream_t st) {
+  need_from_mask_kernel<<<dim3((W + 255) / 256, H), 256, 0, st>>>(mask_f, mask_u8, H, W, radius, need);
+  LAUNCH_END();
+}
+void launch_need_pool2(const uint8_t* src, int H, int W, uint8_t* pooled, uint8_t* dilated, cudaStream_t st) {
+  MITB_CHECK(H % 2 == 0 && W % 2 == 0, "need_pool2: odd size");
+  need_pool2_kernel<<<dim3((W / 2 + 255) / 256, H / 2), 256, 0, st>>>(src, H, W, pooled);
+  LAUNCH_END();
+  if (dilated) { need_dilate1_kernel<<<dim3((W / 2 + 255) / 256, H / 2), 256, 0, st>>>(pooled, H / 2, W / 2, dilated); LAUNCH_END(); }
+}
+
 // blend: out = pred*mask + (1-mask)*img, pred planar NCHW view (inpainting_lama_mpe.py:726)
 __global__ void lama_blend_kernel(const float* pred, const float* img, const float* mask, float* out, int N, long HW) {
   const long total = (long)N * 3 * HW;

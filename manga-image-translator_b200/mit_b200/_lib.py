@@ -33,6 +33,7 @@ SIGNATURES = {
     "mitb_workspace_bytes": (C.c_size_t, [P]),
     "mitb_set_tensor_cores": (I, [I]),
     "mitb_set_ffc_mode": (I, [I]),
+    "mitb_set_sparse_decoder": (I, [I]),
     "mitb_profile_enable": (I, [P, I]),
     "mitb_profile_report": (C.c_char_p, [P]),
     "mitb_dbnet_load": (I, [P, C.POINTER(MitbTensor), I]),

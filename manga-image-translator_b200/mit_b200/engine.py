@@ -148,6 +148,11 @@ class Engine:
         with self._lock:
             self.lib.mitb_set_tensor_cores(1 if on else 0)
 
+    def set_sparse_decoder(self, on: bool):
+        """Process-wide: output-sparse LaMa decoder (default on); off = every tile of the upsampling stages is computed."""
+        with self._lock:
+            self.lib.mitb_set_sparse_decoder(1 if on else 0)
+
     def set_ffc_mode(self, mode: int):
         """Process-wide LaMa FFC implementation: 0 generic planar, 1 fused NHWC when no layer needs split-K (default), 2 fused whenever capable."""
         with self._lock:

@@ -206,3 +206,36 @@ def test_lama_mpe256_tables_equal_full_resolution_tables(eng):
         b = eng.lama_forward(img, mask, rel2[None], direct2[None], tables256=True)
         assert torch.equal(a, b), (h, w, (a - b).abs().max().item())
     eng.unload_lama()
+
+
+@pytest.mark.gpu
+def test_lama_sparse_decoder_is_bit_identical_to_dense(eng):
+    """The output-sparse decoder (tiles of the upsampling stages and of the 7x7 output conv that cannot reach a hole pixel are skipped)
+    against the dense computation: the blended result must be identical in every bit, on the fp32 entry and on the uint8 entry."""
+    sd, msd = weights.lama_weights(9), weights.mpe_weights()
+    rng = np.random.default_rng(12)
+    H, W = 512, 384
+    img_u8 = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    mask_u8 = np.zeros((H, W), np.uint8)
+    for (y0, x0, hh, ww) in ((10, 20, 40, 200), (300, 5, 150, 30), (480, 300, 32, 84), (200, 200, 9, 11), (0, 0, 3, 3)):
+        mask_u8[y0:y0 + hh, x0:x0 + ww] = 255
+    mask_u8[250, 100] = 127                     # below the 0.5 threshold: not a hole
+    img = torch.from_numpy(img_u8.astype(np.float32).transpose(2, 0, 1)[None] / 255.0)
+    m = torch.from_numpy((mask_u8 >= 128).astype(np.float32)[None, None])
+    rel, direct = nets.mpe_tables(m[0, 0].numpy())
+    eng.load_lama(sd, msd)
+    try:
+        outs = {}
+        for mode in (True, False):
+            eng.set_sparse_decoder(mode)
+            a = eng.lama_forward(img * (1 - m), m, rel[None], direct[None]).cpu().numpy()
+            from mit_b200.host import mpe as mpe_host
+            small = mpe_host.small_mask_256((mask_u8 >= 128))
+            r256, d256 = eng.mpe_tables_256(small)
+            b = eng.lama_infer_u8(torch.from_numpy(img_u8).to(eng.device), torch.from_numpy(mask_u8).to(eng.device), r256, d256, composite=True).cpu().numpy()
+            outs[mode] = (a, b)
+        assert np.array_equal(outs[True][0], outs[False][0]) and np.array_equal(outs[True][1], outs[False][1])
+        assert np.isfinite(outs[True][0]).all()
+    finally:
+        eng.set_sparse_decoder(True)
+        eng.unload_lama()
