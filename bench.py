@@ -582,6 +582,9 @@ def run_ours(args, rank, world, local_rank):
                        "value_region": "resident pages, per-launch CUDA-event profiler ON (feeds `roofline`)" + (", incl. the NCCL all-gather of the result records" if world > 1 else ""),
                        "value_without_profiler": value_unprofiled, "workers": args.workers,
                        "l2": f"inputs larger than L2 ({staged_bytes / 1e9:.1f} GB of staged pages per step)",
+                       "lama_decoder": "output-sparse: decoder tiles from which no hole pixel of the final blend pred*mask+(1-mask)*img is reachable are "
+                                       "skipped, bit-identical to the dense path (synthetic masks cover ~7 % of a page; MITB_DENSE_TAIL=1 = dense)",
+                       "ocr_crops": "cut on the device from the resident page (mitb_op_warp_lines_u8), CTC collapse on the device",
                        "weights": "seeded random (no checkpoints offline); detector binarize bias -11 so the random-weight probability map is sparse "
                                   "(~50 candidate contours per page, like a real page, instead of ~10^6 noise pixels)"},
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
