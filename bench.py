@@ -202,14 +202,17 @@ def gpu_bar(W, dev, n_pages, warm_pages=2, modes=("tf32_bf16", "fp32")):
             for i in range(warm_pages):
                 one_page(staged[i % len(staged)], tf32)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(n_pages):
-                one_page(staged[i % len(staged)], tf32)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-            out[mode] = {"pages_per_s": n_pages / (ms / 1e3), "ms_per_page": ms / n_pages, "pages_timed": n_pages}
+            ms = None
+            for _ in range(2):                                 # best of two passes: the bar is the library at its best, not a cold-start artefact
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(n_pages):
+                    one_page(staged[i % len(staged)], tf32)
+                e1.record()
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1)
+                ms = t if ms is None else min(ms, t)
+            out[mode] = {"pages_per_s": n_pages / (ms / 1e3), "ms_per_page": ms / n_pages, "pages_timed": n_pages, "passes": 2}
             log(f"[gpu bar] {mode}: {ms / n_pages:.1f} ms/page")
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
