@@ -154,6 +154,13 @@ int mitb_op_warp_lines_u8(mitb_ctx* ctx, const uint8_t* page, int h, int w, cons
 int mitb_op_ctc_collapse(mitb_ctx* ctx, const int32_t* argmax, const float* logprob, const float* colors, int n, int t, int32_t* counts,
                          int32_t* steps, int32_t* chars, float* logprob_out, float* colors_out, void* stream);
 
+/* `quadrilateral_can_merge_region` (utils/generic.py:653-698) for every pair of text lines - the O(n^2) part of the OCR
+ * direction graph (ocr/common.py:12-39) and of textline_merge (textline_merge/__init__.py:110-126).  quads: device double [n][16] =
+ * corners (8), AABB x, y, w, h, font_size, aspect_ratio, angle, flags (bit 0 approximately axis aligned, bit 1 convex).
+ * adj: uint8 [n][n], symmetric: 1 mergeable, 0 not, 2 undecided (a non-convex quad: the caller evaluates that pair itself). */
+int mitb_op_textline_pairs(mitb_ctx* ctx, const double* quads, int n, double ratio, double discard_connection_gap, double char_gap_tolerance,
+                           double char_gap_tolerance2, double font_size_ratio_tol, double aspect_ratio_tol, uint8_t* adj, void* stream);
+
 /* ---- mask refinement (manga_translator/mask_refinement/__init__.py:9-31, text_mask_utils.py:64-190) ---- */
 /* cv2.resize(src, (dw, dh), interpolation=INTER_LINEAR) for uint8 [sh,sw,channels] (channels 1 or 3), bit-exact; binarize != 0
  * additionally maps every non-zero result to 255 (`mask[mask > 0] = 255`, __init__.py:18,28). */

@@ -374,6 +374,16 @@ int mitb_op_ctc_collapse(mitb_ctx* ctx, const int32_t* argmax, const float* logp
   API_END(ctx)
 }
 
+int mitb_op_textline_pairs(mitb_ctx* ctx, const double* quads, int n, double ratio, double discard_connection_gap, double char_gap_tolerance,
+                           double char_gap_tolerance2, double font_size_ratio_tol, double aspect_ratio_tol, uint8_t* adj, void* stream) {
+  API_BEGIN(ctx)
+  g_launch_counter = &ctx->c.launches; ++g_launch_epoch;
+  const double pp[6] = {ratio, discard_connection_gap, char_gap_tolerance, char_gap_tolerance2, font_size_ratio_tol, aspect_ratio_tol};
+  launch_textline_pairs(quads, n, pp, adj, (cudaStream_t)stream);
+  g_launch_counter = nullptr;
+  API_END(ctx)
+}
+
 #define MITB_OP(body)                                             \
   API_BEGIN(ctx)                                                  \
   g_launch_counter = &ctx->c.launches; ++g_launch_epoch;          \

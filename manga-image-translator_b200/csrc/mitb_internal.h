@@ -175,6 +175,7 @@ void launch_need_pool2(const uint8_t* src, int H, int W, uint8_t* pooled /*[H/2]
 // warp.cu: perspective crops of text lines into the OCR chunk canvas (cv2.warpPerspective + rotate, bit-exact) and greedy CTC collapse
 void launch_warp_lines(const uint8_t* page, int H, int W, const double* lines /*[n][16]*/, int n, uint8_t* canvas, int canvas_h, int canvas_w,
                        cudaStream_t st);
+void launch_textline_pairs(const double* quads /*[n][16]*/, int n, const double* params6 /*host*/, uint8_t* adj /*[n][n]*/, cudaStream_t st);
 void launch_ctc_collapse(const int* argmax, const float* logprob, const float* colors, int n, int T, int* counts, int* steps, int* chars,
                          float* lp_out, float* col_out, cudaStream_t st);
 void launch_mpe_tables(const uint8_t* small /*[n,256,256] INTER_AREA-reduced mask*/, int n, int* rel_pos, int* direct, cudaStream_t st);

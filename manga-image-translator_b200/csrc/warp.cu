@@ -120,3 +120,123 @@ void launch_ctc_collapse(const int* argmax, const float* logprob, const float* c
 }
 
 }  // namespace mitb
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the O(n^2) part of the text-line graph - `quadrilateral_can_merge_region` (utils/generic.py:653-698) for every pair of
+// lines, as used by the OCR direction graph (ocr/common.py:12-39) and by textline_merge (textline_merge/__init__.py:110-126).
+// One thread per pair (i < j).  Per line the host passes 16 doubles: corners (8), AABB x, y, w, h, font_size, aspect_ratio, angle,
+// flags (bit 0: approximately axis aligned, bit 1: convex).  Arithmetic mirrors mit_b200/host/geometry.py statement by statement in
+// IEEE doubles without contraction (the host port is pinned by the reference's known-answer tests); a pair with a non-convex quad
+// is reported as 2 ("ask the host": its hull has fewer vertices than the quad).
+namespace mitb {
+namespace {
+
+struct PairParams { double ratio, gap, tol, tol2, fs_tol, ar_tol; };
+
+__device__ __forceinline__ double orient_d(const double* p, const double* q, const double* r) {
+  return __dsub_rn(__dmul_rn(__dsub_rn(q[0], p[0]), __dsub_rn(r[1], p[1])), __dmul_rn(__dsub_rn(q[1], p[1]), __dsub_rn(r[0], p[0])));
+}
+// inside or on the boundary (cv2.pointPolygonTest(..) >= 0): boundary points have distance 0 to an edge anyway, so only the strict
+// interior matters for the caller
+__device__ bool inside_quad(const double* poly, const double* pt) {
+  bool in = false;
+  for (int i = 0, j = 3; i < 4; j = i++) {
+    const double xi = poly[2 * i], yi = poly[2 * i + 1], xj = poly[2 * j], yj = poly[2 * j + 1];
+    if ((yi > pt[1]) != (yj > pt[1]) && pt[0] < (xj - xi) * (pt[1] - yi) / (yj - yi) + xi) in = !in;
+  }
+  return in;
+}
+__device__ double pts_to_segs(const double* P, const double* S) {      // min over the 4 points of P and the 4 edges S[j] -> S[j+1]
+  double best = 1e300;
+  for (int j = 0; j < 4; ++j) {
+    const double* s0 = S + 2 * j; const double* s1 = S + 2 * ((j + 1) & 3);
+    const double abx = __dsub_rn(s1[0], s0[0]), aby = __dsub_rn(s1[1], s0[1]);
+    const double den = __dadd_rn(__dmul_rn(abx, abx), __dmul_rn(aby, aby));
+    for (int i = 0; i < 4; ++i) {
+      const double apx = __dsub_rn(P[2 * i], s0[0]), apy = __dsub_rn(P[2 * i + 1], s0[1]);
+      double t = 0.0;
+      if (den != 0.0) { t = __ddiv_rn(__dadd_rn(__dmul_rn(apx, abx), __dmul_rn(apy, aby)), den); t = t < 0.0 ? 0.0 : t > 1.0 ? 1.0 : t; }
+      const double ox = __dsub_rn(P[2 * i], __dadd_rn(s0[0], __dmul_rn(t, abx))), oy = __dsub_rn(P[2 * i + 1], __dadd_rn(s0[1], __dmul_rn(t, aby)));
+      const double d = sqrt(__dadd_rn(__dmul_rn(ox, ox), __dmul_rn(oy, oy)));
+      best = d < best ? d : best;
+    }
+  }
+  return best;
+}
+__device__ double polygon_distance_d(const double* p1, const double* p2) {
+  for (int i = 0; i < 4; ++i) {
+    const double* a = p1 + 2 * i; const double* b = p1 + 2 * ((i + 1) & 3);
+    for (int j = 0; j < 4; ++j) {
+      const double* c = p2 + 2 * j; const double* d = p2 + 2 * ((j + 1) & 3);
+      if (__dmul_rn(orient_d(a, b, c), orient_d(a, b, d)) < 0.0 && __dmul_rn(orient_d(c, d, a), orient_d(c, d, b)) < 0.0) return 0.0;
+    }
+  }
+  if (inside_quad(p1, p2) || inside_quad(p2, p1)) return 0.0;
+  const double d1 = pts_to_segs(p1, p2), d2 = pts_to_segs(p2, p1);
+  return d1 < d2 ? d1 : d2;
+}
+
+__global__ void __launch_bounds__(128) textline_pairs_kernel(const double* __restrict__ q, int n, PairParams pp, uint8_t* __restrict__ adj) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= (long)n * n) return;
+  const int i = (int)(idx / n), j = (int)(idx % n);
+  if (i >= j) { if (i == j) adj[idx] = 0; return; }
+  const double* A = q + 16 * (size_t)i; const double* B = q + 16 * (size_t)j;
+  const double x1 = A[8], y1 = A[9], w1 = A[10], h1 = A[11], x2 = B[8], y2 = B[9], w2 = B[10], h2 = B[11];
+  const double fa = A[12], fb = B[12], ara = A[13], arb = B[13];
+  const int fla = (int)A[15], flb = (int)B[15];
+  uint8_t res = 0;
+  // Types follow the host port under numpy 2 (NEP 50): font sizes and aspect ratios are float32 scalars, so products / quotients with
+  // Python numbers stay float32 and a Python-float distance is rounded to float32 when compared with them; AABB numbers are int64 /
+  // float64 and compare in float64.  (The pinned case: dist 51.0 against 85 * 0.6 = 51.000004f.)
+  const float fa32 = (float)fa, fb32 = (float)fb, ara32 = (float)ara, arb32 = (float)arb;
+  do {
+    const float cs32 = fminf(fa32, fb32);
+    const double cs = (double)cs32;
+    const double gx = fmax(0.0, __dsub_rn(fmax(x1, x2), fmin(__dadd_rn(x1, w1), __dadd_rn(x2, w2))));
+    const double gy = fmax(0.0, __dsub_rn(fmax(y1, y2), fmin(__dadd_rn(y1, h1), __dadd_rn(y2, h2))));
+    if (sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy))) > (double)__fmul_rn((float)pp.gap, cs32)) break;
+    if (!(fla & 2) || !(flb & 2)) { res = 2; break; }                     // a non-convex quad: let the host decide this pair
+    const double dist = polygon_distance_d(A, B);
+    const float dist32 = (float)dist;
+    if (dist32 > __fmul_rn((float)pp.gap, cs32)) break;
+    if (__fdiv_rn(fmaxf(fa32, fb32), cs32) > (float)pp.fs_tol) break;
+    const float inv_ar = (float)(1.0 / pp.ar_tol);
+    if (ara32 > (float)pp.ar_tol && arb32 < inv_ar) break;
+    if (arb32 > (float)pp.ar_tol && ara32 < inv_ar) break;
+    if ((fla & 1) && (flb & 1)) {
+      if (dist32 >= __fmul_rn(cs32, (float)pp.tol)) break;
+      if (fabs(__dsub_rn(__dadd_rn(x1, floor(w1 / 2.0)), __dadd_rn(x2, floor(w2 / 2.0)))) < pp.tol2) { res = 1; break; }
+      if ((w1 > __dmul_rn(h1, pp.ratio) && h2 > __dmul_rn(w2, pp.ratio)) || (w2 > __dmul_rn(h2, pp.ratio) && h1 > __dmul_rn(w1, pp.ratio))) break;
+      const double lim = (double)__fmul_rn(cs32, (float)pp.tol2);
+      if (w1 > __dmul_rn(h1, pp.ratio) || w2 > __dmul_rn(h2, pp.ratio)) {
+        res = (fabs(__dsub_rn(x1, x2)) < lim || fabs(__dsub_rn(__dadd_rn(x1, w1), __dadd_rn(x2, w2))) < lim) ? 1 : 0; break;
+      }
+      if (h1 > __dmul_rn(w1, pp.ratio) || h2 > __dmul_rn(w2, pp.ratio)) {
+        res = (fabs(__dsub_rn(y1, y2)) < lim || fabs(__dsub_rn(__dadd_rn(y1, h1), __dadd_rn(y2, h2))) < lim) ? 1 : 0; break;
+      }
+      break;
+    }
+    if (fabs(__dsub_rn(A[14], B[14])) < 15.0 * 3.14159265358979323846 / 180.0) {
+      if (dist32 > __fmul_rn(cs32, (float)pp.tol2)) break;               // poly_distance == polygon_distance for convex quads
+      res = __fdiv_rn(fabsf(__fsub_rn(fa32, fb32)), cs32) <= 0.25f ? 1 : 0;
+    }
+    (void)cs;
+  } while (false);
+  adj[idx] = res;
+  adj[(size_t)j * n + i] = res;
+}
+
+}  // namespace
+
+void launch_textline_pairs(const double* quads, int n, const double* params6, uint8_t* adj, cudaStream_t st) {
+  MITB_CHECK(n >= 0 && n <= 16384, "textline_pairs: too many lines");
+  if (n == 0) return;
+  PairParams pp{params6[0], params6[1], params6[2], params6[3], params6[4], params6[5]};
+  const long total = (long)n * n;
+  textline_pairs_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(quads, n, pp, adj);
+  count_launch();
+  CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace mitb

@@ -23,7 +23,7 @@ class MitbError(RuntimeError):
 _lib = None
 
 # name -> (restype, argtypes); mirrors include/mitb.h one to one (checked by tests/test_host.py::test_abi_header_and_library_agree)
-P, I, F, LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+P, I, F, LL, D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 SIGNATURES = {
     "mitb_create": (I, [I, C.POINTER(P)]),
     "mitb_destroy": (None, [P]),
@@ -63,6 +63,7 @@ SIGNATURES = {
     "mitb_op_bilateral17": (I, [P, P, I, I, P, P]),
     "mitb_op_warp_lines_u8": (I, [P, P, I, I, P, I, P, I, I, P]),
     "mitb_op_ctc_collapse": (I, [P, P, P, P, I, I, P, P, P, P, P, P]),
+    "mitb_op_textline_pairs": (I, [P, P, I, D, D, D, D, D, D, P, P]),
     "mitb_op_resize_linear_u8": (I, [P, P, I, I, I, P, I, I, I, P]),
     "mitb_op_cut_rects": (I, [P, P, I, I, P, I, P]),
     "mitb_op_cc_label": (I, [P, P, I, I, P, P, P, I, P, P]),

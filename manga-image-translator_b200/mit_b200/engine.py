@@ -385,6 +385,16 @@ class Engine:
                    canvas_w, self._stream())
         return canvas
 
+    def textline_pairs(self, features: np.ndarray, params) -> np.ndarray:
+        """`can_merge_region` for every pair of lines: features float64 [n,16] (host.geometry.pair_features), params =
+        (ratio, discard_connection_gap, char_gap_tolerance, char_gap_tolerance2, font_size_ratio_tol, aspect_ratio_tol); returns uint8
+        [n,n] on the host (1 mergeable, 0 not, 2 undecided)."""
+        f = self.h2d(np.ascontiguousarray(features, dtype=np.float64))
+        n = int(f.shape[0])
+        adj = torch.empty((n, n), dtype=torch.uint8, device=self.device)
+        self._call(self.lib.mitb_op_textline_pairs, _ptr(f), n, *[C.c_double(float(v)) for v in params], _ptr(adj), self._stream())
+        return self.d2h(adj).copy()
+
     def ctc_collapse(self, idx: torch.Tensor, logprob: torch.Tensor, colors: torch.Tensor):
         """Greedy CTC collapse on the device (row O8): returns (counts [n], steps [n,T], chars [n,T], logprob [n,T], colors [n,T,6]) with
         the kept steps compacted to the front of each row; entries past counts[i] are unspecified."""

@@ -307,14 +307,53 @@ def can_merge_region(a: Quadrilateral, b: Quadrilateral, ratio=1.9, discard_conn
     return False
 
 
-def generate_text_direction(bboxes: List[Quadrilateral]):
-    """Yield (quad, majority direction of its merge-group), groups ordered reading-wise (ocr/common.py:12-39)."""
+def pair_features(bboxes) -> np.ndarray:
+    """Per-line record of `mitb_op_textline_pairs` (include/mitb.h): float64 [n,16] = corners, AABB, font_size, aspect_ratio, angle, flags
+    (bit 0: approximately axis aligned, bit 1: strictly convex - the device evaluates polygon distances on the quad itself, which
+    equals the convex hull the reference uses only then)."""
+    f = np.zeros((len(bboxes), 16), dtype=np.float64)
+    for i, b in enumerate(bboxes):
+        p = np.asarray(b.pts, dtype=np.float64)
+        f[i, :8] = p.reshape(-1)
+        a = b.aabb
+        f[i, 8:12] = (a.x, a.y, a.w, a.h)
+        e = np.roll(p, -1, axis=0) - p
+        en = np.roll(e, -1, axis=0)
+        turn = e[:, 0] * en[:, 1] - e[:, 1] * en[:, 0]
+        convex = bool((turn > 0).all() or (turn < 0).all())
+        f[i, 12:16] = (b.font_size, b.aspect_ratio, b.angle, (1 if b.is_approximate_axis_aligned else 0) | (2 if convex else 0))
+    return f
+
+
+def can_merge_matrix(bboxes, engine, ratio=1.9, discard_connection_gap=2, char_gap_tolerance=0.6, char_gap_tolerance2=1.5,
+                     font_size_ratio_tol=1.5, aspect_ratio_tol=2) -> np.ndarray:
+    """`can_merge_region` for all pairs at once on the device; pairs the kernel leaves undecided (a non-convex quad)
+    are evaluated here.  Returns a symmetric bool matrix."""
+    n = len(bboxes)
+    if n < 2:
+        return np.zeros((n, n), dtype=bool)
+    params = (ratio, discard_connection_gap, char_gap_tolerance, char_gap_tolerance2, font_size_ratio_tol, aspect_ratio_tol)
+    adj = engine.textline_pairs(pair_features(bboxes), params)
+    for u, v in np.argwhere(np.triu(adj == 2, 1)):
+        r = can_merge_region(bboxes[int(u)], bboxes[int(v)], *params)
+        adj[u, v] = adj[v, u] = 1 if r else 0
+    return adj == 1
+
+
+def generate_text_direction(bboxes: List[Quadrilateral], engine=None):
+    """Yield (quad, majority direction of its merge-group), groups ordered reading-wise (ocr/common.py:12-39).  With `engine` the
+    pair predicate runs on the device (`mitb_op_textline_pairs`)."""
     if not bboxes:
         return
     import networkx as nx
     G = nx.Graph()
     for i, box in enumerate(bboxes):
         G.add_node(i, box=box)
+    if engine is not None:
+        for u, v in np.argwhere(np.triu(can_merge_matrix(bboxes, engine, aspect_ratio_tol=1), 1)):
+            G.add_edge(int(u), int(v))
+        yield from _ordered_groups(G, bboxes)
+        return
     # The reference tests all n(n-1)/2 pairs in Python; every pair whose AABB gap already exceeds the connection distance is
     # rejected by can_merge_region's first test, so a vectorised (slightly conservative) version of that test prunes the pair list
     # first - same edges, a fraction of the interpreter time on pages with many lines.
@@ -326,6 +365,11 @@ def generate_text_direction(bboxes: List[Quadrilateral]):
     for u, v in np.argwhere(np.triu(near, 1)):
         if can_merge_region(bboxes[int(u)], bboxes[int(v)], aspect_ratio_tol=1):
             G.add_edge(int(u), int(v))
+    yield from _ordered_groups(G, bboxes)
+
+
+def _ordered_groups(G, bboxes):
+    import networkx as nx
     for comp in nx.algorithms.components.connected_components(G):
         nodes = list(comp)
         major = Counter(bboxes[i].direction for i in nodes).most_common(1)[0][0]

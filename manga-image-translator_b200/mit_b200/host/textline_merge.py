@@ -12,7 +12,7 @@ from typing import Dict, Iterable, List, Sequence, Set, Tuple
 
 import numpy as np
 
-from .geometry import Quadrilateral, can_merge_region, polygon_distance
+from .geometry import Quadrilateral, can_merge_matrix, can_merge_region, polygon_distance
 
 
 class _DisjointSets:
@@ -94,13 +94,18 @@ def _majority_direction(lines: Sequence[Quadrilateral]) -> str:
     return direction
 
 
-def merge_text_regions(bboxes: Sequence[Quadrilateral], width: int, height: int):
-    """Yields (line indices in reading order, fg colour, bg colour, direction) per text region (`:110-181`)."""
+def merge_text_regions(bboxes: Sequence[Quadrilateral], width: int, height: int, engine=None):
+    """Yields (line indices in reading order, fg colour, bg colour, direction) per text region (`:110-181`).  With `engine` the O(n^2)
+    pair predicate runs on the device (`mitb_op_textline_pairs`); the graph work stays here."""
     n = len(bboxes)
     nodes = list(range(n))
-    edges = [(u, v) for u, v in itertools.combinations(nodes, 2)
-             if can_merge_region(bboxes[u], bboxes[v], aspect_ratio_tol=1.3, font_size_ratio_tol=2, char_gap_tolerance=1,
-                                 char_gap_tolerance2=3)]
+    if engine is not None and n >= 2:
+        adj = can_merge_matrix(bboxes, engine, aspect_ratio_tol=1.3, font_size_ratio_tol=2, char_gap_tolerance=1, char_gap_tolerance2=3)
+        edges = [(int(u), int(v)) for u, v in np.argwhere(np.triu(adj, 1))]
+    else:
+        edges = [(u, v) for u, v in itertools.combinations(nodes, 2)
+                 if can_merge_region(bboxes[u], bboxes[v], aspect_ratio_tol=1.3, font_size_ratio_tol=2, char_gap_tolerance=1,
+                                     char_gap_tolerance2=3)]
     regions: List[Set[int]] = []
     for comp in _components(nodes, edges):
         regions.extend(split_text_region(bboxes, comp))
@@ -131,10 +136,10 @@ class TextRegion:
     line_indices: List[int] = field(default_factory=list)
 
 
-def dispatch(textlines: Sequence[Quadrilateral], width: int, height: int) -> List[TextRegion]:
+def dispatch(textlines: Sequence[Quadrilateral], width: int, height: int, engine=None) -> List[TextRegion]:
     total_area = sum(q.area for q in textlines)
     out: List[TextRegion] = []
-    for members, fg, bg, direction in merge_text_regions(textlines, width, height):
+    for members, fg, bg, direction in merge_text_regions(textlines, width, height, engine):
         lines = [textlines[i] for i in members]
         logp = sum(np.log(q.prob) * q.area for q in lines) / total_area      # normalised by the area of ALL lines, as the reference
         angle = float(np.rad2deg(np.mean([q.angle for q in lines])) - 90)

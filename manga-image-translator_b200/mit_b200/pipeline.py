@@ -87,7 +87,7 @@ class HotPath:
         from .host import textline_merge
         textlines, raw_mask, _ = asyncio.run(self.det.infer(page, self.detect_size, 0.5, 0.7, 2.3))
         lines = asyncio.run(self.ocr.infer(page, textlines, OcrConfig(prob=ocr_prob))) if textlines else []
-        regions = textline_merge.dispatch(lines, page.shape[1], page.shape[0]) if lines else []
+        regions = textline_merge.dispatch(lines, page.shape[1], page.shape[0], engine=self.engine) if lines else []
         if not regions:
             return [], np.zeros(page.shape[:2], np.uint8), page.copy()
         mask = asyncio.run(mask_refinement.dispatch(regions, page, raw_mask, "fit_text", dilation_offset, 0, False, kernel_size,

@@ -163,6 +163,15 @@ class Model48pxCTCOCR(_InjectableWeights, OfflineOCR):
     async def _unload(self):
         self.engine.unload_ocr()
 
+    def _generate_text_direction(self, bboxes):
+        """CommonOCR._generate_text_direction (ocr/common.py:12-39) with the O(n^2) pair predicate on the device (SURVEY 8f N3);
+        MITB_HOST_PAIRS=1 keeps the host evaluation."""
+        from .host.geometry import generate_text_direction
+        eng = None if os.environ.get("MITB_HOST_PAIRS", "0") == "1" else getattr(self, "engine", None)
+        if eng is not None and not (hasattr(eng, "textline_pairs") and all(isinstance(b, Quadrilateral) for b in bboxes)):
+            eng = None
+        yield from generate_text_direction(bboxes, engine=eng)
+
     async def _infer(self, image: np.ndarray, textlines: List[Quadrilateral], config: OcrConfig, verbose: bool = False):
         text_height, max_chunk_size = 48, 16
         ignore_bubble = getattr(config, "ignore_bubble", 0)

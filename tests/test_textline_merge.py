@@ -39,3 +39,44 @@ def test_merge_region_fields_and_ordering():
     assert block.fg_color == (10, 0, 0) and block.bg_color == (255, 255, 250)
     assert 0 < block.prob <= 1 and by_size[1].direction == "v"
     assert textline_merge.dispatch([], 10, 10) == []
+
+
+@pytest.mark.gpu
+def test_device_pair_predicate_equals_host():
+    """SURVEY 8f N3 on the device: mitb_op_textline_pairs against the host `can_merge_region` (the port the known-answer tests above
+    pin) for EVERY pair of lines of every reference case, under both parameter sets in use (OCR direction graph, text-line merge), and
+    on rotated random quads; then the whole merge with the device predicate reproduces the host's (= the reference's) regions."""
+    import itertools
+    from mit_b200.engine import get_engine
+    from mit_b200.host import geometry
+    eng = get_engine("cuda:0")
+    rng = np.random.default_rng(8)
+    sets = [[Quadrilateral(np.array(l), "", 1.0) for l in c["lines"]] for c in CASES]
+    rnd = []
+    for t in range(80):                                       # clustered so that many pairs pass the distance gates
+        cx, cy = rng.uniform(200, 500), rng.uniform(200, 500)
+        ww, hh = rng.uniform(30, 200), rng.uniform(12, 40)
+        if t % 3 == 0:
+            ww, hh = hh, ww
+        ang = rng.uniform(-0.5, 0.5) if t % 2 else 0.0
+        c, s = np.cos(ang), np.sin(ang)
+        pts = np.array([[-ww / 2, -hh / 2], [ww / 2, -hh / 2], [ww / 2, hh / 2], [-ww / 2, hh / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]
+        rnd.append(Quadrilateral(pts.astype(np.int64), "", 1.0))
+    sets.append(rnd)
+    sets.append([Quadrilateral(np.array([[0, 0], [100, 0], [30, 10], [0, 40]]), "", 1.0), rnd[0], rnd[1]])      # a non-convex quad
+    n_true = n_pairs = 0
+    for quads in sets:
+        for params in (dict(aspect_ratio_tol=1), dict(aspect_ratio_tol=1.3, font_size_ratio_tol=2, char_gap_tolerance=1, char_gap_tolerance2=3)):
+            got = geometry.can_merge_matrix(quads, eng, **params)
+            for u, v in itertools.combinations(range(len(quads)), 2):
+                want = geometry.can_merge_region(quads[u], quads[v], **params)
+                assert bool(got[u, v]) == bool(want) == bool(got[v, u]), (u, v, params)
+                n_true += bool(want)
+                n_pairs += 1
+    print(f"pair predicate: {n_pairs} pairs, {n_true} mergeable, device == host")
+    assert n_true > 50 and n_pairs > 3000
+    for case in CASES:
+        quads = [Quadrilateral(np.array(l), "", 1) for l in case["lines"]]
+        regions = textline_merge.dispatch(quads, case["width"], case["height"], engine=eng)
+        assert {tuple(sorted(r.line_indices)) for r in regions} == {tuple(c) for c in case["expected"]}
+    assert [d for _, d in geometry.generate_text_direction(rnd, engine=eng)] == [d for _, d in geometry.generate_text_direction(rnd)]
