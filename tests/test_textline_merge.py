@@ -80,3 +80,38 @@ def test_device_pair_predicate_equals_host():
         regions = textline_merge.dispatch(quads, case["width"], case["height"], engine=eng)
         assert {tuple(sorted(r.line_indices)) for r in regions} == {tuple(c) for c in case["expected"]}
     assert [d for _, d in geometry.generate_text_direction(rnd, engine=eng)] == [d for _, d in geometry.generate_text_direction(rnd)]
+
+
+def test_pair_matrix_glue_with_a_fake_engine():
+    """Host side of the device pair predicate (no GPU): the feature records, the undecided-pair fallback (value 2 for a non-convex
+    quad) and the graph built from the matrix give the same regions as the all-host path."""
+    import itertools
+    from mit_b200.host import geometry
+
+    class Fake:
+        def __init__(self, quads):
+            self.q, self.asked = quads, 0
+
+        def textline_pairs(self, feat, params):
+            assert feat.shape == (len(self.q), 16) and feat.dtype == np.float64
+            n = len(self.q)
+            adj = np.zeros((n, n), np.uint8)
+            for u, v in itertools.combinations(range(n), 2):
+                if not (int(feat[u, 15]) & 2 and int(feat[v, 15]) & 2):
+                    adj[u, v] = adj[v, u] = 2                                      # what the kernel reports for a non-convex quad
+                    self.asked += 1
+                else:
+                    adj[u, v] = adj[v, u] = 1 if geometry.can_merge_region(self.q[u], self.q[v], *params) else 0
+            return adj
+
+    case = CASES[0]
+    quads = [Quadrilateral(np.array(l), "", 1) for l in case["lines"]]
+    quads.append(Quadrilateral(np.array([[0, 0], [100, 0], [30, 10], [0, 40]]), "", 1))      # non-convex: decided on the host
+    fake = Fake(quads)
+    f = geometry.pair_features(quads)
+    assert int(f[-1, 15]) & 2 == 0 and all(int(v) & 2 for v in f[:-1, 15])
+    assert np.array_equal(f[0, :8], np.asarray(quads[0].pts, float).reshape(-1)) and f[0, 12] == quads[0].font_size
+    with_dev = textline_merge.dispatch(quads, case["width"], case["height"], engine=fake)
+    host = textline_merge.dispatch(quads, case["width"], case["height"])
+    assert [r.line_indices for r in with_dev] == [r.line_indices for r in host] and fake.asked == len(quads) - 1
+    assert [d for _, d in geometry.generate_text_direction(quads, engine=fake)] == [d for _, d in geometry.generate_text_direction(quads)]
