@@ -15,6 +15,10 @@ Two third-party dependencies of that code are absent from this image and from /r
   d+1 axes with (1/2, 1, 1/2), slice with alpha = 1 / (1 + 2^-d); Potts compatibility; mean field Q <- softmax(-U + sum_k w_k K_k Q).
   **Parity unpinned**: no run of the real library is possible here, so tests can only check this restatement against closed-form
   properties and the CUDA path against this restatement.
+
+Pinned part: tests/test_mask_refine.py::test_oracle_dispatch_equals_reference_code_with_restated_dependencies runs the reference's own,
+unmodified mask_refinement package (from /root/reference) with shapely / pydensecrf bound to the restatements below and requires
+`dispatch` here to return the same mask bit for bit - so everything outside those two libraries is pinned on the reference's code.
 """
 import math
 
