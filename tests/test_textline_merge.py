@@ -115,3 +115,57 @@ def test_pair_matrix_glue_with_a_fake_engine():
     host = textline_merge.dispatch(quads, case["width"], case["height"])
     assert [r.line_indices for r in with_dev] == [r.line_indices for r in host] and fake.asked == len(quads) - 1
     assert [d for _, d in geometry.generate_text_direction(quads, engine=fake)] == [d for _, d in geometry.generate_text_direction(quads)]
+
+
+def test_merge_predicate_equals_reference_code():
+    """`host.geometry.can_merge_region` against the reference's own `quadrilateral_can_merge_region` (utils/generic.py:653-698), executed
+    unmodified with shapely's Polygon bound to our polygon-distance restatement: every pair of every known-answer case and of a set of
+    rotated random quads, under both parameter sets in use.  Pins the rule cascade and its numpy scalar-type semantics (the distance
+    function itself is the restated part)."""
+    import itertools
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("/root/reference not present")
+    import warnings
+    warnings.filterwarnings("ignore")
+    from mit_b200.host import geometry
+    U = refload.load()["utils"]
+    G = __import__("manga_translator.utils.generic", fromlist=["x"])
+
+    class Polygon:
+        def __init__(self, pts):
+            self.p = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+
+        def distance(self, other):
+            return geometry.polygon_distance(self.p, other.p)
+
+    saved = G.Polygon
+    G.Polygon = Polygon
+    try:
+        rng = np.random.default_rng(8)
+        sets = [[np.array(l) for l in c["lines"]] for c in CASES]
+        rnd = []
+        for t in range(60):
+            cx, cy = rng.uniform(200, 500), rng.uniform(200, 500)
+            ww, hh = rng.uniform(30, 200), rng.uniform(12, 40)
+            if t % 3 == 0:
+                ww, hh = hh, ww
+            ang = rng.uniform(-0.5, 0.5) if t % 2 else 0.0
+            c, s = np.cos(ang), np.sin(ang)
+            rnd.append((np.array([[-ww / 2, -hh / 2], [ww / 2, -hh / 2], [ww / 2, hh / 2], [-ww / 2, hh / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]).astype(np.int64))
+        sets.append(rnd)
+        n_true = n_pairs = 0
+        for pts_list in sets:
+            mine = [Quadrilateral(p, "", 1.0) for p in pts_list]
+            ref = [U.Quadrilateral(p, "", 1.0) for p in pts_list]
+            for r, m in zip(ref, mine):                       # the angled branch asks Quadrilateral.poly_distance (hull polygons)
+                r.__dict__["polygon"] = Polygon(geometry._hull(m.pts))
+            for params in (dict(aspect_ratio_tol=1), dict(aspect_ratio_tol=1.3, font_size_ratio_tol=2, char_gap_tolerance=1, char_gap_tolerance2=3)):
+                for u, v in itertools.combinations(range(len(mine)), 2):
+                    want = bool(G.quadrilateral_can_merge_region(ref[u], ref[v], **params))
+                    assert bool(geometry.can_merge_region(mine[u], mine[v], **params)) == want, (u, v, params)
+                    n_true += want
+                    n_pairs += 1
+        assert n_true > 50 and n_pairs > 3000
+    finally:
+        G.Polygon = saved
