@@ -169,3 +169,81 @@ def test_merge_predicate_equals_reference_code():
         assert n_true > 50 and n_pairs > 3000
     finally:
         G.Polygon = saved
+
+
+def test_regions_and_direction_graph_equal_reference_code_on_random_pages():
+    """Beyond the 11 known-answer cases: the reference's own `merge_bboxes_text_region` (textline_merge/__init__.py:110-181) and
+    `CommonOCR._generate_text_direction` (ocr/common.py:12-39), executed unmodified with shapely bound to our geometry restatements, against
+    `host.textline_merge.merge_text_regions` / `host.geometry.generate_text_direction` on random clustered pages of rotated lines."""
+    import importlib.util
+    import sys
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("/root/reference not present")
+    import warnings
+    warnings.filterwarnings("ignore")
+    from mit_b200.host import geometry
+    U = refload.load()["utils"]
+    G = __import__("manga_translator.utils.generic", fromlist=["x"])
+    common = sys.modules["manga_translator.ocr.common"]
+
+    class Polygon:
+        def __init__(self, pts):
+            self.p = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+
+        @property
+        def area(self):
+            return geometry.polygon_area(self.p)
+
+        @property
+        def convex_hull(self):
+            return Polygon(geometry._hull(self.p))
+
+        def distance(self, other):
+            return geometry.polygon_distance(self.p, other.p)
+
+    class MultiPoint(Polygon):
+        pass
+
+    path = os.path.join(refload.REF_ROOT, "manga_translator", "textline_merge", "__init__.py")
+    spec = importlib.util.spec_from_file_location("manga_translator.textline_merge", path, submodule_search_locations=[os.path.dirname(path)])
+    ref_merge = importlib.util.module_from_spec(spec)
+    sys.modules["manga_translator.textline_merge"] = ref_merge
+    spec.loader.exec_module(ref_merge)
+    saved = (G.Polygon, G.MultiPoint, ref_merge.Polygon)
+    G.Polygon, G.MultiPoint, ref_merge.Polygon = Polygon, MultiPoint, Polygon
+    try:
+        rng = np.random.default_rng(21)
+        n_regions = 0
+        for page in range(12):
+            pts_list = []
+            for blk in range(int(rng.integers(2, 5))):           # a few "speech bubbles" of stacked lines + stray lines
+                bx, by = rng.uniform(100, 900), rng.uniform(100, 700)
+                vertical = rng.random() < 0.5
+                fs = rng.uniform(18, 40)
+                ang = rng.uniform(-0.12, 0.12) if rng.random() < 0.4 else 0.0
+                for k in range(int(rng.integers(1, 6))):
+                    ln = rng.uniform(60, 260)
+                    w, h = (fs, ln) if vertical else (ln, fs)
+                    cx, cy = (bx - k * fs * rng.uniform(1.05, 1.6), by + rng.uniform(-8, 8)) if vertical else (bx + rng.uniform(-8, 8), by + k * fs * rng.uniform(1.05, 1.6))
+                    c, s = np.cos(ang), np.sin(ang)
+                    pts_list.append((np.array([[-w / 2, -h / 2], [w / 2, -h / 2], [w / 2, h / 2], [-w / 2, h / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]).astype(np.int64))
+            cols = [tuple(int(v) for v in rng.integers(0, 256, 6)) for _ in pts_list]
+            mine = [Quadrilateral(p, f"t{i}", 0.9, *c) for i, (p, c) in enumerate(zip(pts_list, cols))]
+            ref = [U.Quadrilateral(p, f"t{i}", 0.9, *c) for i, (p, c) in enumerate(zip(pts_list, cols))]
+            for q in mine + ref:
+                q.assigned_direction = q.direction
+            want = [([ref.index(q) for q in tl], fg, bg) for tl, fg, bg in ref_merge.merge_bboxes_text_region(ref, 1000, 800)]
+            got = [(list(members), fg, bg) for members, fg, bg, _ in textline_merge.merge_text_regions(mine, 1000, 800)]
+            key = lambda r: tuple(sorted(r[0]))
+            assert sorted(map(key, got)) == sorted(map(key, want))                                       # same partition ...
+            assert sorted(got, key=key) == sorted(want, key=key), (page, got, want)                      # ... same reading order and colours
+            n_regions += len(want)
+            rd = [(ref.index(q), d) for q, d in common.CommonOCR._generate_text_direction(None, ref)]
+            md = [(mine.index(q), d) for q, d in geometry.generate_text_direction(mine)]
+            assert sorted(rd) == sorted(md)
+            # the order of whole groups follows networkx's component iteration in both; within a group it must agree
+            assert rd == md, (page, rd, md)
+        assert n_regions > 30
+    finally:
+        G.Polygon, G.MultiPoint, ref_merge.Polygon = saved
