@@ -94,3 +94,130 @@ def test_lama_odd_spectrum_sizes(ref):
     rel, direct = nets.mpe_tables(mask[0, 0].numpy())
     o = nets.lama_forward(sd, msd, img, mask, torch.from_numpy(rel)[None], torch.from_numpy(direct)[None])
     assert (r - o).abs().max() < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The three `_infer` glue paths: oracle/pipeline_ref.py (what the GPU plugin tests compare the product with) against the reference's own
+# `_infer` methods, executed unmodified on the CPU with a duck-typed `self` (constructing the plugin classes would need model
+# directories) and the absent third-party libraries bound to the repo's restatements (pyclipper -> Clipper 6.4.2 restatement, shapely ->
+# geometry restatements).  Closes the loop: reference `_infer` == pipeline_ref here, plugin == pipeline_ref on the GPU.
+def _bind_third_party(ref):
+    import importlib
+    import sys
+    from mit_b200.host import det_post, geometry
+    G = importlib.import_module("manga_translator.utils.generic")
+    du = importlib.import_module("manga_translator.detection.default_utils.dbnet_utils")
+
+    class _Offset:
+        def AddPath(self, box, jt, et):
+            self.box = box
+
+        def Execute(self, d):
+            return [det_post.clipper_offset_round(self.box, d)]
+
+    class Polygon:
+        def __init__(self, pts):
+            self.p = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+            self.area, self.length = geometry.polygon_area(self.p), geometry.polygon_perimeter(self.p)
+
+        @property
+        def convex_hull(self):
+            return Polygon(geometry._hull(self.p))
+
+        def distance(self, other):
+            return geometry.polygon_distance(self.p, other.p)
+
+    saved = (du.pyclipper, du.Polygon, G.Polygon, G.MultiPoint)
+    du.pyclipper = type("pc", (), dict(PyclipperOffset=_Offset, JT_ROUND=1, ET_CLOSEDPOLYGON=2))
+    du.Polygon = G.Polygon = G.MultiPoint = Polygon
+
+    def restore():
+        du.pyclipper, du.Polygon, G.Polygon, G.MultiPoint = saved
+    return restore
+
+
+def test_detector_infer_glue_equals_reference_code(ref):
+    import asyncio
+    import logging
+    import types
+    from mit_b200 import synth
+    from oracle import pipeline_ref
+    det = ref["det"]
+    sd = {k: v.clone() for k, v in weights.dbnet_weights().items()}
+    sd["conv_db.binarize.4.bias"] -= 1.0
+    net = det.DBNetConvNext().eval()
+    net.load_state_dict(sd)
+    det.MODEL = net
+    me = types.SimpleNamespace(device="cpu", logger=logging.getLogger("ref-det"), model=net)
+    restore = _bind_third_party(ref)
+    try:
+        for page, detect_size in ((synth.make_page(5, 512, 384, 6)[0], 512), (synth.make_page(4, 384, 384, 5)[0], 512)):   # pad path; upscale path
+            r_lines, r_mask, _ = asyncio.run(det.DBConvNextDetector._infer(me, page, detect_size, 0.5, 0.6, 2.3))
+            o_lines, o_mask, _, _ = pipeline_ref.detector_infer(sd, page, detect_size, 0.5, 0.6, 2.3)
+            assert len(r_lines) == len(o_lines) and len(r_lines) > 3
+            for a, b in zip(r_lines, o_lines):
+                assert np.array_equal(a.pts, b.pts) and a.prob == b.prob and a.direction == b.direction
+            assert r_mask.dtype == np.uint8 and np.array_equal(r_mask, o_mask)
+    finally:
+        restore()
+
+
+def test_ocr_infer_glue_equals_reference_code(ref):
+    import asyncio
+    import logging
+    import sys
+    import types
+    from mit_b200 import synth
+    from mit_b200.host import geometry
+    from oracle import pipeline_ref
+    V = cases.OCR_VOCAB_SMALL
+    dictionary = weights.synthetic_dictionary(V)
+    sd = weights.ocr_weights(V)
+    model = ref["ocr"].OCR(dictionary, 768).eval()
+    model.load_state_dict(sd, strict=False)
+    common = sys.modules["manga_translator.ocr.common"]
+    page, boxes, _ = synth.make_page(3, 512, 384, 6)
+    U = ref["utils"]
+    restore = _bind_third_party(ref)
+    try:
+        me = types.SimpleNamespace(device="cpu", use_gpu=False, logger=logging.getLogger("ref-ocr"), model=model)
+        me._generate_text_direction = lambda bboxes: common.CommonOCR._generate_text_direction(me, bboxes)
+        r_quads = [U.Quadrilateral(b.copy(), "", 1.0) for b in boxes]
+        cfg = types.SimpleNamespace(ignore_bubble=0, prob=0.0)
+        r_out = asyncio.run(ref["ocr"].Model48pxCTCOCR._infer(me, page, r_quads, cfg, False))
+        o_out = pipeline_ref.ocr_infer(sd, dictionary, page, [geometry.Quadrilateral(b.copy(), "", 1.0) for b in boxes], 0.0)
+        assert len(r_out) == len(o_out) >= 4
+        for a, b in zip(r_out, o_out):
+            assert np.array_equal(a.pts, b.pts) and a.text == b.text and len(a.text) > 0
+            assert abs(a.prob - b.prob) < 1e-4 * max(a.prob, 1e-30)            # the two fp32 network evaluations differ by ~1e-5 in log-probability
+            assert (a.fg_r, a.fg_g, a.fg_b, a.bg_r, a.bg_g, a.bg_b) == (b.fg_r, b.fg_g, b.fg_b, b.bg_r, b.bg_g, b.bg_b)
+    finally:
+        restore()
+
+
+def test_inpainter_infer_glue_equals_reference_code(ref):
+    import asyncio
+    import logging
+    import types
+    from mit_b200 import synth
+    from oracle import pipeline_ref
+    lama = ref["lama"]
+    sd, msd = weights.lama_weights(9), weights.mpe_weights()
+    lf = lama.LamaFourier(build_discriminator=False, use_mpe=True)
+    lf.generator.load_state_dict(sd)
+    lf.mpe.load_state_dict(msd)
+    lf.eval()
+    me = types.SimpleNamespace(device="cpu", logger=logging.getLogger("ref-inp"), model=lf)
+    rng = np.random.default_rng(6)
+    page = rng.integers(0, 256, (200, 152, 3), dtype=np.uint8)
+    mask = np.zeros((200, 152), np.uint8)
+    mask[20:50, 10:120] = 255
+    mask[120:180, 60:90] = 255
+    mask[100:104, 5:40] = 130
+    mask[10, 10] = 127                                            # the 127 / 128 threshold quirk
+    for size in (1024, 128):                                      # no resize; keep-aspect resize + back
+        r = asyncio.run(lama.LamaMPEInpainter._infer(me, page.copy(), mask.copy(), types.SimpleNamespace(inpainting_precision="fp32"), size, False))
+        o, _ = pipeline_ref.lama_infer(sd, msd, page.copy(), mask.copy(), size)
+        assert r.dtype == o.dtype == np.uint8 and r.shape == page.shape
+        d = np.abs(r.astype(int) - o.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3, (int(d.max()), float((d > 0).mean()))     # x*255 truncation of fp32 values 2e-5 apart
