@@ -221,3 +221,76 @@ def test_inpainter_infer_glue_equals_reference_code(ref):
         assert r.dtype == o.dtype == np.uint8 and r.shape == page.shape
         d = np.abs(r.astype(int) - o.astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 1e-3, (int(d.max()), float((d > 0).mean()))     # x*255 truncation of fp32 values 2e-5 apart
+
+
+def test_common_detector_detect_equals_reference_code(ref):
+    """D12: the stand-in `CommonDetector.detect` of mit_b200.compat (border for small pages, rotation, inversion, gamma correction,
+    auto-rotation; used when the reference package cannot be imported) against the reference's own `detection/common.py` code, both
+    wrapped around the same stub `_detect`: identical text lines, raw mask and mask for every combination of the switches."""
+    import asyncio
+    import importlib
+    import itertools
+    import importlib.util
+    import sys
+    from mit_b200 import compat as _compat_loaded
+    from mit_b200.host import geometry
+    rc = importlib.import_module("manga_translator.detection.common")
+    # a second copy of mit_b200/compat.py imported while `manga_translator` is hidden: that is the stand-in the GPU box gets
+    hidden = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "manga_translator" or k.startswith("manga_translator.")}
+    sys.modules["manga_translator"] = None                       # makes `import manga_translator...` raise ImportError
+    try:
+        spec = importlib.util.spec_from_file_location("mit_b200._compat_standin", _compat_loaded.__file__)
+        compat = importlib.util.module_from_spec(spec)
+        sys.modules["mit_b200._compat_standin"] = compat
+        spec.loader.exec_module(compat)
+    finally:
+        del sys.modules["manga_translator"]
+        sys.modules.update(hidden)
+    assert not compat.HAVE_REFERENCE
+    U = ref["utils"]
+    restore = _bind_third_party(ref)
+
+    def stub(quad_cls):
+        async def _detect(self, image, detect_size, text_threshold, box_threshold, unclip_ratio, verbose=False):
+            self.seen.append(image.copy())
+            h, w = image.shape[:2]
+            rng = np.random.default_rng(h * 7919 + w)
+            lines = []
+            for _ in range(6):
+                x0, y0 = int(rng.integers(0, w - 40)), int(rng.integers(0, h - 40))
+                bw, bh = int(rng.integers(12, 120)), int(rng.integers(8, 60))
+                lines.append(quad_cls(np.array([[x0, y0], [x0 + bw, y0], [x0 + bw, y0 + bh], [x0, y0 + bh]]), "", 0.9))
+            lines.append(quad_cls(np.array([[5, 5], [6, 5], [6, 6], [5, 6]]), "", 0.5))          # area 1: filtered
+            raw = (rng.random((h, w)) * 255).astype(np.uint8)
+            return lines, raw, (rng.random((h, w)) > 0.5).astype(np.uint8) * 255
+        return _detect
+
+    class RefDet(rc.CommonDetector):
+        _detect = stub(U.Quadrilateral)
+
+    class OurDet(compat.OfflineDetector):
+        _detect = stub(geometry.Quadrilateral)
+
+        async def _load(self, device):
+            pass
+
+        async def _unload(self):
+            pass
+
+        async def _infer(self, *a, **k):
+            raise AssertionError("not used: `_detect` is stubbed")
+
+    try:
+        rng = np.random.default_rng(2)
+        for (h, w) in ((300, 200), (520, 450), (380, 700)):
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            for invert, gamma, rotate, auto in itertools.product((False, True), repeat=4):
+                r, o = RefDet(), OurDet()
+                r.seen, o.seen = [], []
+                rt, rraw, rmask = asyncio.run(r.detect(img.copy(), 1024, 0.5, 0.7, 2.3, invert, gamma, rotate, auto))
+                ot, oraw, omask = asyncio.run(o.detect(img.copy(), 1024, 0.5, 0.7, 2.3, invert, gamma, rotate, auto))
+                assert len(r.seen) == len(o.seen) and all(np.array_equal(a, b) for a, b in zip(r.seen, o.seen)), (h, w, invert, gamma, rotate, auto)
+                assert len(rt) == len(ot) and all(np.array_equal(a.pts, b.pts) for a, b in zip(rt, ot))
+                assert np.array_equal(rraw, oraw) and np.array_equal(rmask, omask)
+    finally:
+        restore()
