@@ -550,3 +550,26 @@ def test_warp_oracle_equals_cv2():
     assert n_px > 10 ** 6
     tab = warp_ref.bilinear_itab()
     assert tab[0].tolist() == [32767, 0, 0, 1] and (tab.sum(1) == 32768).all()
+
+
+def test_traffic_summary_tooling(tmp_path):
+    """tools/ncu_traffic.py on the committed ncu launch list (sparse conv launches separated from the dense class, every launch
+    classified) and bench.latest_traffic_summary (natural version order, summary of the current CUDA sources preferred)."""
+    import importlib.util
+    import json as _json
+    import bench
+    spec = importlib.util.spec_from_file_location("ncu_traffic", os.path.join(ROOT, "tools", "ncu_traffic.py"))
+    nt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nt)
+    src = os.path.join(ROOT, "profiles", "r02_ncu_launches_v17_1page.csv")
+    dst = tmp_path / "t.json"
+    nt.main(src, str(dst))
+    doc = _json.load(open(dst))
+    cls = doc["classes"]
+    assert cls["conv_tc_sparse"]["launches"] == 27 and cls["conv_tc"]["launches"] > 450           # 12 sparse convs + 12 tile maps + 3 splits
+    assert abs(doc["conv_class_dram_bytes_per_page"] - cls["conv_tc"]["dram_bytes"]) < 1 and 30e9 < cls["conv_tc"]["dram_bytes"] < 45e9
+    assert abs(sum(c["share_of_time"] for c in cls.values()) - 1.0) < 1e-9 and cls.get("other", {"launches": 0})["launches"] < 20
+    d, name = bench.latest_traffic_summary()
+    assert name.startswith("r02_ncu_traffic_v") and int(re.search(r"_v(\d+)", name).group(1)) >= 17
+    committed = _json.load(open(os.path.join(ROOT, "profiles", name)))
+    assert committed["csrc_sha"] == bench.csrc_hash(), "profiles/*_ncu_traffic_*.json was not regenerated for the current CUDA sources"
